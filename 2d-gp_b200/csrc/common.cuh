@@ -1,0 +1,91 @@
+// Shared device helpers for the gp2d sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gp2d {
+
+constexpr int TILE = 128;      // every internal matrix dimension is padded to a multiple of this
+constexpr int BK = 16;         // k-depth of one shared-memory stage (doubles)
+constexpr int NTHREADS = 256;  // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
+constexpr int TILE_DOUBLES = TILE * BK;   // 2048 doubles = 16 KB per operand stage
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- cp.async (LDGSTS) -------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- FP64 tensor pipe: DMMA.8x8x4 (the only native f64 MMA shape on sm_100a) --------
+// A 8x4 row-major fragment: lane holds A[lane>>2][lane&3]
+// B 4x8 col-major fragment: lane holds B[lane&3][lane>>2]
+// C 8x8: lane holds C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- shared-memory operand tiles -----------------------------------------------------
+// K-major tile  : T[128 rows(m or n)][16 k]   (element (r,k)); 16-byte chunk index k>>1 is
+//                 XOR-swizzled with ((r&3)<<1) so the 4 rows x 4 k of a half-warp fragment
+//                 read hit 16 distinct 8-byte bank pairs.
+// MN-major tile : T[16 k][128 (m or n)]       (element (k,r)); chunk index r>>1 is swizzled
+//                 with ((k&3)<<1).
+__device__ __forceinline__ int kmaj_off(int r, int k) {
+    return r * BK + ((((k >> 1) ^ ((r & 3) << 1)) << 1) | (k & 1));
+}
+__device__ __forceinline__ int mnmaj_off(int k, int r) {
+    return k * TILE + ((((r >> 1) ^ ((k & 3) << 1)) << 1) | (r & 1));
+}
+
+// Load one 128x16 operand tile with 16-byte cp.async, 4 chunks per thread.
+// KMAJ: global element (r,k) at g[r*ld + k];  MN-major: global element (k,r) at g[k*ld + r].
+template <bool MNMAJ>
+__device__ __forceinline__ void load_tile_async(double* smem, const double* g, long ld, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        int q = tid + it * NTHREADS;
+        if (!MNMAJ) {
+            int r = q >> 3, ch = q & 7;
+            cp_async16(smem + r * BK + ((ch ^ ((r & 3) << 1)) << 1), g + (long)r * ld + (ch << 1));
+        } else {
+            int k = q >> 6, ch = q & 63;
+            cp_async16(smem + k * TILE + ((ch ^ ((k & 3) << 1)) << 1), g + (long)k * ld + (ch << 1));
+        }
+    }
+}
+
+// One BK=16 stage of DMMAs for a 64x32 warp tile.  acc[mb][nb][2].
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void mma_stage(const double* As, const double* Bs, int wm, int wn,
+                                          int lane, double (&acc)[8][4][2]) {
+    const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+        double a[8], b[4];
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) {
+            int m = wm * 64 + mb * 8 + g;
+            a[mb] = A_MN ? As[mnmaj_off(kk + tig, m)] : As[kmaj_off(m, kk + tig)];
+        }
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            int n = wn * 32 + nb * 8 + g;
+            b[nb] = B_MN ? Bs[mnmaj_off(kk + tig, n)] : Bs[kmaj_off(n, kk + tig)];
+        }
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+    }
+}
+
+}  // namespace gp2d

@@ -1,0 +1,258 @@
+"""fp64 numpy/scipy restatement of the reference's GP hot path.  TEST INFRASTRUCTURE.
+
+Every function cites the reference lines it restates (paths relative to the
+upstream repo rafaelcgon/2D-GP).  Nothing here is imported by the product
+package; see ``oracle/__init__.py`` for who may call it and for the pinning
+status of each part.
+
+Conventions:
+  * X is [N,2] (x, y) in km; y is the stacked observation vector [u; v] of
+    length 2N (GP_laser.py:98,174; GP_plots.py:721-722).
+  * Covariances use the reference's component-major block layout: row c*N+i,
+    column c'*M+j (myKernel.py:40-43; GP_scripts.py:89-95).
+  * theta = (l_df, l_cf, ratio); noise is the Gaussian noise *variance*.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+__all__ = [
+    "helmholtz_K", "helmholtz_Kdiag", "helmholtz_dK", "kernel_grad_sums",
+    "fit", "predict", "lml", "lml_and_grad", "fit_predict_inverse_form",
+    "haversine_km", "simlaser_inputs", "rbf_ard_K", "LOG_2PI",
+]
+
+LOG_2PI = math.log(2.0 * math.pi)
+
+
+# --------------------------------------------------------------------------------------
+# kernel
+# --------------------------------------------------------------------------------------
+def _pair_terms(X, X2):
+    """dx1, dx2 and the outer-product terms (myKernel.py:30-35)."""
+    X = np.asarray(X, dtype=np.float64)
+    X2 = X if X2 is None else np.asarray(X2, dtype=np.float64)
+    dx1 = X[:, 0][:, None] - X2[:, 0]
+    dx2 = X[:, 1][:, None] - X2[:, 1]
+    return dx1, dx2, dx1 * dx1, dx1 * dx2, dx2 * dx2
+
+
+def _blk(a11, a12, a21, a22):
+    """2x2 block stacking used throughout the reference (myKernel.py:40-41)."""
+    return np.concatenate([np.concatenate([a11, a12], axis=1),
+                           np.concatenate([a21, a22], axis=1)], axis=0)
+
+
+def helmholtz_K(X, X2, l_df, l_cf, ratio):
+    """ratio*K_divfree + (1-ratio)*K_curlfree, [2N,2M].
+
+    Restates myKernel.myKernel.K (myKernel.py:27-53), identical to
+    GP_scripts.myKernel (GP_scripts.py:6-42).  ratio=1 gives nonDivK.K
+    (myKernel.py:159-176), ratio=0 gives nonRotK.K (myKernel.py:255-271).
+    """
+    dx1, dx2, B11, B12, B22 = _pair_terms(X, X2)
+    # the reference takes sqrt then squares (myKernel.py:35,38); kept for rounding parity
+    norm = np.sqrt(np.square(dx1) + np.square(dx2))
+    rdf2 = l_df * l_df
+    Cdf = np.square(norm / l_df)
+    aux = 1.0 - Cdf                                    # (p-1) - C with p = 2
+    Adf = _blk(B11 / rdf2 + aux, B12 / rdf2, B12 / rdf2, B22 / rdf2 + aux)
+    Kdf = np.square(1.0 / l_df) * np.exp(-_blk(Cdf, Cdf, Cdf, Cdf) / 2.0) * Adf
+    rcf2 = l_cf * l_cf
+    Ccf = np.square(norm / l_cf)
+    Acf = _blk(1.0 - B11 / rcf2, -B12 / rcf2, -B12 / rcf2, 1.0 - B22 / rcf2)
+    Kcf = np.square(1.0 / l_cf) * np.exp(-_blk(Ccf, Ccf, Ccf, Ccf) / 2.0) * Acf
+    return ratio * Kdf + (1.0 - ratio) * Kcf
+
+
+def helmholtz_Kdiag(M, l_df, l_cf, ratio):
+    """Prior variance replicated 2M times (myKernel.py:55-57; M = X.shape[0])."""
+    var = ratio * (1.0 / l_df ** 2) + (1.0 - ratio) * (1.0 / l_cf ** 2)
+    return np.ones(2 * int(M)) * var
+
+
+def helmholtz_dK(X, X2, l_df, l_cf, ratio, reference_compat=False):
+    """(dK/dl_df, dK/dl_cf, dK/dratio), each [2N,2M].
+
+    reference_compat=True reproduces myKernel.update_gradients_full's integrands
+    verbatim (myKernel.py:77-81, 91-96, 99-102), including its wrong length-scale
+    terms.  reference_compat=False is the analytically correct derivative
+    (SURVEY.md §8(a) row G), checked against central differences in the tests.
+    """
+    dx1, dx2, B11, B12, B22 = _pair_terms(X, X2)
+    r2 = np.square(dx1) + np.square(dx2)
+    out = []
+    for which, l, w in (("df", l_df, ratio), ("cf", l_cf, 1.0 - ratio)):
+        l2, l3, l5 = l * l, l ** 3, l ** 5
+        C = r2 / l2
+        if which == "df":
+            A = _blk(B11 / l2 + 1.0 - C, B12 / l2, B12 / l2, B22 / l2 + 1.0 - C)
+            G = _blk(r2 - B11, -B12, -B12, r2 - B22)        # r^2 I - B
+        else:
+            A = _blk(1.0 - B11 / l2, -B12 / l2, -B12 / l2, 1.0 - B22 / l2)
+            G = _blk(B11, B12, B12, B22)                    # B
+        C4 = _blk(C, C, C, C)
+        E = np.exp(-C4 / 2.0)
+        if reference_compat:
+            # myKernel.py:81 / :96   dAdf + Adf*(2*l2 - C*l2)/l5
+            d = w * E * ((2.0 / l3) * G + A * (2.0 * l2 - C4 * l2) / l5)
+        else:
+            d = w * E * ((C4 - 2.0) / l3 * A + (2.0 / l5) * G)
+        out.append(d)
+    Kdf = helmholtz_K(X, X2, l_df, l_cf, 1.0)
+    Kcf = helmholtz_K(X, X2, l_df, l_cf, 0.0)
+    out.append(Kdf - Kcf)                                   # myKernel.py:99-102
+    return tuple(out)
+
+
+def kernel_grad_sums(dL_dK, X, X2, l_df, l_cf, ratio, reference_compat=False):
+    """What update_gradients_full stores in .gradient: sum(dK/dtheta * dL_dK)
+    for (length_df, length_cf, ratio)  (myKernel.py:104-106)."""
+    d = helmholtz_dK(X, X2, l_df, l_cf, ratio, reference_compat)
+    return np.array([np.sum(di * dL_dK) for di in d])
+
+
+def rbf_ard_K(X, X2, variance, lengthscales):
+    """variance * exp(-0.5 * sum_d (dx_d/l_d)^2): the scalar ARD-RBF of
+    krig.py:174 (sklearn ``HP[0]*RBF(length_scale=[...])``) / krig.py:388."""
+    X = np.asarray(X, dtype=np.float64)
+    X2 = X if X2 is None else np.asarray(X2, dtype=np.float64)
+    ls = np.asarray(lengthscales, dtype=np.float64)
+    a = X / ls
+    b = X2 / ls
+    d2 = np.zeros((X.shape[0], X2.shape[0]))
+    for k in range(X.shape[1]):                 # elementwise differences: no cancellation
+        diff = a[:, k][:, None] - b[:, k][None, :]
+        d2 += diff * diff
+    return variance * np.exp(-0.5 * d2)
+
+
+# --------------------------------------------------------------------------------------
+# fit / predict / log marginal likelihood  (Rasmussen & Williams Alg. 2.1, the algebra of
+# sklearn _gpr.py:350-367,446-491,583-656 and of GPy's ExactGaussianInference)
+# --------------------------------------------------------------------------------------
+def fit(X, y, l_df, l_cf, ratio, noise, jitter=0.0):
+    """L = chol(K + (noise+jitter) I), alpha = K^-1 y, LML.
+
+    Reference call sites: GPy GPRegression(X,Y,k) at GP_plots.py:763, krig.py:411;
+    numpy K + noise*I at GP_laser.py:113-115,177-179; LML convention of
+    sklearn _gpr.py:613-615 (-0.5 y'alpha - sum log L_ii - n/2 log 2pi).
+    """
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = helmholtz_K(X, None, l_df, l_cf, ratio)
+    n = K.shape[0]
+    K[np.diag_indices(n)] += noise + jitter
+    L = sla.cholesky(K, lower=True, check_finite=False)
+    alpha = sla.cho_solve((L, True), y, check_finite=False)
+    val = -0.5 * float(y @ alpha) - float(np.sum(np.log(np.diag(L)))) - 0.5 * n * LOG_2PI
+    return {"L": L, "alpha": alpha, "lml": val}
+
+
+def lml(X, y, l_df, l_cf, ratio, noise, jitter=0.0):
+    return fit(X, y, l_df, l_cf, ratio, noise, jitter)["lml"]
+
+
+def predict(X, fitres, l_df, l_cf, ratio, Xs, noise=0.0, include_noise=False, chunk=4096):
+    """Posterior mean [2M] and marginal variance [2M] at Xs.
+
+    mean = K* alpha (sklearn _gpr.py:446-447; GP_scripts.getMean GP_scripts.py:44-46);
+    V = L^-1 K*^T, var = diag(K**) - colsumsq(V), negatives clamped to 0
+    (_gpr.py:460-462,480-491).  include_noise adds the Gaussian noise variance as
+    GPy's model.predict does (krig.py:543-544).  Outputs are component-major:
+    [:M] first component, [M:] second (GP_laser.py:184-185).
+    """
+    Xs = np.asarray(Xs, dtype=np.float64)
+    M = Xs.shape[0]
+    mean = np.empty(2 * M)
+    var = np.empty(2 * M)
+    kss = helmholtz_Kdiag(1, l_df, l_cf, ratio)[0]
+    L, alpha = fitres["L"], fitres["alpha"]
+    for s in range(0, M, chunk):
+        e = min(M, s + chunk)
+        Ks = helmholtz_K(Xs[s:e], X, l_df, l_cf, ratio)           # [2m, 2N] rows = grid
+        mu = Ks @ alpha
+        V = sla.solve_triangular(L, Ks.T, lower=True, check_finite=False)
+        v = kss - np.einsum("ij,ij->j", V, V)
+        m = e - s
+        mean[s:e], mean[M + s:M + e] = mu[:m], mu[m:]
+        var[s:e], var[M + s:M + e] = v[:m], v[m:]
+    var = np.where(var < 0.0, 0.0, var)
+    if include_noise:
+        var = var + noise
+    return mean, var
+
+
+def lml_and_grad(X, y, l_df, l_cf, ratio, noise, jitter=0.0, reference_compat=False):
+    """LML and d LML / d(l_df, l_cf, ratio, noise).
+
+    dL_dK = 0.5 (alpha alpha' - K^-1) (GPy ExactGaussianInference; sklearn
+    _gpr.py:629-654), kernel parameters through kernel_grad_sums
+    (myKernel.py:104-106), noise through trace(dL_dK).
+    """
+    f = fit(X, y, l_df, l_cf, ratio, noise, jitter)
+    L, alpha = f["L"], f["alpha"]
+    n = L.shape[0]
+    Kinv = sla.cho_solve((L, True), np.eye(n), check_finite=False)
+    dL_dK = 0.5 * (np.outer(alpha, alpha) - Kinv)
+    g = kernel_grad_sums(dL_dK, X, None, l_df, l_cf, ratio, reference_compat)
+    return f["lml"], np.concatenate([g, [np.trace(dL_dK)]])
+
+
+def fit_predict_inverse_form(X, y, l_df, l_cf, ratio, noise, Xs, ks_cf_weight=None,
+                             want_var=True):
+    """The reference's own numpy formulation (explicit inverse).
+
+    K = rate*K_df + (1-rate)*K_cf + noise*I; Ki = inv(K)  (GP_laser.py:113-118,177-180)
+    Ks = K(X*, X)                                         (GP_laser.py:122,181)
+    mean = Ks Ki y                                        (GP_scripts.py:44-46)
+    Cov  = Kss - Ks Ki Ks^T, only its diagonal kept       (GP_laser.py:128-131)
+    ks_cf_weight overrides the curl-free weight in K* only: simLaser uses
+    (1-rate)*rate there (GP_laser.py:181, a reference defect).
+    """
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = helmholtz_K(X, None, l_df, l_cf, ratio)
+    K = K + np.identity(K.shape[0]) * noise
+    Ki = np.linalg.inv(K)
+    if ks_cf_weight is None:
+        Ks = helmholtz_K(Xs, X, l_df, l_cf, ratio)
+    else:
+        Ks = (ratio * helmholtz_K(Xs, X, l_df, l_cf, 1.0)
+              + ks_cf_weight * helmholtz_K(Xs, X, l_df, l_cf, 0.0))
+    mean = np.reshape(np.dot(Ks, np.dot(Ki, y)), [-1])
+    if not want_var:
+        return mean, None
+    kss = helmholtz_Kdiag(1, l_df, l_cf, ratio)[0]
+    var = kss - np.einsum("ij,ij->i", Ks @ Ki, Ks)
+    return mean, var
+
+
+# --------------------------------------------------------------------------------------
+# config-1 data preparation (host side; GP_laser.py:147-175)
+# --------------------------------------------------------------------------------------
+def haversine_km(lat1, lon1, lat2, lon2, radius_km=6371.009):
+    """Great-circle distance on a sphere of geopy's default radius; stands in for
+    geopy.distance.GreatCircleDistance(...).km (GP_laser.py:166-167), geopy absent."""
+    p1, p2 = np.radians(lat1), np.radians(lat2)
+    dphi = p2 - p1
+    dlmb = np.radians(np.asarray(lon2) - np.asarray(lon1))
+    a = np.sin(dphi / 2.0) ** 2 + np.cos(p1) * np.cos(p2) * np.sin(dlmb / 2.0) ** 2
+    return 2.0 * radius_km * np.arcsin(np.sqrt(a))
+
+
+def simlaser_inputs(tr, ts=0, lat0=28.69, lon0=-88.28, dx=0.5):
+    """Observation coordinates/velocities and the 51x51 grid of GP_laser.simLaser
+    (GP_laser.py:147-175).  Distances are unsigned, like the reference's."""
+    lat = np.asarray(tr.lat)[:, ts]
+    lon = np.asarray(tr.lon)[:, ts]
+    xo = haversine_km(lat, lon, lat, np.full_like(lon, lon0))
+    yo = haversine_km(lat, lon, np.full_like(lat, lat0), lon)
+    uo = np.asarray(tr.u)[:, ts]
+    vo = np.asarray(tr.v)[:, ts]
+    x = np.arange(0, 25 + dx, dx)
+    yv = np.arange(0, 25 + dx, dx)
+    Xg, Yg = np.meshgrid(x, yv)
+    Xs = np.stack([Xg.reshape(-1), Yg.reshape(-1)], axis=1)
+    return np.stack([xo, yo], axis=1), np.concatenate([uo, vo]), Xs

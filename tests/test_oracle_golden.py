@@ -1,0 +1,157 @@
+"""Pin the oracle (oracle/gp_oracle.py) against vectors produced by the reference's own
+code (tests/golden/make_golden.py runs verbatim slices of the reference).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from oracle import ref_slices as rs
+
+
+@pytest.fixture(scope="module")
+def ks(golden_dir):
+    return np.load(os.path.join(golden_dir, "kernel_small.npz"))
+
+
+def test_kernel_matches_three_reference_implementations(ks):
+    X, X2 = ks["X"], ks["X2"]
+    for t, (ldf, lcf, r) in enumerate(ks["thetas"]):
+        K_sym = orc.helmholtz_K(X, None, ldf, lcf, r)
+        K_x = orc.helmholtz_K(X, X2, ldf, lcf, r)
+        # class form myKernel.py:27-53, function form GP_scripts.py:6-42, loops GP_scripts.py:57-123
+        np.testing.assert_allclose(K_sym, ks["ref_K_class_sym_%d" % t], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(K_x, ks["ref_K_class_x_%d" % t], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(K_x, ks["ref_K_func_x_%d" % t], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(K_sym, ks["ref_K_loops_sym_%d" % t], rtol=0, atol=2e-15)
+        # compute_Ks is K(X*, X): rows = grid
+        np.testing.assert_allclose(orc.helmholtz_K(X2, X, ldf, lcf, r), ks["ref_Ks_loops_%d" % t],
+                                   rtol=0, atol=2e-15)
+        np.testing.assert_array_equal(orc.helmholtz_Kdiag(X2.shape[0], ldf, lcf, r),
+                                      ks["ref_Kdiag_%d" % t])
+
+
+def test_single_component_kernels(ks):
+    X, X2 = ks["X"], ks["X2"]
+    np.testing.assert_allclose(orc.helmholtz_K(X, X2, 1.7, 1.0, 1.0), ks["ref_nonDivK"], atol=1e-15)
+    np.testing.assert_allclose(orc.helmholtz_K(X, X2, 1.0, 0.9, 0.0), ks["ref_nonRotK"], atol=1e-15)
+    np.testing.assert_allclose(orc.helmholtz_Kdiag(X2.shape[0], 1.7, 1.0, 1.0), ks["ref_nonDivK_diag"])
+    np.testing.assert_allclose(orc.helmholtz_Kdiag(X2.shape[0], 1.0, 0.9, 0.0), ks["ref_nonRotK_diag"])
+
+
+def test_compat_gradient_reproduces_reference(ks):
+    X, X2 = ks["X"], ks["X2"]
+    for t, (ldf, lcf, r) in enumerate(ks["thetas"]):
+        g = orc.kernel_grad_sums(ks["W_sym"], X, None, ldf, lcf, r, reference_compat=True)
+        np.testing.assert_allclose(g, ks["ref_grad_compat_sym_%d" % t], rtol=1e-12, atol=1e-13)
+        g = orc.kernel_grad_sums(ks["W_x"], X, X2, ldf, lcf, r, reference_compat=True)
+        np.testing.assert_allclose(g, ks["ref_grad_compat_x_%d" % t], rtol=1e-12, atol=1e-13)
+    g = orc.kernel_grad_sums(ks["W_x"], X, X2, 1.7, 1.0, 1.0, reference_compat=True)
+    np.testing.assert_allclose(g[0], ks["ref_nonDivK_grad_compat"][0], rtol=1e-12)
+    g = orc.kernel_grad_sums(ks["W_x"], X, X2, 1.0, 0.9, 0.0, reference_compat=True)
+    np.testing.assert_allclose(g[1], ks["ref_nonRotK_grad_compat"][0], rtol=1e-12)
+
+
+def test_correct_gradient_matches_central_differences(ks):
+    X, X2, W = ks["X"], ks["X2"], ks["W_x"]
+    h = 1e-6
+    for (ldf, lcf, r) in [(2.0, 2.0, 0.5), (1.3, 3.1, 0.2)]:
+        g = orc.kernel_grad_sums(W, X, X2, ldf, lcf, r)
+        f = lambda a, b, c: np.sum(orc.helmholtz_K(X, X2, a, b, c) * W)
+        fd = np.array([(f(ldf + h, lcf, r) - f(ldf - h, lcf, r)) / (2 * h),
+                       (f(ldf, lcf + h, r) - f(ldf, lcf - h, r)) / (2 * h),
+                       (f(ldf, lcf, r + h) - f(ldf, lcf, r - h)) / (2 * h)])
+        np.testing.assert_allclose(g, fd, rtol=1e-7, atol=1e-8)
+        # and the reference's formula is NOT the derivative
+        gc = orc.kernel_grad_sums(W, X, X2, ldf, lcf, r, reference_compat=True)
+        assert abs(gc[0] - fd[0]) > 1e-3 * abs(fd[0])
+        np.testing.assert_allclose(gc[2], fd[2], rtol=1e-7)
+
+
+def test_known_answers():
+    # K(0) = I / l^2; uu minimum -2 e^{-3/2} / l^2 at distance sqrt(3) l along y (div-free)
+    l = 0.2
+    K0 = orc.helmholtz_K(np.zeros((1, 2)), None, l, l, 1.0)
+    np.testing.assert_allclose(K0, np.eye(2) / l ** 2)
+    Xa = np.zeros((1, 2))
+    Xb = np.array([[0.0, np.sqrt(3.0) * l]])
+    Kdf = orc.helmholtz_K(Xa, Xb, l, l, 1.0)
+    np.testing.assert_allclose(Kdf[0, 0], -2 * np.exp(-1.5) / l ** 2, rtol=1e-13)
+    Xb = np.array([[np.sqrt(3.0) * l, 0.0]])
+    Kcf = orc.helmholtz_K(Xa, Xb, l, l, 0.0)
+    np.testing.assert_allclose(Kcf[0, 0], -2 * np.exp(-1.5) / l ** 2, rtol=1e-13)
+    # uv sign: +d1 d2 (div-free), -d1 d2 (curl-free)
+    Xb = np.array([[0.1, 0.1]])
+    assert orc.helmholtz_K(Xa, Xb, l, l, 1.0)[0, 1] > 0
+    assert orc.helmholtz_K(Xa, Xb, l, l, 0.0)[0, 1] < 0
+
+
+@pytest.mark.parametrize("ts", [0, 100])
+def test_simlaser_pipeline(golden_dir, ts):
+    """Cholesky formulation (oracle.fit/predict) vs the reference's explicit-inverse numpy
+    pipeline run through the reference's own functions (GP_laser.py:177-185,128-131)."""
+    g = np.load(os.path.join(golden_dir, "simlaser_ts%d.npz" % ts))
+    X, y, Xs = g["X"], g["y"], g["Xs"]
+    ldf, lcf, r = g["theta"]
+    noise = float(g["noise"])
+    f = orc.fit(X, y, ldf, lcf, r, noise)
+    mean, var = orc.predict(X, f, ldf, lcf, r, Xs)
+    np.testing.assert_allclose(mean, g["ref_mean"], rtol=1e-8, atol=1e-10 * np.abs(g["ref_mean"]).max())
+    np.testing.assert_allclose(var, g["ref_var"], rtol=1e-8)
+    np.testing.assert_allclose(f["lml"], float(g["derived_lml"]), rtol=1e-12)
+    # the simLaser K* weighting defect (GP_laser.py:181) reproduced on request
+    m2, _ = orc.fit_predict_inverse_form(X, y, ldf, lcf, r, noise, Xs, ks_cf_weight=(1 - r) * r,
+                                         want_var=False)
+    np.testing.assert_allclose(m2, g["ref_mean_simlaser"], rtol=1e-9, atol=1e-12)
+    if ts == 0:
+        assert abs(f["lml"] - 317.0291777225) < 1e-9       # SURVEY.md §4 / BASELINE.md probe
+
+
+def test_lml_grad_vs_finite_differences(golden_dir):
+    g = np.load(os.path.join(golden_dir, "simlaser_ts0.npz"))
+    X, y = g["X"][:120], np.concatenate([g["y"][:120], g["y"][400:520]])
+    th = (1.3, 3.1, 0.2, 0.05)
+    val, grad = orc.lml_and_grad(X, y, *th)
+    h = 1e-6
+    for p in range(4):
+        a = list(th); b = list(th)
+        a[p] += h; b[p] -= h
+        fd = (orc.lml(X, y, *a) - orc.lml(X, y, *b)) / (2 * h)
+        np.testing.assert_allclose(grad[p], fd, rtol=2e-6, atol=1e-6)
+
+
+def test_generic_gp_algebra_vs_sklearn():
+    """The fit/predict/LML algebra is sklearn's (krig.py:174-194 call site); check the same
+    algebra on a scalar ARD-RBF + WhiteKernel against live scikit-learn."""
+    from sklearn.gaussian_process import GaussianProcessRegressor, kernels
+    import scipy.linalg as sla
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 10, size=(60, 3))
+    yv = np.sin(X[:, 0]) + 0.1 * rng.normal(size=60)
+    Xs = rng.uniform(0, 10, size=(25, 3))
+    var0, ls, noise = 1.7, [1.1, 2.3, 0.9], 0.03
+    k = var0 * kernels.RBF(length_scale=ls) + kernels.WhiteKernel(noise_level=noise)
+    m = GaussianProcessRegressor(kernel=k, optimizer=None, alpha=0.0).fit(X, yv)
+    mu_s, sd_s = m.predict(Xs, return_std=True)
+    K = orc.rbf_ard_K(X, None, var0, ls) + noise * np.eye(60)
+    L = sla.cholesky(K, lower=True)
+    alpha = sla.cho_solve((L, True), yv)
+    Ks = orc.rbf_ard_K(Xs, X, var0, ls)
+    V = sla.solve_triangular(L, Ks.T, lower=True)
+    var = var0 + noise - np.einsum("ij,ij->j", V, V)          # WhiteKernel is in sklearn's diag
+    np.testing.assert_allclose(Ks @ alpha, mu_s, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(np.sqrt(var), sd_s, rtol=1e-8)
+    lml = -0.5 * yv @ alpha - np.log(np.diag(L)).sum() - 30 * np.log(2 * np.pi)
+    np.testing.assert_allclose(lml, m.log_marginal_likelihood_value_, rtol=1e-10)
+
+
+@pytest.mark.skipif(not rs.available(), reason="reference tree not present (GPU box)")
+def test_live_reference_slices_agree_with_oracle():
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 5, size=(13, 2))
+    X2 = rng.uniform(0, 5, size=(7, 2))
+    k = rs.mykernel_class(1.1, 2.7, 0.35)
+    np.testing.assert_allclose(orc.helmholtz_K(X, X2, 1.1, 2.7, 0.35), k.K(X, X2), atol=1e-15)
+    gs = rs.gp_scripts()
+    np.testing.assert_allclose(orc.helmholtz_K(X, X2, 1.1, 2.7, 0.35),
+                               gs["myKernel"](X, X2, 1.1, 2.7, 0.35), atol=1e-15)
