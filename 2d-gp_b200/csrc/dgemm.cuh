@@ -1,0 +1,130 @@
+// FP64 GEMM on the DMMA tensor pipe for the blocked Cholesky / triangular inverse / K^-1.
+//
+//   C[M,N] = alpha * opA(A) * opB(B) + beta * C        (all row-major storage, ld in doubles)
+//
+// A operand: element (m,k) at A[m*lda + k] (K-major, "N") or A[k*lda + m] (MN-major, "T").
+// B operand: element (n,k) at B[n*ldb + k] (K-major, i.e. C = A * B^T) or
+//            B[k*ldb + n] (MN-major, i.e. C = A * B).
+// M, N are multiples of 128 and K of 16; triangular structure is exploited by clipping the
+// k-range per 128x128 output tile (KR_* flags) and by skipping tiles above the diagonal
+// (lower_out).  128x128x16 CTA tile, 4-stage cp.async pipeline, XOR-swizzled shared
+// memory, 8 warps x (64x32) DMMA.8x8x4 register tiles.
+#pragma once
+#include "common.cuh"
+
+namespace gp2d {
+
+enum : int {
+    KR_FULL = 0,
+    KR_LE_M = 1,   // k <  (tm+1)*128 : A operand lower-triangular in (m,k)
+    KR_LE_N = 2,   // k <  (tn+1)*128 : B operand lower-triangular in (n,k)  (Z^T as K-major B)
+    KR_GE_N = 4,   // k >= tn*128     : B operand (k,n) lower-triangular, zero for k < n
+    KR_GE_M = 8,   // k >= tm*128     : A operand (k,m) lower-triangular, zero for k < m
+};
+
+struct GemmArgs {
+    const double* A; long lda;
+    const double* B; long ldb;
+    double* C; long ldc;
+    int M, N, K;
+    double alpha, beta;
+    int lower_out;
+    int krule;
+};
+
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + GEMM_STAGES * TILE_DOUBLES;
+
+    int tm, tn;
+    if (p.lower_out) {
+        // linear index over the lower triangle of the tile grid, heaviest rows last
+        int t = blockIdx.x;
+        tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((long)(tm + 1) * (tm + 2) / 2 <= t) ++tm;
+        while ((long)tm * (tm + 1) / 2 > t) --tm;
+        tn = t - tm * (tm + 1) / 2;
+    } else {
+        int tiles_n = p.N / TILE;
+        tm = blockIdx.x / tiles_n;
+        tn = blockIdx.x % tiles_n;
+    }
+    int k0 = 0, k1 = p.K;
+    if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TILE);
+    if (p.krule & KR_LE_N) k1 = min(k1, (tn + 1) * TILE);
+    if (p.krule & KR_GE_N) k0 = max(k0, tn * TILE);
+    if (p.krule & KR_GE_M) k0 = max(k0, tm * TILE);
+    const int nk = (k1 - k0) / BK;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+
+    const double* Ag = A_MN ? p.A + (long)k0 * p.lda + (long)tm * TILE
+                            : p.A + (long)tm * TILE * p.lda + k0;
+    const double* Bg = B_MN ? p.B + (long)k0 * p.ldb + (long)tn * TILE
+                            : p.B + (long)tn * TILE * p.ldb + k0;
+    const long a_step = A_MN ? (long)BK * p.lda : BK;
+    const long b_step = B_MN ? (long)BK * p.ldb : BK;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+        if (s < nk) {
+            load_tile_async<A_MN>(As + s * TILE_DOUBLES, Ag + s * a_step, p.lda, tid);
+            load_tile_async<B_MN>(Bs + s * TILE_DOUBLES, Bg + s * b_step, p.ldb, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        int nxt = kt + GEMM_STAGES - 1;
+        if (nxt < nk) {
+            int s = nxt % GEMM_STAGES;
+            load_tile_async<A_MN>(As + s * TILE_DOUBLES, Ag + nxt * a_step, p.lda, tid);
+            load_tile_async<B_MN>(Bs + s * TILE_DOUBLES, Bg + nxt * b_step, p.ldb, tid);
+        }
+        cp_async_commit();
+        int s = kt % GEMM_STAGES;
+        mma_stage<A_MN, B_MN>(As + s * TILE_DOUBLES, Bs + s * TILE_DOUBLES, wm, wn, lane, acc);
+    }
+    cp_async_wait<0>();
+
+    // epilogue: lane holds C[g][2*tig + {0,1}] of each 8x8 block -> 16-byte stores
+    const int g = lane >> 2, tig = lane & 3;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+        long row = (long)tm * TILE + wm * 64 + mb * 8 + g;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            long col = (long)tn * TILE + wn * 32 + nb * 8 + 2 * tig;
+            double2* dst = reinterpret_cast<double2*>(p.C + row * p.ldc + col);
+            double2 v;
+            v.x = alpha * acc[mb][nb][0];
+            v.y = alpha * acc[mb][nb][1];
+            if (beta != 0.0) {
+                double2 old = *dst;
+                v.x = fma(beta, old.x, v.x);
+                v.y = fma(beta, old.y, v.y);
+            }
+            *dst = v;
+        }
+    }
+}
+
+// host launcher (dgemm.cu)
+cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& args, cudaStream_t stream);
+cudaError_t dgemm_init();
+
+}  // namespace gp2d

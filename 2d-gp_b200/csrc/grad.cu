@@ -1,0 +1,70 @@
+// Log-marginal-likelihood gradient: d LML / d(l_df, l_cf, ratio, noise)
+//   = sum_ij W_ij dK_ij/dtheta,  W = 0.5 (alpha alpha^T - K^-1)     (noise: trace W)
+// Replaces GPy's dL_dK + kern.update_gradients_full (myKernel.py:59-106) +
+// likelihood.update_gradients, i.e. sklearn _gpr.py:629-654.  K^-1 = Z^T Z comes from the
+// DMMA GEMM (lower tiles); dK/dtheta is regenerated on the fly from the point pairs, so
+// the only HBM traffic is one read of the lower triangle of K^-1.
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "linalg.h"
+#include "reduce.cuh"
+
+namespace gp2d {
+
+__global__ void __launch_bounds__(256)
+lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                const double* __restrict__ X, int N, HelmParams hp, int compat,
+                double* __restrict__ partial) {
+    __shared__ double sh[4 * 32];
+    int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((long)I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int jj = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int j = J * 64 + jj;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (j < N) {
+        const double bx = X[2 * (long)j], by = X[2 * (long)j + 1];
+        const double b0 = alpha[2 * j], b1 = alpha[2 * j + 1];
+        for (int ii = ty; ii < 64; ii += 4) {
+            const int i = I * 64 + ii;
+            if (i >= N || i < j) continue;
+            const double* r0 = Kinv + (long)(2 * i) * ld + 2 * j;
+            const double2 q0 = *reinterpret_cast<const double2*>(r0);
+            const double2 q1 = *reinterpret_cast<const double2*>(r0 + ld);
+            const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
+            const double W11 = 0.5 * (a0 * b0 - q0.x), W12 = 0.5 * (a0 * b1 - q0.y);
+            const double W21 = 0.5 * (a1 * b0 - q1.x), W22 = 0.5 * (a1 * b1 - q1.y);
+            double g[3][3];
+            helm_block_grad(hp, compat, X[2 * (long)i] - bx, X[2 * (long)i + 1] - by, g);
+            const double wgt = (i == j) ? 1.0 : 2.0;
+            const double Ws = W12 + W21;
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                acc[p] += wgt * (g[p][0] * W11 + g[p][1] * Ws + g[p][2] * W22);
+            if (i == j) acc[3] += W11 + W22;
+        }
+    }
+    block_reduce<4>(acc, sh);
+    if (threadIdx.x == 0) {
+        double* o = partial + 4 * (long)blockIdx.x;
+        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+    }
+}
+
+int lml_grad_partials(int npad) {
+    int T = npad / TILE;
+    return T * (T + 1) / 2;
+}
+
+cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha_int,
+                            const double* X, int N, const HelmParams& hp, int compat,
+                            double* partial, double* out4, cudaStream_t st) {
+    int count = lml_grad_partials(npad);
+    lml_grad_kernel<<<count, 256, 0, st>>>(Kinv, ld, alpha_int, X, N, hp, compat, partial);
+    final_reduce_kernel<4><<<1, 1024, 0, st>>>(partial, count, out4);
+    return cudaGetLastError();
+}
+
+}  // namespace gp2d

@@ -1,0 +1,218 @@
+"""Device-level engine: thin Python over the C ABI (include/gp2d.h).
+
+torch is used only for device memory, streams and host<->device copies; every number is
+produced by the hand-written sm_100a kernels in csrc/.  There is no CPU path: calls raise
+if CUDA or libgp2d.so is unavailable.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, Gp2dError
+
+__all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
+           "HelmholtzGP", "fit_predict_host"]
+
+
+class LinAlgError(np.linalg.LinAlgError):
+    """Raised when the covariance is not positive definite (the reference surfaces this as
+    numpy/GPy LinAlgError)."""
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise Gp2dError("gp2d needs a CUDA device: the hot path has no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def as_dev(a, device=None, shape=None) -> torch.Tensor:
+    """float64, contiguous, on the GPU (numpy arrays go through pinned memory)."""
+    dev = _device(device)
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=dev, dtype=torch.float64, non_blocking=True)
+    else:
+        h = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        t = h.pin_memory().to(dev, non_blocking=True) if h.numel() > 65536 else h.to(dev)
+    t = t.contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _points(X, device=None) -> torch.Tensor:
+    t = as_dev(X, device)
+    if t.dim() != 2 or t.shape[1] != 2:
+        raise ValueError("points must be [N,2] (the kernels assume input_dim == 2, myKernel.py:15)")
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+def kernel_K(X, X2=None, l_df=1.0, l_cf=1.0, ratio=1.0, diag_add=0.0, out=None) -> torch.Tensor:
+    """[2N,2M] Helmholtz covariance in the reference block layout (device tensor)."""
+    Xd = _points(X)
+    X2d = None if X2 is None else _points(X2, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    if out is None:
+        out = torch.empty((2 * N, 2 * M), dtype=torch.float64, device=Xd.device)
+    if N and M:
+        with torch.cuda.device(Xd.device):
+            check(lib.gp2d_kernel_build(_ptr(Xd), N, _ptr(X2d), M, l_df, l_cf, ratio, diag_add,
+                                        _ptr(out), out.stride(0), _stream()), "gp2d_kernel_build")
+    return out
+
+
+def kernel_Kdiag(M, l_df, l_cf, ratio, device=None) -> torch.Tensor:
+    out = torch.empty(2 * int(M), dtype=torch.float64, device=_device(device))
+    with torch.cuda.device(out.device):
+        check(lib.gp2d_kdiag(int(M), l_df, l_cf, ratio, _ptr(out), _stream()), "gp2d_kdiag")
+    return out
+
+
+def kernel_grad_sums(dL_dK, X, X2, l_df, l_cf, ratio, reference_compat=False) -> torch.Tensor:
+    """sum(dK/dtheta * dL_dK) for (l_df, l_cf, ratio) -> device tensor[3]."""
+    Xd = _points(X)
+    X2d = None if X2 is None else _points(X2, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    W = as_dev(dL_dK, Xd.device)
+    if tuple(W.shape) != (2 * N, 2 * M):
+        raise ValueError("dL_dK must be [2N,2M]")
+    nb = lib.gp2d_kernel_grad_workspace_bytes(N, M)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    out = torch.empty(3, dtype=torch.float64, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        check(lib.gp2d_kernel_grad(_ptr(Xd), N, _ptr(X2d), M, l_df, l_cf, ratio, int(bool(reference_compat)),
+                                   _ptr(W), W.stride(0), _ptr(ws), nb, _ptr(out), _stream()),
+              "gp2d_kernel_grad")
+    return out
+
+
+def potrf(A, overwrite=False):
+    """Lower Cholesky of a row-major SPD matrix on the device.  Returns (L, info)."""
+    Ad = as_dev(A)
+    if not (overwrite and isinstance(A, torch.Tensor) and Ad.data_ptr() == A.data_ptr()):
+        Ad = Ad.clone()
+    n = Ad.shape[0]
+    nb = lib.gp2d_potrf_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Ad.device)
+    info = torch.zeros(1, dtype=torch.int32, device=Ad.device)
+    with torch.cuda.device(Ad.device):
+        check(lib.gp2d_potrf(_ptr(Ad), n, Ad.stride(0), _ptr(ws), nb, _ptr(info), _stream()), "gp2d_potrf")
+    return torch.tril(Ad), int(info.item())
+
+
+# ------------------------------------------------------------------------------------------
+class HelmholtzGP:
+    """Fit state of one snapshot on one GPU.
+
+    fit(): K + (noise+jitter) I -> Cholesky / L^-1 -> alpha, LML  (gp2d_fit)
+    predict(Xs): fused K* / mean / variance                       (gp2d_predict)
+    lml_and_grad(): LML and d/d(l_df, l_cf, ratio, noise)          (gp2d_lml_grad)
+    """
+
+    def __init__(self, X, y, l_df, l_cf, ratio, noise, jitter=0.0, device=None):
+        self.X = _points(X, device)
+        self.N = int(self.X.shape[0])
+        self.y = as_dev(y, self.X.device).reshape(-1)
+        if self.y.numel() != 2 * self.N:
+            raise ValueError("y must stack both components: length 2N (GP_laser.py:98,174)")
+        self.set_params(l_df, l_cf, ratio, noise)
+        self.jitter = float(jitter)
+        self.ws_bytes = lib.gp2d_fit_workspace_bytes(self.N)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.X.device)
+        self._scal = torch.zeros(8, dtype=torch.float64, device=self.X.device)
+        self._info = torch.zeros(1, dtype=torch.int32, device=self.X.device)
+        self.fitted = False
+        self.lml = None
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def set_params(self, l_df, l_cf, ratio, noise):
+        self.l_df, self.l_cf, self.ratio, self.noise = float(l_df), float(l_cf), float(ratio), float(noise)
+        self.fitted = False
+
+    def fit_async(self, alpha_out=None):
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_fit(_ptr(self.X), self.N, _ptr(self.y), self.l_df, self.l_cf, self.ratio,
+                               self.noise, self.jitter, _ptr(self.ws), self.ws_bytes, _ptr(alpha_out),
+                               _ptr(self._scal), _ptr(self._info), _stream()), "gp2d_fit")
+        self.fitted = True
+
+    def fit(self):
+        """Returns the log marginal likelihood; raises LinAlgError when not PD."""
+        self.fit_async()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(self._scal[0].item())
+        return self.lml
+
+    def alpha(self) -> torch.Tensor:
+        """K^-1 y in the caller's stacked order."""
+        out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
+        self.fit_async(alpha_out=out)
+        return out
+
+    def predict(self, Xs, include_noise=False, out_mean=None, out_var=None):
+        """mean[2M], var[2M] (component-major) as device tensors."""
+        if not self.fitted:
+            self.fit()
+        Xsd = _points(Xs, self.device)
+        M = int(Xsd.shape[0])
+        mean = out_mean if out_mean is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        var = out_var if out_var is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        if M:
+            with torch.cuda.device(self.device):
+                check(lib.gp2d_predict(_ptr(self.ws), self.N, self.l_df, self.l_cf, self.ratio, _ptr(Xsd), M, M,
+                                       self.noise if include_noise else 0.0, _ptr(mean), _ptr(var), _stream()),
+                      "gp2d_predict")
+        return mean, var
+
+    def lml_and_grad(self, reference_compat=False):
+        """(LML, grad[4]) with grad over (l_df, l_cf, ratio, noise) as host floats."""
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_lml_grad(_ptr(self.X), self.N, _ptr(self.y), self.l_df, self.l_cf, self.ratio,
+                                    self.noise, self.jitter, int(bool(reference_compat)), _ptr(self.ws),
+                                    self.ws_bytes, _ptr(self._scal), _ptr(self._info), _stream()),
+                  "gp2d_lml_grad")
+        self.fitted = True
+        host = self._scal[:5].cpu().numpy()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(host[0])
+        return self.lml, host[1:5].copy()
+
+
+def fit_predict_host(X, y, l_df, l_cf, ratio, noise, Xs, jitter=0.0, include_noise=False):
+    """Whole pipeline through the host-pointer C entry point (numpy in, numpy out)."""
+    import ctypes as C
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    N, M = X.shape[0], Xs.shape[0]
+    mean = np.empty(2 * M)
+    var = np.empty(2 * M)
+    lml = np.zeros(1)
+    _device()
+    rc = lib.gp2d_fit_predict_host(X.ctypes.data, N, y.ctypes.data, l_df, l_cf, ratio, noise, jitter,
+                                   Xs.ctypes.data, M, int(include_noise), mean.ctypes.data, var.ctypes.data,
+                                   lml.ctypes.data)
+    check(rc, "gp2d_fit_predict_host")
+    if rc > 0:
+        raise LinAlgError("covariance not positive definite (pivot %d)" % rc)
+    return mean, var, float(lml[0])

@@ -1,0 +1,115 @@
+/* gp2d -- C ABI of the B200-native Helmholtz Gaussian-process hot path.
+ *
+ * Drop-in boundary for rafaelcgon/2D-GP's kernel / fit / predict / likelihood path
+ * (SURVEY.md §8b).  Plain C: pointers and sizes only, no torch or C++ types.  Unless a
+ * function name ends in _host, every data pointer is a CALLER-OWNED DEVICE pointer to
+ * IEEE fp64, `stream` is a cudaStream_t passed as void*, calls are asynchronous on that
+ * stream, allocate nothing (workspace is sized by the *_workspace_bytes queries), keep no
+ * global state and are re-entrant across streams.
+ *
+ * Return value: 0 = launched OK; -k = argument k (1-based) is invalid;
+ * <= -1000 = -(1000 + cudaError_t).  Numerical failure of the factorisation is reported
+ * LAPACK-style through an `int* info` in device memory: 0, or the 1-based index of the
+ * first non-positive pivot (the matrix is not positive definite).
+ *
+ * Layouts (the reference's): X is [N,2] row-major (x, y); y is the stacked observation
+ * vector [first component; second component] of length 2N (GP_laser.py:98,174);
+ * covariance matrices are component-major blocks, row c*N+i, column c'*M+j, row-major
+ * with leading dimension ld (myKernel.py:40-43; GP_scripts.py:89-95); predictive outputs
+ * are [component][point].  theta = (l_df, l_cf, ratio); `noise` is a variance.
+ */
+#ifndef GP2D_H
+#define GP2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP2D_VERSION 100
+
+int gp2d_version(void);
+/* Human-readable text for a negative return code (static storage). */
+const char* gp2d_error_string(int code);
+
+/* ---- covariance ------------------------------------------------------------------ */
+
+/* K[2N,2M] = ratio*K_divfree + (1-ratio)*K_curlfree between X[N,2] and X2[M,2].
+ * X2 == NULL means X2 = X (then diag_add is added on the diagonal).
+ * Replaces myKernel.myKernel.K(X,X2) (myKernel.py:27-53), nonDivK.K (ratio=1,
+ * myKernel.py:159-176), nonRotK.K (ratio=0, myKernel.py:255-271), GP_scripts.myKernel
+ * (GP_scripts.py:6-42), compute_K (GP_scripts.py:74-95) and, with the roles of X and X2
+ * swapped, compute_Ks (GP_scripts.py:97-123). */
+int gp2d_kernel_build(const double* X, int N, const double* X2, int M,
+                      double l_df, double l_cf, double ratio, double diag_add,
+                      double* K, int64_t ldk, void* stream);
+
+/* out[2M] = ratio/l_df^2 + (1-ratio)/l_cf^2.  Replaces myKernel.Kdiag (myKernel.py:55-57),
+ * nonDivK.Kdiag (:178-180), nonRotK.Kdiag (:273-275). */
+int gp2d_kdiag(int M, double l_df, double l_cf, double ratio, double* out, void* stream);
+
+/* out3 = sum(dK/dtheta * dL_dK) for theta = (l_df, l_cf, ratio); dL_dK is [2N,2M] in the
+ * block layout.  reference_compat != 0 reproduces the integrands of
+ * myKernel.update_gradients_full (myKernel.py:59-106) verbatim; 0 gives the analytic
+ * derivative (the reference's length-scale terms are not the derivative of its K). */
+size_t gp2d_kernel_grad_workspace_bytes(int N, int M);
+int gp2d_kernel_grad(const double* X, int N, const double* X2, int M,
+                     double l_df, double l_cf, double ratio, int reference_compat,
+                     const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                     double* out3, void* stream);
+
+/* ---- dense factorisation --------------------------------------------------------- */
+
+/* In-place lower Cholesky of the row-major SPD matrix A[n,n] (upper triangle untouched).
+ * Replaces scipy/LAPACK dpotrf as used by GPy and sklearn. */
+size_t gp2d_potrf_workspace_bytes(int n);
+int gp2d_potrf(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* ---- GP fit / predict / likelihood ----------------------------------------------- */
+
+/* Fit: build K + (noise+jitter) I, factorise, alpha = K^-1 y,
+ * LML = -1/2 y'alpha - sum log L_ii - N log 2pi.  The workspace then holds the fit state
+ * consumed by gp2d_predict (layout private, a pure function of N).
+ * alpha_out (2N, block order) may be NULL.  lml_out: 1 double, info: 1 int (device).
+ * Replaces GPy GPRegression(X,Y,k) (GP_plots.py:763; krig.py:411), the numpy
+ * K + noise*I ; inv path (GP_laser.py:113-118,177-180) and sklearn .fit (krig.py:182-185). */
+size_t gp2d_fit_workspace_bytes(int N);
+int gp2d_fit(const double* X, int N, const double* y,
+             double l_df, double l_cf, double ratio, double noise, double jitter,
+             void* ws, size_t ws_bytes, double* alpha_out, double* lml_out, int* info,
+             void* stream);
+
+/* Predict at Xs[M,2] from a fit state: mean[c*out_stride + j], var[c*out_stride + j],
+ * c in {0,1}, j in [0,M).  var = k** - |L^-1 k*|^2 clamped at 0, plus var_add (pass the
+ * noise variance to reproduce GPy's predict, 0 for sklearn/GP_laser).
+ * Replaces GPy model.predict (krig.py:543-544,600-601), getMean + diag of Cov
+ * (GP_scripts.py:44-46; GP_laser.py:129-131) and sklearn predict(return_std=True)
+ * (krig.py:194).  Independent grid shards may be issued on different streams / GPUs. */
+int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio,
+                 const double* Xs, int M, int64_t out_stride, double var_add,
+                 double* mean, double* var, void* stream);
+
+/* LML and its gradient in one pass: out5 = (LML, dLML/dl_df, dLML/dl_cf, dLML/dratio,
+ * dLML/dnoise).  Leaves a valid fit state in ws.  Replaces one objective evaluation of
+ * optimize_restarts (krig.py:450; GP_plots.py:765): kernel build + Cholesky + dL_dK +
+ * update_gradients_full + noise gradient (sklearn _gpr.py:583-656). */
+int gp2d_lml_grad(const double* X, int N, const double* y,
+                  double l_df, double l_cf, double ratio, double noise, double jitter,
+                  int reference_compat, void* ws, size_t ws_bytes, double* out5, int* info,
+                  void* stream);
+
+/* ---- host-buffer convenience (allocates, copies, synchronises) -------------------- */
+
+/* Whole fit + predict with HOST pointers on the current device; returns info (> 0) or an
+ * error code (< 0).  lml may be NULL. */
+int gp2d_fit_predict_host(const double* X, int N, const double* y,
+                          double l_df, double l_cf, double ratio, double noise, double jitter,
+                          const double* Xs, int M, int include_noise,
+                          double* mean, double* var, double* lml);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GP2D_H */

@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: libgp2d.so builds, loads, and exports every
+function include/gp2d.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gp2d.h")
+LIB = os.path.join(ROOT, "2d-gp_b200", "libgp2d.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gp2d_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "2d-gp_b200", "build.py")])
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_path():
+    names = declared_functions()
+    for must in ["gp2d_kernel_build", "gp2d_kdiag", "gp2d_kernel_grad", "gp2d_potrf", "gp2d_fit",
+                 "gp2d_predict", "gp2d_lml_grad", "gp2d_fit_predict_host"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), "libgp2d.so does not export %s" % name
+
+
+def test_binding_table_matches_header(lib):
+    import gp2d_b200
+    from gp2d_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    assert _lib.lib.gp2d_version() == 100
+    assert _lib.lib.gp2d_error_string(-3).decode() == "invalid argument 3"
+    assert _lib.lib.gp2d_error_string(7).decode().startswith("matrix not positive definite")
+
+
+def test_workspace_queries_and_argument_validation(lib):
+    from gp2d_b200._lib import lib as L
+    # pure host arithmetic: no device needed
+    n400 = L.gp2d_fit_workspace_bytes(400)
+    assert n400 >= 2 * 896 * 896 * 8           # A and Z padded to 896
+    assert L.gp2d_fit_workspace_bytes(0) == 0
+    assert L.gp2d_potrf_workspace_bytes(1000) >= 2 * 1024 * 1024 * 8
+    assert L.gp2d_kernel_build(None, 4, None, 4, 1.0, 1.0, 0.5, 0.0, None, 8, None) == -1
+    assert L.gp2d_predict(None, 4, 1.0, 1.0, 0.5, None, 1, 1, 0.0, None, None, None) == -1
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import numpy as np
+    import gp2d_b200 as gp
+    with pytest.raises(RuntimeError):
+        gp.kernel_K(np.zeros((3, 2)), None, 1.0, 1.0, 0.5)
+    with pytest.raises(RuntimeError):
+        gp.HelmholtzGP(np.zeros((3, 2)), np.zeros(6), 1.0, 1.0, 0.5, 0.1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "2d-gp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors generated from the reference.  Run on the B200 box:  pytest tests -m gpu"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():          # collected on the CPU box, run on the GPU box
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import gp2d_b200 as gp                      # noqa: E402
+from gp2d_b200 import synthetic             # noqa: E402
+from gp2d_b200._lib import lib              # noqa: E402
+from oracle import gp_oracle as orc        # noqa: E402
+
+DEV = torch.device("cuda:0")
+THETAS = [(2.0, 2.0, 0.5), (1.3, 3.1, 0.2), (0.6, 0.6, 1.0), (0.7, 1.9, 0.0)]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---- bring-up hooks ---------------------------------------------------------------------
+lib.gp2d_dbg_gemm.restype = C.c_int
+lib.gp2d_dbg_gemm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                              C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                              C.c_int, C.c_void_p]
+lib.gp2d_dbg_potri.restype = C.c_int
+lib.gp2d_dbg_potri.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_dgemm_layouts(a_mn, b_mn):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    M, N, K = 256, 384, 160
+    A = torch.randn(M, K, generator=g, dtype=torch.float64).to(DEV)
+    B = torch.randn(K, N, generator=g, dtype=torch.float64).to(DEV)
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64).to(DEV)
+    Ast = A.t().contiguous() if a_mn else A.contiguous()          # MN-major: stored [K][M]
+    Bst = B.contiguous() if b_mn else B.t().contiguous()          # K-major: stored [N][K]
+    Cc = C0.clone()
+    rc = lib.gp2d_dbg_gemm(a_mn, b_mn, Ast.data_ptr(), Ast.stride(0), Bst.data_ptr(), Bst.stride(0),
+                           Cc.data_ptr(), Cc.stride(0), M, N, K, -1.5, 0.75, 0, 0, stream())
+    assert rc == 0, lib.gp2d_error_string(rc)
+    ref = -1.5 * (A @ B) + 0.75 * C0
+    torch.testing.assert_close(Cc, ref, rtol=1e-12, atol=1e-11)
+
+
+def test_dgemm_triangular_clipping():
+    g = torch.Generator(device="cpu").manual_seed(2)
+    n = 384
+    Zl = torch.tril(torch.randn(n, n, generator=g, dtype=torch.float64)).to(DEV)
+    ti = torch.arange(n, device=DEV) // 128
+    tile_upper = (ti[None, :] > ti[:, None]).to(torch.float64)
+    Zgarb = Zl + 7.0 * tile_upper              # never-read tiles hold garbage
+    D = torch.randn(n, n, generator=g, dtype=torch.float64).to(DEV)
+    out = torch.zeros(n, n, dtype=torch.float64, device=DEV)
+    # KR_LE_N (2): C = D * Z^T with Z lower (upper off-diagonal tiles hold garbage)
+    rc = lib.gp2d_dbg_gemm(0, 0, D.data_ptr(), n, Zgarb.data_ptr(), n, out.data_ptr(), n, n, n, n, 1.0, 0.0, 0, 2, stream())
+    assert rc == 0
+    torch.testing.assert_close(out, D @ Zl.t(), rtol=1e-12, atol=1e-11)
+    # KR_GE_N (4): C = D * Z (B MN-major)
+    rc = lib.gp2d_dbg_gemm(0, 1, D.data_ptr(), n, Zgarb.data_ptr(), n, out.data_ptr(), n, n, n, n, 1.0, 0.0, 0, 4, stream())
+    assert rc == 0
+    torch.testing.assert_close(out, D @ Zl, rtol=1e-12, atol=1e-11)
+    # KR_LE_M (1): C = -Z * D (A lower, B MN-major)
+    rc = lib.gp2d_dbg_gemm(0, 1, Zgarb.data_ptr(), n, D.data_ptr(), n, out.data_ptr(), n, n, n, n, -1.0, 0.0, 0, 1, stream())
+    assert rc == 0
+    torch.testing.assert_close(out, -(Zl @ D), rtol=1e-12, atol=1e-11)
+    # KR_GE_M (8) + lower_out: lower tiles of Z^T Z
+    out.zero_()
+    rc = lib.gp2d_dbg_gemm(1, 1, Zgarb.data_ptr(), n, Zgarb.data_ptr(), n, out.data_ptr(), n, n, n, n, 1.0, 0.0, 1, 8, stream())
+    assert rc == 0
+    ref = Zl.t() @ Zl
+    tile_lower = (torch.arange(n, device=DEV)[None, :] // 128 <= torch.arange(n, device=DEV)[:, None] // 128)
+    torch.testing.assert_close(out * tile_lower, ref * tile_lower, rtol=1e-12, atol=1e-11)
+    assert float((out * ~tile_lower).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [128, 256, 384, 1024])
+def test_potri_recursion(n):
+    g = torch.Generator(device="cpu").manual_seed(n)
+    Bm = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = (Bm @ Bm.t() / n + torch.eye(n, dtype=torch.float64)).to(DEV)
+    Lref = torch.linalg.cholesky(A)
+    for need_inv, keep_L in [(1, 0), (1, 1), (0, 1)]:
+        Aw = A.clone()
+        Z = torch.zeros(n, n, dtype=torch.float64, device=DEV)
+        W = torch.zeros(n * n // 4 + 64, dtype=torch.float64, device=DEV)
+        logd = torch.zeros(n, dtype=torch.float64, device=DEV)
+        info = torch.zeros(1, dtype=torch.int32, device=DEV)
+        rc = lib.gp2d_dbg_potri(Aw.data_ptr(), n, Z.data_ptr(), logd.data_ptr(), info.data_ptr(), need_inv,
+                                keep_L, W.data_ptr(), stream())
+        assert rc == 0, lib.gp2d_error_string(rc)
+        assert int(info.item()) == 0
+        torch.testing.assert_close(logd, torch.log(torch.diagonal(Lref)), rtol=1e-11, atol=1e-12)
+        if keep_L:
+            torch.testing.assert_close(torch.tril(Aw), Lref, rtol=1e-10, atol=1e-11)
+        if need_inv:
+            Zi = torch.linalg.inv(Lref)
+            torch.testing.assert_close(torch.tril(Z), Zi, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 300, 1000])
+def test_potrf_public(n):
+    g = torch.Generator(device="cpu").manual_seed(100 + n)
+    Bm = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = (Bm @ Bm.t() / n + torch.eye(n, dtype=torch.float64)).to(DEV)
+    L, info = gp.potrf(A)
+    assert info == 0
+    torch.testing.assert_close(L, torch.linalg.cholesky(A), rtol=1e-10, atol=1e-11)
+
+
+def test_potrf_not_positive_definite():
+    n = 200
+    A = torch.eye(n, dtype=torch.float64, device=DEV)
+    A[150, 150] = -1.0
+    _, info = gp.potrf(A)
+    assert info == 151
+
+
+# ---- kernel build -------------------------------------------------------------------------
+def test_kernel_build_golden(golden_dir):
+    ks = np.load(os.path.join(golden_dir, "kernel_small.npz"))
+    X, X2 = ks["X"], ks["X2"]
+    for t, (ldf, lcf, r) in enumerate(ks["thetas"]):
+        K = gp.kernel_K(X, None, ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(K, ks["ref_K_class_sym_%d" % t], rtol=0, atol=2e-14)
+        K = gp.kernel_K(X, X2, ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(K, ks["ref_K_class_x_%d" % t], rtol=0, atol=2e-14)
+        # compute_Ks orientation: K(X*, X)
+        K = gp.kernel_K(X2, X, ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(K, ks["ref_Ks_loops_%d" % t], rtol=0, atol=2e-14)
+        d = gp.kernel_Kdiag(X2.shape[0], ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(d, ks["ref_Kdiag_%d" % t], rtol=1e-15)
+
+
+@pytest.mark.parametrize("N,M", [(1, 1), (3, 7), (33, 64), (130, 129), (257, 1000)])
+def test_kernel_build_ragged_vs_oracle(N, M):
+    rng = np.random.default_rng(N * 1000 + M)
+    X = rng.uniform(0, 20, size=(N, 2))
+    X2 = rng.uniform(0, 20, size=(M, 2))
+    for (ldf, lcf, r) in THETAS[:2]:
+        K = gp.kernel_K(X, X2, ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(K, orc.helmholtz_K(X, X2, ldf, lcf, r), rtol=0, atol=1e-14)
+    Ks = gp.kernel_K(X, None, 2.0, 2.0, 0.5, diag_add=0.05).cpu().numpy()
+    ref = orc.helmholtz_K(X, None, 2.0, 2.0, 0.5) + 0.05 * np.eye(2 * N)
+    np.testing.assert_allclose(Ks, ref, rtol=0, atol=1e-14)
+    # strided output (ld > 2M)
+    out = torch.full((2 * N, 2 * M + 3), -7.0, dtype=torch.float64, device=DEV)
+    gp.kernel_K(X, X2, 1.3, 3.1, 0.2, out=out[:, :2 * M])
+    np.testing.assert_allclose(out[:, :2 * M].cpu().numpy(), orc.helmholtz_K(X, X2, 1.3, 3.1, 0.2), atol=1e-14)
+    assert float(out[:, 2 * M:].min()) == -7.0 and float(out[:, 2 * M:].max()) == -7.0
+
+
+def test_kernel_far_points_underflow():
+    X = np.array([[0.0, 0.0], [1e4, -1e4], [3.0, 4.0]])
+    K = gp.kernel_K(X, None, 0.5, 0.7, 0.3).cpu().numpy()
+    np.testing.assert_allclose(K, orc.helmholtz_K(X, None, 0.5, 0.7, 0.3), rtol=0, atol=1e-15)
+    assert np.isfinite(K).all()
+
+
+def test_kernel_grad_sums_golden(golden_dir):
+    ks = np.load(os.path.join(golden_dir, "kernel_small.npz"))
+    X, X2 = ks["X"], ks["X2"]
+    for t, (ldf, lcf, r) in enumerate(ks["thetas"]):
+        g = gp.kernel_grad_sums(ks["W_sym"], X, None, ldf, lcf, r, reference_compat=True).cpu().numpy()
+        np.testing.assert_allclose(g, ks["ref_grad_compat_sym_%d" % t], rtol=1e-11, atol=1e-12)
+        g = gp.kernel_grad_sums(ks["W_x"], X, X2, ldf, lcf, r, reference_compat=True).cpu().numpy()
+        np.testing.assert_allclose(g, ks["ref_grad_compat_x_%d" % t], rtol=1e-11, atol=1e-12)
+        g = gp.kernel_grad_sums(ks["W_x"], X, X2, ldf, lcf, r).cpu().numpy()
+        np.testing.assert_allclose(g, orc.kernel_grad_sums(ks["W_x"], X, X2, ldf, lcf, r), rtol=1e-11, atol=1e-12)
+
+
+# ---- fit / predict / likelihood -------------------------------------------------------------
+@pytest.mark.parametrize("ts", [0, 100])
+def test_simlaser_fit_predict(golden_dir, ts):
+    """Config 1: simulTracks.pkl snapshot through GP_laser.simLaser's defaults, against the
+    reference's own numpy pipeline (tests/golden/make_golden.py).  Tolerances from
+    BASELINE.json: 1e-8 relative on mean/variance, 1e-6 on the log-likelihood."""
+    g = np.load(os.path.join(golden_dir, "simlaser_ts%d.npz" % ts))
+    X, y, Xs = g["X"], g["y"], g["Xs"]
+    ldf, lcf, r = g["theta"]
+    m = gp.HelmholtzGP(X, y, ldf, lcf, r, float(g["noise"]))
+    lml = m.fit()
+    mean, var = m.predict(Xs)
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    scale = np.abs(g["ref_mean"]).max()
+    np.testing.assert_allclose(mean, g["ref_mean"], rtol=1e-8, atol=1e-8 * scale)
+    np.testing.assert_allclose(var, g["ref_var"], rtol=1e-8)
+    assert abs(lml - float(g["derived_lml"])) <= 1e-6 * abs(float(g["derived_lml"]))
+    f = orc.fit(X, y, ldf, lcf, r, float(g["noise"]))
+    np.testing.assert_allclose(m.alpha().cpu().numpy(), f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
+    # GPy convention: noise variance included
+    _, var_n = m.predict(Xs, include_noise=True)
+    np.testing.assert_allclose(var_n.cpu().numpy(), g["ref_var"] + float(g["noise"]), rtol=1e-8)
+
+
+@pytest.mark.parametrize("N,M,theta", [(1, 3, THETAS[0]), (7, 1, THETAS[1]), (64, 64, THETAS[0]),
+                                       (65, 130, THETAS[1]), (300, 517, THETAS[2]), (513, 200, THETAS[3])])
+def test_fit_predict_vs_oracle(N, M, theta):
+    X, y = synthetic.drifter_snapshot(N, config_id=9, seed_offset=N)
+    Xs = synthetic.prediction_grid(X, M, 1)
+    ldf, lcf, r = theta
+    noise = 0.05
+    m = gp.HelmholtzGP(X, y, ldf, lcf, r, noise)
+    lml = m.fit()
+    mean, var = m.predict(Xs)
+    f = orc.fit(X, y, ldf, lcf, r, noise)
+    mo, vo = orc.predict(X, f, ldf, lcf, r, Xs)
+    np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-9 * max(np.abs(mo).max(), 1e-3))
+    np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+    assert abs(lml - f["lml"]) <= 1e-6 * max(abs(f["lml"]), 1.0)
+
+
+def test_lml_grad_vs_oracle():
+    X, y = synthetic.drifter_snapshot(200, config_id=4)
+    for theta in [(2.0, 2.0, 0.5), (1.3, 3.1, 0.2)]:
+        m = gp.HelmholtzGP(X, y, *theta, 0.05, jitter=1e-8)
+        for compat in (False, True):
+            lml, grad = m.lml_and_grad(reference_compat=compat)
+            lo, go = orc.lml_and_grad(X, y, *theta, 0.05, jitter=1e-8, reference_compat=compat)
+            assert abs(lml - lo) <= 1e-6 * abs(lo)
+            np.testing.assert_allclose(grad, go, rtol=1e-6, atol=1e-7)
+        # a valid fit state is left behind
+        mean, _ = m.predict(X[:5])
+        f = orc.fit(X, y, *theta, 0.05, jitter=1e-8)
+        mo, _ = orc.predict(X, f, *theta, X[:5])
+        np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-10)
+
+
+def test_not_positive_definite_raises():
+    X = np.zeros((40, 2))                     # coincident points, no noise -> singular
+    y = np.ones(80)
+    m = gp.HelmholtzGP(X, y, 1.0, 1.0, 0.5, 0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        m.fit()
+
+
+def test_host_pointer_entry_point(golden_dir):
+    g = np.load(os.path.join(golden_dir, "simlaser_ts0.npz"))
+    ldf, lcf, r = g["theta"]
+    mean, var, lml = gp.fit_predict_host(g["X"], g["y"], ldf, lcf, r, float(g["noise"]), g["Xs"])
+    np.testing.assert_allclose(mean, g["ref_mean"], rtol=1e-8, atol=1e-8 * np.abs(g["ref_mean"]).max())
+    np.testing.assert_allclose(var, g["ref_var"], rtol=1e-8)
+    assert abs(lml - float(g["derived_lml"])) < 1e-6 * abs(float(g["derived_lml"]))
+
+
+def test_bad_arguments():
+    X = dev(np.zeros((4, 2)))
+    out = torch.zeros(8, 8, dtype=torch.float64, device=DEV)
+    assert lib.gp2d_kernel_build(X.data_ptr(), 4, None, 4, -1.0, 1.0, 0.5, 0.0, out.data_ptr(), 8, None) == -5
+    assert lib.gp2d_kernel_build(None, 4, None, 4, 1.0, 1.0, 0.5, 0.0, out.data_ptr(), 8, None) == -1
+    assert lib.gp2d_kernel_build(X.data_ptr(), 4, None, 4, 1.0, 1.0, 0.5, 0.0, out.data_ptr(), 7, None) == -10
+    assert lib.gp2d_fit(X.data_ptr(), 4, out.data_ptr(), 1.0, 1.0, 0.5, 0.1, 0.0, out.data_ptr(), 16, None, None,
+                        None, None) == -10
+
+
+# ---- full-size configuration: size-independent properties + sampled oracle -------------------
+def test_config2_full_size_properties():
+    """BASELINE.json configs[1]: N=2000 (4k x 4k covariance), 102 400-point grid."""
+    N, nx, ny = 2000, 320, 320
+    X, y = synthetic.drifter_snapshot(N, config_id=2)
+    Xs = synthetic.prediction_grid(X, nx, ny)
+    theta, noise = (1.3, 3.1, 0.2), 0.05
+    m = gp.HelmholtzGP(X, y, *theta, noise)
+    lml = m.fit()
+    mean, var = m.predict(Xs)
+    M = Xs.shape[0]
+    kss = orc.helmholtz_Kdiag(1, *theta)[0]
+    assert float(var.min()) >= 0.0 and float(var.max()) <= kss * (1 + 1e-12)
+    # sampled oracle (the CPU fit at this size takes seconds)
+    f = orc.fit(X, y, *theta, noise)
+    assert abs(lml - f["lml"]) <= 1e-6 * abs(f["lml"])
+    idx = np.random.default_rng(0).choice(M, 300, replace=False)
+    mo, vo = orc.predict(X, f, *theta, Xs[idx])
+    mg = np.concatenate([mean[idx].cpu().numpy(), mean[M + idx].cpu().numpy()])
+    vg = np.concatenate([var[idx].cpu().numpy(), var[M + idx].cpu().numpy()])
+    np.testing.assert_allclose(mg, mo, rtol=1e-8, atol=1e-9 * np.abs(mo).max())
+    np.testing.assert_allclose(vg, vo, rtol=1e-8, atol=1e-12)
+    # shard invariance: any partition of the grid gives bit-identical results
+    cut = 40001
+    m1, v1 = m.predict(Xs[:cut])
+    m2, v2 = m.predict(Xs[cut:])
+    assert torch.equal(torch.cat([m1[:cut], m2[:M - cut], m1[cut:], m2[M - cut:]]), mean)
+    assert torch.equal(torch.cat([v1[:cut], v2[:M - cut], v1[cut:], v2[M - cut:]]), var)
+    # linearity of the mean in the observations
+    y2 = np.roll(y, 17)
+    ma = gp.HelmholtzGP(X, y2, *theta, noise); ma.fit()
+    mb = gp.HelmholtzGP(X, y + 2.0 * y2, *theta, noise); mb.fit()
+    pa, _ = ma.predict(Xs[:5000]); pb, _ = mb.predict(Xs[:5000]); p0, _ = m.predict(Xs[:5000])
+    torch.testing.assert_close(pb, p0 + 2.0 * pa, rtol=1e-8, atol=1e-10)
+    # interpolation: tiny noise reproduces the observations at the observation sites
+    mt = gp.HelmholtzGP(X[:500], np.concatenate([y[:500], y[N:N + 500]]), 2.0, 2.0, 0.5, 1e-6); mt.fit()
+    pm, pv = mt.predict(X[:500])
+    assert float((pm - mt.y).abs().max()) < 5e-3
+    assert float(pv.max()) < 1e-4
