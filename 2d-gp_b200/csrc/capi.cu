@@ -77,19 +77,31 @@ __global__ void unpad_lower_kernel(const double* __restrict__ P, int npad, doubl
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS) dmma_peak_kernel(double* out, int iters) {
-    double c[16][2];
+// mode 0: DMMA only; 1: DFMA only; 2: 16 DMMA + 16 DFMA per iteration (shared FP64 pipe?)
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS) fp64_peak_kernel(double* out, int iters) {
+    double c[16][2], d[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) c[j][0] = c[j][1] = 0.0;
+    for (int j = 0; j < 16; ++j) { c[j][0] = c[j][1] = 0.0; d[j] = 1e-3 * j; }
     const double a = 1e-3 * (threadIdx.x & 31), b = 1e-3;
     for (int it = 0; it < iters; ++it) {
+        if (MODE == 0 || MODE == 2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dmma884(c[j][0], c[j][1], a, b);
+            for (int j = 0; j < 16; ++j) dmma884(c[j][0], c[j][1], a, b);
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { c[j][0] = fma(c[j][0], a, b); c[j][1] = fma(c[j][1], a, b); }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = fma(d[j], a, b);
+        }
     }
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s += c[j][0] + c[j][1];
-    if (s == 123.456) out[0] = s;      // keep the loop alive
+    for (int j = 0; j < 16; ++j) s += c[j][0] + c[j][1] + d[j];
+    if (s == 123.456) out[0] = s;      // keep the loops alive
 }
 
 // fit core shared by gp2d_fit and gp2d_lml_grad
@@ -232,8 +244,17 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
     return 0;
 }
 
+size_t gp2d_predict_workspace_bytes(int N, int M) {
+    if (N <= 0 || M <= 0) return 256;
+    long tiles = ((long)M + 63) / 64;
+    long ctas = predict_max_ctas();
+    if (tiles < ctas) ctas = tiles;
+    return align256((size_t)ctas * predict_panel_bytes(round_up(2 * N, TILE)));
+}
+
 int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, const double* Xs,
-                 int M, int64_t out_stride, double var_add, double* mean, double* var, void* stream) {
+                 int M, int64_t out_stride, double var_add, double* mean, double* var, void* ws,
+                 size_t ws_bytes, void* stream) {
     if (!fit_ws) return -1;
     if (N <= 0) return -2;
     if (!theta_ok(l_df, l_cf, ratio)) return -3;
@@ -244,9 +265,12 @@ int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double rat
     if (!mean) return -10;
     if (!var) return -11;
     FitLayout L = fit_layout(N);
+    if (!ws) return -12;
+    if (ws_bytes < predict_panel_bytes(L.npad)) return -13;
     return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Z), L.npad, L.npad, at<double>(fit_ws, L.off_alpha),
                                  at<double>(fit_ws, L.off_X), N, make_helm(l_df, l_cf, ratio), Xs, M,
-                                 (long)out_stride, var_add, mean, var, (cudaStream_t)stream));
+                                 (long)out_stride, var_add, mean, var, (double*)ws, ws_bytes,
+                                 (cudaStream_t)stream));
 }
 
 int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l_cf, double ratio,
@@ -294,10 +318,11 @@ int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, 
     if (M < 0) return -10;
     if (M > 0 && (!Xs || !mean || !var)) return -9;
     size_t wsb = gp2d_fit_workspace_bytes(N);
+    size_t pwsb = gp2d_predict_workspace_bytes(N, M);
     char* dev = nullptr;
     size_t in_b = align256(2 * (size_t)N * 8) * 2 + align256(2 * (size_t)(M > 0 ? M : 1) * 8);
     size_t out_b = align256(2 * (size_t)(M > 0 ? M : 1) * 8) * 2 + 256;
-    cudaError_t e = cudaMalloc(&dev, wsb + in_b + out_b);
+    cudaError_t e = cudaMalloc(&dev, wsb + in_b + out_b + pwsb);
     if (e != cudaSuccess) return cuda_rc(e);
     char* q = dev + wsb;
     double* dX = (double*)q; q += align256(2 * (size_t)N * 8);
@@ -305,7 +330,8 @@ int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, 
     double* dXs = (double*)q; q += align256(2 * (size_t)(M > 0 ? M : 1) * 8);
     double* dmean = (double*)q; q += align256(2 * (size_t)(M > 0 ? M : 1) * 8);
     double* dvar = (double*)q; q += align256(2 * (size_t)(M > 0 ? M : 1) * 8);
-    double* dlml = (double*)q; int* dinfo = (int*)(q + 64);
+    double* dlml = (double*)q; int* dinfo = (int*)(q + 64); q += 256;
+    void* dpws = (void*)q;
     int rc = 0, info = 0;
     cudaStream_t st = 0;
     do {
@@ -314,7 +340,7 @@ int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, 
         if (M > 0 && (e = cudaMemcpyAsync(dXs, Xs, 2 * (size_t)M * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         rc = gp2d_fit(dX, N, dy, l_df, l_cf, ratio, noise, jitter, dev, wsb, nullptr, dlml, dinfo, st);
         if (rc) break;
-        rc = gp2d_predict(dev, N, l_df, l_cf, ratio, dXs, M, M, include_noise ? noise : 0.0, dmean, dvar, st);
+        rc = gp2d_predict(dev, N, l_df, l_cf, ratio, dXs, M, M, include_noise ? noise : 0.0, dmean, dvar, dpws, pwsb, st);
         if (rc) break;
         if (M > 0) {
             if ((e = cudaMemcpyAsync(mean, dmean, 2 * (size_t)M * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
@@ -331,12 +357,21 @@ int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, 
 }
 
 /* ---- bring-up / test hooks (not part of include/gp2d.h) ---------------------------------- */
-// Register-resident DMMA.8x8x4 loop: the FP64 tensor-pipe ceiling bench.py reports against
-// (MEASURED_PEAKS.json carries no fp64 figure).  flops = ctas * 8 warps * iters * 16 * 512.
+// Register-resident FP64 loops: the tensor-pipe ceiling bench.py reports against
+// (MEASURED_PEAKS.json carries no fp64 figure).  mode 0: DMMA.8x8x4, flops = ctas * 8 warps *
+// iters * 16 * 512; mode 1: DFMA, flops = ctas * 256 threads * iters * 32 * 2; mode 2: both.
 int gp2d_dbg_fp64_peak(int iters, int ctas, double* out, void* stream) {
-    dmma_peak_kernel<<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    fp64_peak_kernel<0><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
     return cuda_rc(cudaGetLastError());
 }
+int gp2d_dbg_fp64_mode(int mode, int iters, int ctas, double* out, void* stream) {
+    if (mode == 0) fp64_peak_kernel<0><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    else if (mode == 1) fp64_peak_kernel<1><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    else fp64_peak_kernel<2><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    return cuda_rc(cudaGetLastError());
+}
+
+int gp2d_dbg_set_cta_threads(int nt) { set_cta_threads(nt); return get_cta_threads(); }
 
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,

@@ -7,7 +7,11 @@ namespace gp2d {
 
 constexpr int TILE = 128;      // every internal matrix dimension is padded to a multiple of this
 constexpr int BK = 16;         // k-depth of one shared-memory stage (doubles)
-constexpr int NTHREADS = 256;  // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
+constexpr int NTHREADS = 256;  // default CTA: 8 warps, 2 (M) x 4 (N), warp tile 64 x 32
+// CTA shapes: NT threads = (NT/128) warps along M x 4 warps along N over a 128 x 128 tile;
+// a warp owns MB(NT) x 4 DMMA accumulator blocks (8 x 8 each): 64x32 at NT=256, 32x32 at NT=512.
+__host__ __device__ constexpr int warps_m(int nt) { return nt / 128; }
+__host__ __device__ constexpr int mblocks(int nt) { return 16 / warps_m(nt); }
 constexpr int TILE_DOUBLES = TILE * BK;   // 2048 doubles = 16 KB per operand stage
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -48,11 +52,11 @@ __device__ __forceinline__ int mnmaj_off(int k, int r) {
 
 // Load one 128x16 operand tile with 16-byte cp.async, 4 chunks per thread.
 // KMAJ: global element (r,k) at g[r*ld + k];  MN-major: global element (k,r) at g[k*ld + r].
-template <bool MNMAJ>
+template <bool MNMAJ, int NT = NTHREADS>
 __device__ __forceinline__ void load_tile_async(double* smem, const double* g, long ld, int tid) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        int q = tid + it * NTHREADS;
+    for (int it = 0; it < 1024 / NT; ++it) {
+        int q = tid + it * NT;
         if (!MNMAJ) {
             int r = q >> 3, ch = q & 7;
             cp_async16(smem + r * BK + ((ch ^ ((r & 3) << 1)) << 1), g + (long)r * ld + (ch << 1));
@@ -63,17 +67,17 @@ __device__ __forceinline__ void load_tile_async(double* smem, const double* g, l
     }
 }
 
-// One BK=16 stage of DMMAs for a 64x32 warp tile.  acc[mb][nb][2].
-template <bool A_MN, bool B_MN>
+// One BK=16 stage of DMMAs for a (8*MB)x32 warp tile.  acc[mb][nb][2].
+template <bool A_MN, bool B_MN, int MB>
 __device__ __forceinline__ void mma_stage(const double* As, const double* Bs, int wm, int wn,
-                                          int lane, double (&acc)[8][4][2]) {
+                                          int lane, double (&acc)[MB][4][2]) {
     const int g = lane >> 2, tig = lane & 3;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-        double a[8], b[4];
+        double a[MB], b[4];
 #pragma unroll
-        for (int mb = 0; mb < 8; ++mb) {
-            int m = wm * 64 + mb * 8 + g;
+        for (int mb = 0; mb < MB; ++mb) {
+            int m = wm * (MB * 8) + mb * 8 + g;
             a[mb] = A_MN ? As[mnmaj_off(kk + tig, m)] : As[kmaj_off(m, kk + tig)];
         }
 #pragma unroll
@@ -82,7 +86,7 @@ __device__ __forceinline__ void mma_stage(const double* As, const double* Bs, in
             b[nb] = B_MN ? Bs[mnmaj_off(kk + tig, n)] : Bs[kmaj_off(n, kk + tig)];
         }
 #pragma unroll
-        for (int mb = 0; mb < 8; ++mb)
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
     }

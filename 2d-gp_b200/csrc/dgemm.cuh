@@ -35,8 +35,9 @@ struct GemmArgs {
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
+template <bool A_MN, bool B_MN, int NT>
+__global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
+    constexpr int MB = mblocks(NT), WM = warps_m(NT);
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + GEMM_STAGES * TILE_DOUBLES;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
     const int nk = (k1 - k0) / BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1;
+    const int wm = warp % WM, wn = warp / WM;
 
     const double* Ag = A_MN ? p.A + (long)k0 * p.lda + (long)tm * TILE
                             : p.A + (long)tm * TILE * p.lda + k0;
@@ -71,17 +72,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
     const long a_step = A_MN ? (long)BK * p.lda : BK;
     const long b_step = B_MN ? (long)BK * p.ldb : BK;
 
-    double acc[8][4][2];
+    double acc[MB][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MB; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile_async<A_MN>(As + s * TILE_DOUBLES, Ag + s * a_step, p.lda, tid);
-            load_tile_async<B_MN>(Bs + s * TILE_DOUBLES, Bg + s * b_step, p.ldb, tid);
+            load_tile_async<A_MN, NT>(As + s * TILE_DOUBLES, Ag + s * a_step, p.lda, tid);
+            load_tile_async<B_MN, NT>(Bs + s * TILE_DOUBLES, Bg + s * b_step, p.ldb, tid);
         }
         cp_async_commit();
     }
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
         int nxt = kt + GEMM_STAGES - 1;
         if (nxt < nk) {
             int s = nxt % GEMM_STAGES;
-            load_tile_async<A_MN>(As + s * TILE_DOUBLES, Ag + nxt * a_step, p.lda, tid);
-            load_tile_async<B_MN>(Bs + s * TILE_DOUBLES, Bg + nxt * b_step, p.ldb, tid);
+            load_tile_async<A_MN, NT>(As + s * TILE_DOUBLES, Ag + nxt * a_step, p.lda, tid);
+            load_tile_async<B_MN, NT>(Bs + s * TILE_DOUBLES, Bg + nxt * b_step, p.ldb, tid);
         }
         cp_async_commit();
         int s = kt % GEMM_STAGES;
-        mma_stage<A_MN, B_MN>(As + s * TILE_DOUBLES, Bs + s * TILE_DOUBLES, wm, wn, lane, acc);
+        mma_stage<A_MN, B_MN, MB>(As + s * TILE_DOUBLES, Bs + s * TILE_DOUBLES, wm, wn, lane, acc);
     }
     cp_async_wait<0>();
 
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
     const int g = lane >> 2, tig = lane & 3;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-    for (int mb = 0; mb < 8; ++mb) {
-        long row = (long)tm * TILE + wm * 64 + mb * 8 + g;
+    for (int mb = 0; mb < MB; ++mb) {
+        long row = (long)tm * TILE + wm * (MB * 8) + mb * 8 + g;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
             long col = (long)tn * TILE + wn * 32 + nb * 8 + 2 * tig;
@@ -126,5 +127,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmArgs p) {
 // host launcher (dgemm.cu)
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& args, cudaStream_t stream);
 cudaError_t dgemm_init();
+// CTA shape used by GEMM / predict launches: 256 (8 warps, 64x32 warp tiles) or 512.
+void set_cta_threads(int nt);
+int get_cta_threads();
 
 }  // namespace gp2d

@@ -28,37 +28,48 @@ inline HelmParams make_helm(double l_df, double l_cf, double ratio) {
     return p;
 }
 
-// exp(x) for x <= 0 (covariance envelopes).  Cody-Waite range reduction to
-// |f| <= ln2/2 and a degree-13 Taylor/Horner polynomial: ~1 ulp, no table, no branches
-// beyond the underflow clamp.  Cheaper than libdevice exp() on the shared FP64 pipe.
+// exp(x) for x <= 0 (covariance envelopes): x = (64 k + j) ln2/64 + r, |r| <= ln2/128,
+//   exp(x) = 2^k * 2^(j/64) * p5(r)
+// 64-entry table of correctly rounded 2^(j/64), two-term Cody-Waite reduction and a
+// degree-5 polynomial (truncation 3.5e-17): ~1 ulp with 10 FP64-pipe operations and a
+// dependency chain half as long as a table-free degree-13 evaluation.  The DMMA and
+// DFMA instructions share one FP64 pipe on sm_100a (measured), so every operation
+// saved here is tensor-pipe time in the fused predictive kernel.
+__device__ const double EXP2_TAB[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
 __device__ __forceinline__ double exp_neg(double x) {
-    x = fmax(x, -745.0);
-    const double L2E = 1.4426950408889634074;
-    const double LN2_HI = 6.93147180369123816490e-01;
-    const double LN2_LO = 1.90821492927058770002e-10;
-    double t = rint(x * L2E);
-    double f = fma(-t, LN2_HI, x);
-    f = fma(-t, LN2_LO, f);
-    double p = 1.605904383682161459939e-10;            // 1/13!
-    p = fma(p, f, 2.087675698786809897921e-09);         // 1/12!
-    p = fma(p, f, 2.505210838544171877505e-08);         // 1/11!
-    p = fma(p, f, 2.755731922398589065256e-07);         // 1/10!
-    p = fma(p, f, 2.755731922398589065256e-06);         // 1/9!
-    p = fma(p, f, 2.480158730158730158730e-05);         // 1/8!
-    p = fma(p, f, 1.984126984126984126984e-04);         // 1/7!
-    p = fma(p, f, 1.388888888888888888889e-03);         // 1/6!
-    p = fma(p, f, 8.333333333333333333333e-03);         // 1/5!
-    p = fma(p, f, 4.166666666666666666667e-02);         // 1/4!
-    p = fma(p, f, 1.666666666666666666667e-01);         // 1/3!
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    // scale by 2^t; t in [-1075, 0]: split so denormal results stay correct
-    int ti = (int)t;
-    int t1 = ti >> 1, t2 = ti - t1;
-    double s1 = __longlong_as_double((long long)(1023 + t1) << 52);
-    double s2 = __longlong_as_double((long long)(1023 + t2) << 52);
-    return p * s1 * s2;
+    x = fmax(x, -708.0);
+    const double INV = 0x1.71547652b82fep+6;      // 64 / ln 2
+    const double C_HI = 0x1.62e42fef80000p-7;    // ln2/64, low 18 bits zero: n * C_HI exact
+    const double C_LO = 0x1.1cf79abc9e3b4p-42;
+    const double nd = rint(x * INV);
+    const int ni = (int)nd;
+    double r = fma(-nd, C_HI, x);
+    r = fma(-nd, C_LO, r);
+    const double r2 = r * r;
+    const double a = fma(r, 1.0 / 6.0, 0.5);            // 1/2 + r/6
+    const double b = fma(r, 1.0 / 120.0, 1.0 / 24.0);   // 1/24 + r/120
+    double p = fma(r2, fma(r2, b, a), r) + 1.0;         // 1 + r + r^2 a + r^4 b
+    // 2^(j/64) with k added to its exponent field (k >= -1022: stays normal)
+    const long long tb = __double_as_longlong(EXP2_TAB[ni & 63]) + ((long long)(ni >> 6) << 52);
+    return p * __longlong_as_double(tb);
 }
 
 // 2x2 block for separation (d1, d2).

@@ -25,20 +25,37 @@ namespace gp2d {
 // ------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------
+static int g_cta_threads = 256;
+void set_cta_threads(int nt) { g_cta_threads = (nt == 512) ? 512 : 256; }
+int get_cta_threads() { return g_cta_threads; }
+
+template <bool A_MN, bool B_MN, int NT>
+static cudaError_t gemm_attr() {
+    return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+}
+
 cudaError_t dgemm_init() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e;
-    e = cudaFuncSetAttribute(dgemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    if ((e = gemm_attr<false, false, 256>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<false, true, 256>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<true, true, 256>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<true, false, 256>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<false, false, 512>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<false, true, 512>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<true, true, 512>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<true, false, 512>()) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
+}
+
+template <int NT>
+static void gemm_launch(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
+    if (!a_mn && !b_mn) dgemm_kernel<false, false, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
+    else if (!a_mn && b_mn) dgemm_kernel<false, true, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
+    else if (a_mn && b_mn) dgemm_kernel<true, true, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
+    else dgemm_kernel<true, false, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
 }
 
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t st) {
@@ -49,10 +66,8 @@ cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t s
     int tm = a.M / TILE, tn = a.N / TILE;
     if (a.lower_out && tm != tn) return cudaErrorInvalidValue;
     unsigned grid = a.lower_out ? (unsigned)((long)tm * (tm + 1) / 2) : (unsigned)(tm * tn);
-    if (!a_mn && !b_mn) dgemm_kernel<false, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(a);
-    else if (!a_mn && b_mn) dgemm_kernel<false, true><<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(a);
-    else if (a_mn && b_mn) dgemm_kernel<true, true><<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(a);
-    else dgemm_kernel<true, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(a);
+    if (g_cta_threads == 512) gemm_launch<512>(a_mn, b_mn, grid, a, st);
+    else gemm_launch<256>(a_mn, b_mn, grid, a, st);
     return cudaGetLastError();
 }
 

@@ -35,9 +35,14 @@ cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int
 int grad_sums_block_partials(int N, int M);
 
 // predict.cu ------------------------------------------------------------------------------
+// scratch: one [npad x 128] K* panel per resident CTA (at most one CTA per SM is launched;
+// fewer panels only reduce the grid).
 cudaError_t predict_fused(const double* Z, long ldz, int npad, const double* alpha_int,
                           const double* X, int N, const HelmParams& hp, const double* Xs, int M,
-                          long out_stride, double var_add, double* mean, double* var, cudaStream_t st);
+                          long out_stride, double var_add, double* mean, double* var,
+                          double* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t predict_panel_bytes(int npad);
+int predict_max_ctas();
 
 // grad.cu ---------------------------------------------------------------------------------
 // From Kinv (lower, interleaved, padded) and alpha_int: out4 = d LML / d(l_df, l_cf, ratio, noise).

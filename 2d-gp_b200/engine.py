@@ -132,6 +132,7 @@ class HelmholtzGP:
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.X.device)
         self._scal = torch.zeros(8, dtype=torch.float64, device=self.X.device)
         self._info = torch.zeros(1, dtype=torch.int32, device=self.X.device)
+        self._pws = None                 # predict scratch (K* panels), grown on demand
         self.fitted = False
         self.lml = None
 
@@ -176,9 +177,12 @@ class HelmholtzGP:
         var = out_var if out_var is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
         if M:
             with torch.cuda.device(self.device):
+                nb = lib.gp2d_predict_workspace_bytes(self.N, M)
+                if self._pws is None or self._pws.numel() < nb:
+                    self._pws = torch.empty(nb, dtype=torch.uint8, device=self.device)
                 check(lib.gp2d_predict(_ptr(self.ws), self.N, self.l_df, self.l_cf, self.ratio, _ptr(Xsd), M, M,
-                                       self.noise if include_noise else 0.0, _ptr(mean), _ptr(var), _stream()),
-                      "gp2d_predict")
+                                       self.noise if include_noise else 0.0, _ptr(mean), _ptr(var),
+                                       _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_predict")
         return mean, var
 
     def lml_and_grad(self, reference_compat=False):

@@ -86,10 +86,15 @@ int gp2d_fit(const double* X, int N, const double* y,
  * noise variance to reproduce GPy's predict, 0 for sklearn/GP_laser).
  * Replaces GPy model.predict (krig.py:543-544,600-601), getMean + diag of Cov
  * (GP_scripts.py:44-46; GP_laser.py:129-131) and sklearn predict(return_std=True)
- * (krig.py:194).  Independent grid shards may be issued on different streams / GPUs. */
+ * (krig.py:194).  Independent grid shards may be issued on different streams / GPUs.
+ *
+ * ws is a per-call scratch (not shared between concurrent calls): one [npad x 128] K*
+ * panel per streaming multiprocessor; gp2d_predict_workspace_bytes(N, M) sizes it for the
+ * current device.  A smaller buffer is accepted down to one panel (fewer resident CTAs). */
+size_t gp2d_predict_workspace_bytes(int N, int M);
 int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio,
                  const double* Xs, int M, int64_t out_stride, double var_add,
-                 double* mean, double* var, void* stream);
+                 double* mean, double* var, void* ws, size_t ws_bytes, void* stream);
 
 /* LML and its gradient in one pass: out5 = (LML, dLML/dl_df, dLML/dl_cf, dLML/dratio,
  * dLML/dnoise).  Leaves a valid fit state in ws.  Replaces one objective evaluation of

@@ -55,7 +55,7 @@ def test_workspace_queries_and_argument_validation(lib):
     assert L.gp2d_fit_workspace_bytes(0) == 0
     assert L.gp2d_potrf_workspace_bytes(1000) >= 2 * 1024 * 1024 * 8
     assert L.gp2d_kernel_build(None, 4, None, 4, 1.0, 1.0, 0.5, 0.0, None, 8, None) == -1
-    assert L.gp2d_predict(None, 4, 1.0, 1.0, 0.5, None, 1, 1, 0.0, None, None, None) == -1
+    assert L.gp2d_predict(None, 4, 1.0, 1.0, 0.5, None, 1, 1, 0.0, None, None, None, 0, None) == -1
 
 
 def test_engine_fails_loudly_without_cuda():

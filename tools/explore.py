@@ -1,0 +1,128 @@
+"""GPU exploration harness (not part of the product): FP64 pipe microbenchmarks and
+per-stage timings under the two CTA shapes.  Usage: python tools/explore.py [what ...]"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gp2d_b200 as gp
+from gp2d_b200 import synthetic
+from gp2d_b200._lib import lib
+
+dev = torch.device("cuda:0")
+lib.gp2d_dbg_fp64_mode.restype = C.c_int
+lib.gp2d_dbg_fp64_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.gp2d_dbg_set_cta_threads.restype = C.c_int
+lib.gp2d_dbg_set_cta_threads.argtypes = [C.c_int]
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def timeit(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def micro():
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    iters = 20000
+    for ctas in (148, 296, 592):
+        for mode in (0, 1, 2):
+            t = timeit(lambda: lib.gp2d_dbg_fp64_mode(mode, iters, ctas, out.data_ptr(), st))
+            dmma = ctas * 8 * iters * 16 * 512 if mode in (0, 2) else 0
+            dfma = ctas * 256 * iters * (32 if mode == 1 else 16 if mode == 2 else 0) * 2
+            print("micro ctas=%d (%d warps/SMSP) mode=%d: %.3f ms  DMMA %.2f TF/s  DFMA %.2f TF/s  sum %.2f" % (
+                ctas, ctas * 8 // (148 * 4), mode, t * 1e3, dmma / t / 1e12, dfma / t / 1e12, (dmma + dfma) / t / 1e12))
+
+
+def stages(N=2000, grid=(320, 320), theta=(1.3, 3.1, 0.2)):
+    X, y = synthetic.drifter_snapshot(N, config_id=2)
+    Xs = synthetic.prediction_grid(X, *grid)
+    M = Xs.shape[0]
+    n = 2 * N
+    for nt in (256, 512):
+        lib.gp2d_dbg_set_cta_threads(nt)
+        m = gp.HelmholtzGP(X, y, *theta, 0.05)
+        Xsd = gp.as_dev(Xs)
+        t_fit = timeit(lambda: m.fit_async())
+        t_pred = timeit(lambda: m.predict(Xsd))
+        t_grad = timeit(lambda: m.lml_and_grad())
+        fl = float(n) * n * 2 * M + 2.0 * n * 2 * M
+        print("stages nt=%d N=%d M=%d: fit %.3f ms  predict %.3f ms (%.2f TF/s)  lml+grad %.3f ms" % (
+            nt, N, M, t_fit * 1e3, t_pred * 1e3, fl / t_pred / 1e12, t_grad * 1e3))
+        m2 = gp.HelmholtzGP(X, y, 2.0, 2.0, 0.5, 0.05)
+        t_pred2 = timeit(lambda: m2.predict(Xsd))
+        print("   equal length scales (one exp): predict %.3f ms (%.2f TF/s)" % (t_pred2 * 1e3, fl / t_pred2 / 1e12))
+    lib.gp2d_dbg_set_cta_threads(256)
+
+
+def potrf_sizes():
+    for nt in (256, 512):
+        lib.gp2d_dbg_set_cta_threads(nt)
+        for n in (1024, 4096, 8192, 16384):
+            g = torch.Generator(device=dev).manual_seed(n)
+            B = torch.randn(n, 256, generator=g, dtype=torch.float64, device=dev)
+            A = B @ B.t() / 256 + torch.eye(n, dtype=torch.float64, device=dev)
+            nb_ws = lib.gp2d_potrf_workspace_bytes(n)
+            ws = torch.empty(nb_ws, dtype=torch.uint8, device=dev)
+            info = torch.zeros(1, dtype=torch.int32, device=dev)
+            Aw = torch.empty_like(A)
+            st = torch.cuda.current_stream().cuda_stream
+
+            def run():
+                Aw.copy_(A)
+                lib.gp2d_potrf(Aw.data_ptr(), n, n, ws.data_ptr(), nb_ws, info.data_ptr(), st)
+            t_copy = timeit(lambda: Aw.copy_(A))
+            t = timeit(run) - t_copy
+            print("potrf nt=%d n=%d: %.3f ms  %.2f TF/s (n^3/3)  info=%d" % (nt, n, t * 1e3, n ** 3 / 3 / t / 1e12, int(info.item())))
+            del A, B, Aw, ws
+    lib.gp2d_dbg_set_cta_threads(256)
+
+
+def gemm():
+    lib.gp2d_dbg_gemm.restype = C.c_int
+    lib.gp2d_dbg_gemm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                  C.c_int, C.c_void_p]
+    st = torch.cuda.current_stream().cuda_stream
+    for nt in (256, 512):
+        lib.gp2d_dbg_set_cta_threads(nt)
+        for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 4096), (16384, 16384, 128), (2048, 2048, 2048)]:
+            A = torch.randn(max(M, K), max(M, K), dtype=torch.float64, device=dev)
+            B = torch.randn(max(N, K), max(N, K), dtype=torch.float64, device=dev)
+            Cm = torch.zeros(M, N, dtype=torch.float64, device=dev)
+            for (a_mn, b_mn) in [(0, 0), (0, 1), (1, 1)]:
+                for beta in (0.0, 1.0):
+                    t = timeit(lambda: lib.gp2d_dbg_gemm(a_mn, b_mn, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                                         Cm.data_ptr(), Cm.stride(0), M, N, K, 1.0, beta, 0, 0, st))
+                    print("gemm nt=%d %dx%dx%d a_mn=%d b_mn=%d beta=%g: %.3f ms %.2f TF/s" % (
+                        nt, M, N, K, a_mn, b_mn, beta, t * 1e3, 2.0 * M * N * K / t / 1e12))
+            del A, B, Cm
+    lib.gp2d_dbg_set_cta_threads(256)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["micro", "stages", "potrf"]
+    if "micro" in what:
+        micro()
+    if "stages" in what:
+        stages()
+    if "potrf" in what:
+        potrf_sizes()
+    if "gemm" in what:
+        gemm()
