@@ -97,6 +97,14 @@ __global__ void __launch_bounds__(NTHREADS) fp64_peak_kernel(double* out, int it
 #pragma unroll
             for (int j = 0; j < 16; ++j) d[j] = fma(d[j], a, b);
         }
+        if (MODE == 3) {      // one dependent DFMA chain: latency = time / (16 * iters)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[0] = fma(d[0], a, b);
+        }
+        if (MODE == 4) {      // one dependent DMMA chain
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dmma884(c[0][0], c[0][1], a, b);
+        }
     }
     double s = 0.0;
 #pragma unroll
@@ -367,11 +375,15 @@ int gp2d_dbg_fp64_peak(int iters, int ctas, double* out, void* stream) {
 int gp2d_dbg_fp64_mode(int mode, int iters, int ctas, double* out, void* stream) {
     if (mode == 0) fp64_peak_kernel<0><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
     else if (mode == 1) fp64_peak_kernel<1><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
-    else fp64_peak_kernel<2><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    else if (mode == 2) fp64_peak_kernel<2><<<ctas, NTHREADS, 0, (cudaStream_t)stream>>>(out, iters);
+    else if (mode == 3) fp64_peak_kernel<3><<<ctas, 32, 0, (cudaStream_t)stream>>>(out, iters);
+    else fp64_peak_kernel<4><<<ctas, 32, 0, (cudaStream_t)stream>>>(out, iters);
     return cuda_rc(cudaGetLastError());
 }
 
 int gp2d_dbg_set_cta_threads(int nt) { set_cta_threads(nt); return get_cta_threads(); }
+
+int gp2d_dbg_set_small_tile_threshold(int t) { set_small_tile_threshold(t); return t; }
 
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,

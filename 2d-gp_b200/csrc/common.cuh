@@ -12,6 +12,16 @@ constexpr int NTHREADS = 256;  // default CTA: 8 warps, 2 (M) x 4 (N), warp tile
 // a warp owns MB(NT) x 4 DMMA accumulator blocks (8 x 8 each): 64x32 at NT=256, 32x32 at NT=512.
 __host__ __device__ constexpr int warps_m(int nt) { return nt / 128; }
 __host__ __device__ constexpr int mblocks(int nt) { return 16 / warps_m(nt); }
+// General form: a TS x TS CTA tile (TS = 128, or 64 for small problems) with NT threads:
+// TS/32 warps along N (32 columns each), the rest along M.
+template <int TS_, int NT_>
+struct TileCfg {
+    static constexpr int TS = TS_, NT = NT_;
+    static constexpr int WN = TS / 32;
+    static constexpr int WM = (NT / 32) / WN;
+    static constexpr int MB = TS / (8 * WM);
+    static constexpr int STAGE_DOUBLES = TS * BK;
+};
 constexpr int TILE_DOUBLES = TILE * BK;   // 2048 doubles = 16 KB per operand stage
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -46,29 +56,30 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ __forceinline__ int kmaj_off(int r, int k) {
     return r * BK + ((((k >> 1) ^ ((r & 3) << 1)) << 1) | (k & 1));
 }
+template <int TS = TILE>
 __device__ __forceinline__ int mnmaj_off(int k, int r) {
-    return k * TILE + ((((r >> 1) ^ ((k & 3) << 1)) << 1) | (r & 1));
+    return k * TS + ((((r >> 1) ^ ((k & 3) << 1)) << 1) | (r & 1));
 }
 
 // Load one 128x16 operand tile with 16-byte cp.async, 4 chunks per thread.
 // KMAJ: global element (r,k) at g[r*ld + k];  MN-major: global element (k,r) at g[k*ld + r].
-template <bool MNMAJ, int NT = NTHREADS>
+template <bool MNMAJ, int NT = NTHREADS, int TS = TILE>
 __device__ __forceinline__ void load_tile_async(double* smem, const double* g, long ld, int tid) {
 #pragma unroll
-    for (int it = 0; it < 1024 / NT; ++it) {
+    for (int it = 0; it < TS * 8 / NT; ++it) {
         int q = tid + it * NT;
         if (!MNMAJ) {
             int r = q >> 3, ch = q & 7;
             cp_async16(smem + r * BK + ((ch ^ ((r & 3) << 1)) << 1), g + (long)r * ld + (ch << 1));
         } else {
-            int k = q >> 6, ch = q & 63;
-            cp_async16(smem + k * TILE + ((ch ^ ((k & 3) << 1)) << 1), g + (long)k * ld + (ch << 1));
+            int k = q / (TS / 2), ch = q % (TS / 2);
+            cp_async16(smem + k * TS + ((ch ^ ((k & 3) << 1)) << 1), g + (long)k * ld + (ch << 1));
         }
     }
 }
 
 // One BK=16 stage of DMMAs for a (8*MB)x32 warp tile.  acc[mb][nb][2].
-template <bool A_MN, bool B_MN, int MB>
+template <bool A_MN, bool B_MN, int MB, int TS = TILE>
 __device__ __forceinline__ void mma_stage(const double* As, const double* Bs, int wm, int wn,
                                           int lane, double (&acc)[MB][4][2]) {
     const int g = lane >> 2, tig = lane & 3;
@@ -78,12 +89,12 @@ __device__ __forceinline__ void mma_stage(const double* As, const double* Bs, in
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
             int m = wm * (MB * 8) + mb * 8 + g;
-            a[mb] = A_MN ? As[mnmaj_off(kk + tig, m)] : As[kmaj_off(m, kk + tig)];
+            a[mb] = A_MN ? As[mnmaj_off<TS>(kk + tig, m)] : As[kmaj_off(m, kk + tig)];
         }
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
             int n = wn * 32 + nb * 8 + g;
-            b[nb] = B_MN ? Bs[mnmaj_off(kk + tig, n)] : Bs[kmaj_off(n, kk + tig)];
+            b[nb] = B_MN ? Bs[mnmaj_off<TS>(kk + tig, n)] : Bs[kmaj_off(n, kk + tig)];
         }
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb)

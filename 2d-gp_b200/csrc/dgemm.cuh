@@ -6,9 +6,10 @@
 // B operand: element (n,k) at B[n*ldb + k] (K-major, i.e. C = A * B^T) or
 //            B[k*ldb + n] (MN-major, i.e. C = A * B).
 // M, N are multiples of 128 and K of 16; triangular structure is exploited by clipping the
-// k-range per 128x128 output tile (KR_* flags) and by skipping tiles above the diagonal
-// (lower_out).  128x128x16 CTA tile, 4-stage cp.async pipeline, XOR-swizzled shared
-// memory, 8 warps x (64x32) DMMA.8x8x4 register tiles.
+// k-range per output tile (KR_* flags) and by skipping tiles above the diagonal
+// (lower_out).  TS x TS x 16 CTA tile (TS = 128 with 8 warps of 64x32, or TS = 64 with
+// 4 warps of 32x32 for problems too small to fill 148 SMs with 128-tiles), 4-stage cp.async
+// pipeline, XOR-swizzled shared memory, DMMA.8x8x4 register tiles.
 #pragma once
 #include "common.cuh"
 
@@ -16,10 +17,10 @@ namespace gp2d {
 
 enum : int {
     KR_FULL = 0,
-    KR_LE_M = 1,   // k <  (tm+1)*128 : A operand lower-triangular in (m,k)
-    KR_LE_N = 2,   // k <  (tn+1)*128 : B operand lower-triangular in (n,k)  (Z^T as K-major B)
-    KR_GE_N = 4,   // k >= tn*128     : B operand (k,n) lower-triangular, zero for k < n
-    KR_GE_M = 8,   // k >= tm*128     : A operand (k,m) lower-triangular, zero for k < m
+    KR_LE_M = 1,   // k <  (tm+1)*TS : A operand lower-triangular in (m,k)
+    KR_LE_N = 2,   // k <  (tn+1)*TS : B operand lower-triangular in (n,k)  (Z^T as K-major B)
+    KR_GE_N = 4,   // k >= tn*TS     : B operand (k,n) lower-triangular, zero for k < n
+    KR_GE_M = 8,   // k >= tm*TS     : A operand (k,m) lower-triangular, zero for k < m
 };
 
 struct GemmArgs {
@@ -33,14 +34,16 @@ struct GemmArgs {
 };
 
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB (TS = 128)
+constexpr int gemm_smem_bytes(int ts) { return GEMM_STAGES * 2 * ts * BK * (int)sizeof(double); }
 
-template <bool A_MN, bool B_MN, int NT>
-__global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
-    constexpr int MB = mblocks(NT), WM = warps_m(NT);
+template <bool A_MN, bool B_MN, int NT, int TS>
+__global__ void __launch_bounds__(NT, (TS == 64 ? 3 : 1)) dgemm_kernel(GemmArgs p) {
+    using Cfg = TileCfg<TS, NT>;
+    constexpr int MB = Cfg::MB, WM = Cfg::WM, SD = Cfg::STAGE_DOUBLES;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
-    double* Bs = smem + GEMM_STAGES * TILE_DOUBLES;
+    double* Bs = smem + GEMM_STAGES * SD;
 
     int tm, tn;
     if (p.lower_out) {
@@ -51,24 +54,24 @@ __global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
         while ((long)tm * (tm + 1) / 2 > t) --tm;
         tn = t - tm * (tm + 1) / 2;
     } else {
-        int tiles_n = p.N / TILE;
+        int tiles_n = p.N / TS;
         tm = blockIdx.x / tiles_n;
         tn = blockIdx.x % tiles_n;
     }
     int k0 = 0, k1 = p.K;
-    if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TILE);
-    if (p.krule & KR_LE_N) k1 = min(k1, (tn + 1) * TILE);
-    if (p.krule & KR_GE_N) k0 = max(k0, tn * TILE);
-    if (p.krule & KR_GE_M) k0 = max(k0, tm * TILE);
+    if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TS);
+    if (p.krule & KR_LE_N) k1 = min(k1, (tn + 1) * TS);
+    if (p.krule & KR_GE_N) k0 = max(k0, tn * TS);
+    if (p.krule & KR_GE_M) k0 = max(k0, tm * TS);
     const int nk = (k1 - k0) / BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
 
-    const double* Ag = A_MN ? p.A + (long)k0 * p.lda + (long)tm * TILE
-                            : p.A + (long)tm * TILE * p.lda + k0;
-    const double* Bg = B_MN ? p.B + (long)k0 * p.ldb + (long)tn * TILE
-                            : p.B + (long)tn * TILE * p.ldb + k0;
+    const double* Ag = A_MN ? p.A + (long)k0 * p.lda + (long)tm * TS
+                            : p.A + (long)tm * TS * p.lda + k0;
+    const double* Bg = B_MN ? p.B + (long)k0 * p.ldb + (long)tn * TS
+                            : p.B + (long)tn * TS * p.ldb + k0;
     const long a_step = A_MN ? (long)BK * p.lda : BK;
     const long b_step = B_MN ? (long)BK * p.ldb : BK;
 
@@ -81,8 +84,8 @@ __global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile_async<A_MN, NT>(As + s * TILE_DOUBLES, Ag + s * a_step, p.lda, tid);
-            load_tile_async<B_MN, NT>(Bs + s * TILE_DOUBLES, Bg + s * b_step, p.ldb, tid);
+            load_tile_async<A_MN, NT, TS>(As + s * SD, Ag + s * a_step, p.lda, tid);
+            load_tile_async<B_MN, NT, TS>(Bs + s * SD, Bg + s * b_step, p.ldb, tid);
         }
         cp_async_commit();
     }
@@ -92,12 +95,12 @@ __global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
         int nxt = kt + GEMM_STAGES - 1;
         if (nxt < nk) {
             int s = nxt % GEMM_STAGES;
-            load_tile_async<A_MN, NT>(As + s * TILE_DOUBLES, Ag + nxt * a_step, p.lda, tid);
-            load_tile_async<B_MN, NT>(Bs + s * TILE_DOUBLES, Bg + nxt * b_step, p.ldb, tid);
+            load_tile_async<A_MN, NT, TS>(As + s * SD, Ag + nxt * a_step, p.lda, tid);
+            load_tile_async<B_MN, NT, TS>(Bs + s * SD, Bg + nxt * b_step, p.ldb, tid);
         }
         cp_async_commit();
         int s = kt % GEMM_STAGES;
-        mma_stage<A_MN, B_MN, MB>(As + s * TILE_DOUBLES, Bs + s * TILE_DOUBLES, wm, wn, lane, acc);
+        mma_stage<A_MN, B_MN, MB, TS>(As + s * SD, Bs + s * SD, wm, wn, lane, acc);
     }
     cp_async_wait<0>();
 
@@ -106,10 +109,10 @@ __global__ void __launch_bounds__(NT, 1) dgemm_kernel(GemmArgs p) {
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
-        long row = (long)tm * TILE + wm * (MB * 8) + mb * 8 + g;
+        long row = (long)tm * TS + wm * (MB * 8) + mb * 8 + g;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
-            long col = (long)tn * TILE + wn * 32 + nb * 8 + 2 * tig;
+            long col = (long)tn * TS + wn * 32 + nb * 8 + 2 * tig;
             double2* dst = reinterpret_cast<double2*>(p.C + row * p.ldc + col);
             double2 v;
             v.x = alpha * acc[mb][nb][0];
@@ -130,5 +133,6 @@ cudaError_t dgemm_init();
 // CTA shape used by GEMM / predict launches: 256 (8 warps, 64x32 warp tiles) or 512.
 void set_cta_threads(int nt);
 int get_cta_threads();
+void set_small_tile_threshold(int tiles128);
 
 }  // namespace gp2d

@@ -29,45 +29,58 @@ static int g_cta_threads = 256;
 void set_cta_threads(int nt) { g_cta_threads = (nt == 512) ? 512 : 256; }
 int get_cta_threads() { return g_cta_threads; }
 
-template <bool A_MN, bool B_MN, int NT>
+template <bool A_MN, bool B_MN, int NT, int TS>
 static cudaError_t gemm_attr() {
-    return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes(TS));
+}
+template <int NT, int TS>
+static cudaError_t gemm_attr_all() {
+    cudaError_t e;
+    if ((e = gemm_attr<false, false, NT, TS>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<false, true, NT, TS>()) != cudaSuccess) return e;
+    if ((e = gemm_attr<true, true, NT, TS>()) != cudaSuccess) return e;
+    return gemm_attr<true, false, NT, TS>();
 }
 
 cudaError_t dgemm_init() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e;
-    if ((e = gemm_attr<false, false, 256>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<false, true, 256>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<true, true, 256>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<true, false, 256>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<false, false, 512>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<false, true, 512>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<true, true, 512>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<true, false, 512>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_all<256, 128>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_all<512, 128>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_all<128, 64>()) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
 
-template <int NT>
+template <int NT, int TS>
 static void gemm_launch(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
-    if (!a_mn && !b_mn) dgemm_kernel<false, false, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
-    else if (!a_mn && b_mn) dgemm_kernel<false, true, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
-    else if (a_mn && b_mn) dgemm_kernel<true, true, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
-    else dgemm_kernel<true, false, NT><<<grid, NT, GEMM_SMEM_BYTES, st>>>(a);
+    constexpr int SM = gemm_smem_bytes(TS);
+    if (!a_mn && !b_mn) dgemm_kernel<false, false, NT, TS><<<grid, NT, SM, st>>>(a);
+    else if (!a_mn && b_mn) dgemm_kernel<false, true, NT, TS><<<grid, NT, SM, st>>>(a);
+    else if (a_mn && b_mn) dgemm_kernel<true, true, NT, TS><<<grid, NT, SM, st>>>(a);
+    else dgemm_kernel<true, false, NT, TS><<<grid, NT, SM, st>>>(a);
 }
+
+// 128-tiles below this count leave most of the 148 SMs idle: switch to 64x64 tiles
+static int g_small_tile_threshold = 296;
+void set_small_tile_threshold(int t) { g_small_tile_threshold = t; }
 
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t st) {
     if (a.M % TILE || a.N % TILE || a.K % BK || a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
     if ((a.lda & 1) || (a.ldb & 1) || (a.ldc & 1)) return cudaErrorInvalidValue;
     cudaError_t e = dgemm_init();
     if (e != cudaSuccess) return e;
-    int tm = a.M / TILE, tn = a.N / TILE;
+    long tm = a.M / TILE, tn = a.N / TILE;
     if (a.lower_out && tm != tn) return cudaErrorInvalidValue;
-    unsigned grid = a.lower_out ? (unsigned)((long)tm * (tm + 1) / 2) : (unsigned)(tm * tn);
-    if (g_cta_threads == 512) gemm_launch<512>(a_mn, b_mn, grid, a, st);
-    else gemm_launch<256>(a_mn, b_mn, grid, a, st);
+    long grid = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
+    if (grid < g_small_tile_threshold) {
+        tm *= 2; tn *= 2;
+        grid = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
+        gemm_launch<128, 64>(a_mn, b_mn, (unsigned)grid, a, st);
+    } else if (g_cta_threads == 512) gemm_launch<512, 128>(a_mn, b_mn, (unsigned)grid, a, st);
+    else gemm_launch<256, 128>(a_mn, b_mn, (unsigned)grid, a, st);
     return cudaGetLastError();
 }
 
@@ -76,61 +89,109 @@ cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t s
 // above the diagonal), log(diag L) and LAPACK-style info (1-based index of the first
 // non-positive pivot, first failure wins).
 // ------------------------------------------------------------------------------------
+// One CTA, 256 threads as a 16 x 16 grid; thread (tr, tc) keeps the 8 x 8 elements
+// (i, c) = (tr + 16 a, tc + 16 b) in registers (2-D cyclic, so the shrinking active window
+// stays balanced).  A single in-place sweep does both jobs, in UNSCALED form (LDL^T-like):
+// with d_j the pivot and q = column j of the Schur complement, at step j every row i > j gets
+//     M[i,c] -= (q_i / d_j) * m_c,   m_c = q_c       (c > j : Cholesky trailing update)
+//                                    m_c = Y[j,c]    (c <= j: inverse accumulator, Y[j,j] = 1)
+// and the slots of column j are recycled for the inverse (Y[:,j] starts at 0).  At the end
+//     L[i,j] = q_i / sqrt(d_j),   Z[i,c] = Y[i,c] / sqrt(d_i)          (Z = L^-1).
+// Per step the critical path is one barrier, one reciprocal and one rank-1 update from
+// registers: the column is broadcast through shared memory, the row comes from the owning
+// lane of the same half-warp by shuffle (tc = tid>>4, tr = tid&15), every register index is
+// static (outer loop over j>>4 unrolled), and all sqrt/log work is deferred.
 constexpr int LEAF_LD = TILE + 1;
 constexpr int LEAF_SMEM_BYTES = TILE * LEAF_LD * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0) {
-    extern __shared__ double S[];
-    const int tid = threadIdx.x;
+    extern __shared__ double S[];                 // [128][129] staging: A in, q/L out, Z out
+    __shared__ double colbuf[2][TILE];
+    __shared__ double dsave[TILE];                // pivots d_j, then 1/sqrt(d_j)
+    __shared__ int first_bad;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tc = tid >> 4, tr = tid & 15;
+    if (tid == 0) first_bad = TILE;
     for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
+        const int r = idx >> 7, c = idx & 127;
         S[r * LEAF_LD + c] = (c <= r) ? A[(long)r * lda + c] : 0.0;
     }
-    // right-looking Cholesky in shared memory
-    const int ti = tid >> 4, tk = tid & 15;
-    for (int j = 0; j < TILE; ++j) {
-        __syncthreads();
-        double d = S[j * LEAF_LD + j];
-        if (!(d > 0.0)) {
-            if (tid == 0) atomicCAS(info, 0, row0 + j + 1);
-            d = nan("");
-        }
-        double sq = sqrt(d), rinv = 1.0 / sq;
-        __syncthreads();
-        if (tid == 0) { S[j * LEAF_LD + j] = sq; logdiag[j] = log(sq); }
-        for (int i = j + 1 + tid; i < TILE; i += NTHREADS) S[i * LEAF_LD + j] *= rinv;
-        __syncthreads();
-        for (int i = j + 1 + ti; i < TILE; i += 16) {
-            double lij = S[i * LEAF_LD + j];
-            for (int k = j + 1 + tk; k <= i; k += 16)
-                S[i * LEAF_LD + k] = fma(-lij, S[k * LEAF_LD + j], S[i * LEAF_LD + k]);
+    __syncthreads();
+    double M[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) M[a][b] = S[(tr + 16 * a) * LEAF_LD + tc + 16 * b];
+    __syncthreads();
+#pragma unroll
+    for (int ja = 0; ja < 8; ++ja) {
+        for (int jr = 0; jr < 16; ++jr) {
+            const int j = 16 * ja + jr;
+            double* cb = colbuf[j & 1];
+            if (tc == jr) {
+                // publish column j (raw), keep it for L, recycle the slots for Y[:,j]
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int i = tr + 16 * a;
+                    cb[i] = M[a][ja];
+                    S[i * LEAF_LD + j] = M[a][ja];
+                    M[a][ja] = (i == j) ? 1.0 : 0.0;
+                }
+            }
+            __syncthreads();
+            double d = cb[j];
+            if (tid == 0) dsave[j] = d;
+            if (!(d > 0.0)) d = nan("");
+            const double rd = 1.0 / d;
+            // row multipliers from the lane that owns row j in this half-warp (unscaled Y[j,c])
+            const int src = (lane & 16) | jr;
+            double m[8], l[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double y = __shfl_sync(0xffffffffu, M[ja][b], src);
+                if (b < ja) m[b] = y;
+                else if (b > ja) m[b] = cb[tc + 16 * b];
+                else m[b] = (tc <= jr) ? y : cb[tc + 16 * b];
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const bool active = (a > ja) || (a == ja && tr > jr);
+                l[a] = active ? cb[tr + 16 * a] * rd : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                if (a < ja) continue;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) M[a][b] = fma(-l[a], m[b], M[a][b]);
+            }
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
-        if (c <= r) A[(long)r * lda + c] = S[r * LEAF_LD + c];
+    if (tid < TILE) {
+        const double d = dsave[tid];
+        logdiag[tid] = 0.5 * log(d);
+        dsave[tid] = (d > 0.0) ? rsqrt(d) : nan("");
+        if (!(d > 0.0)) atomicMin(&first_bad, tid);
     }
-    // in-place inverse, columns right to left; two threads per row split the k-sum
-    const int row = tid >> 1, half = tid & 1;
-    for (int j = TILE - 1; j >= 0; --j) {
-        __syncthreads();
-        double t = 0.0;
-        if (row > j)
-            for (int k = j + 1 + half; k <= row; k += 2)
-                t = fma(S[row * LEAF_LD + k], S[k * LEAF_LD + j], t);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        double dj = 1.0 / S[j * LEAF_LD + j];
-        __syncthreads();
-        if (half == 0) {
-            if (row > j) S[row * LEAF_LD + j] = -t * dj;
-            else if (row == j) S[j * LEAF_LD + j] = dj;
-        }
+    __syncthreads();
+    // LAPACK info: first non-positive pivot, unless an earlier block already failed
+    if (tid == 0 && first_bad < TILE) atomicCAS(info, 0, row0 + first_bad + 1);
+    // L = q * diag(1/sqrt(d)) back to A (lower), Z = diag(1/sqrt(d)) * Y
+    for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c <= r) A[(long)r * lda + c] = S[r * LEAF_LD + c] * dsave[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const double sc = dsave[tr + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) S[(tr + 16 * a) * LEAF_LD + tc + 16 * b] = M[a][b] * sc;
     }
     __syncthreads();
     for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
+        const int r = idx >> 7, c = idx & 127;
         Z[(long)r * ldz + c] = (c <= r) ? S[r * LEAF_LD + c] : 0.0;
     }
 }
@@ -202,8 +263,8 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
     if (n % TILE || n <= 0) return cudaErrorInvalidValue;
     static bool leaf_init = false;
     if (!leaf_init) {
-        cudaError_t e = cudaFuncSetAttribute(potri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+        cudaError_t e0 = cudaFuncSetAttribute(potri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
+        if (e0 != cudaSuccess) return e0;
         leaf_init = true;
     }
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);

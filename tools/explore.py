@@ -50,6 +50,15 @@ def micro():
                 ctas, ctas * 8 // (148 * 4), mode, t * 1e3, dmma / t / 1e12, dfma / t / 1e12, (dmma + dfma) / t / 1e12))
 
 
+def latency():
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    iters = 200000
+    for mode, name in ((3, "DFMA"), (4, "DMMA")):
+        t = timeit(lambda: lib.gp2d_dbg_fp64_mode(mode, iters, 1, out.data_ptr(), st))
+        print("latency %s dependent chain: %.1f ns/op = %.1f cycles @1.965GHz" % (name, t / (16 * iters) * 1e9, t / (16 * iters) * 1.965e9))
+
+
 def stages(N=2000, grid=(320, 320), theta=(1.3, 3.1, 0.2)):
     X, y = synthetic.drifter_snapshot(N, config_id=2)
     Xs = synthetic.prediction_grid(X, *grid)
@@ -120,6 +129,8 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["micro", "stages", "potrf"]
     if "micro" in what:
         micro()
+    if "latency" in what:
+        latency()
     if "stages" in what:
         stages()
     if "potrf" in what:
