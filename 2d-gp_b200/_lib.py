@@ -27,6 +27,10 @@ SIGNATURES = {
                                    c_dp, C.c_int64, C.c_void_p, C.c_size_t, c_dp, c_st]),
     "gp2d_potrf_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gp2d_potrf": (C.c_int, [c_dp, C.c_int, C.c_int64, C.c_void_p, C.c_size_t, c_ip, c_st]),
+    "gp2d_spd_inverse_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "gp2d_spd_inverse": (C.c_int, [c_dp, C.c_int, C.c_int64, C.c_void_p, C.c_size_t, c_ip, c_st]),
+    "gp2d_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, C.c_int64,
+                             c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, c_st]),
     "gp2d_fit_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gp2d_fit": (C.c_int, [c_dp, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                            C.c_void_p, C.c_size_t, c_dp, c_dp, c_ip, c_st]),

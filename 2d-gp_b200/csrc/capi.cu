@@ -112,6 +112,15 @@ __global__ void __launch_bounds__(NTHREADS) fp64_peak_kernel(double* out, int it
     if (s == 123.456) out[0] = s;      // keep the loops alive
 }
 
+// padded lower-tile K^-1 -> full symmetric user matrix
+__global__ void unpad_symmetric_kernel(const double* __restrict__ P, int npad, double* __restrict__ A, long lda, int n) {
+    long total = (long)n * n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int r = (int)(idx / n), c = (int)(idx % n);
+        A[(long)r * lda + c] = (c <= r) ? P[(long)r * npad + c] : P[(long)c * npad + r];
+    }
+}
+
 // fit core shared by gp2d_fit and gp2d_lml_grad
 cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& hp, double diag_add,
                      void* ws, const FitLayout& L, cudaStream_t st) {
@@ -215,6 +224,52 @@ int gp2d_potrf(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* in
     if (e != cudaSuccess) return cuda_rc(e);
     unpad_lower_kernel<<<592, 256, 0, st>>>(P, np, A, (long)lda, n);
     return cuda_rc(cudaGetLastError());
+}
+
+size_t gp2d_spd_inverse_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    size_t np = (size_t)round_up(n, TILE);
+    return align256(np * np * 8) * 2 + align256(np * 8);
+}
+
+int gp2d_spd_inverse(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* info, void* stream) {
+    if (!A) return -1;
+    if (n <= 0) return -2;
+    if (lda < n) return -3;
+    if (!ws || ws_bytes < gp2d_spd_inverse_workspace_bytes(n)) return -5;
+    if (!info) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = round_up(n, TILE);
+    size_t o = 0;
+    double* P = at<double>(ws, o); o += align256((size_t)np * np * 8);
+    double* Z = at<double>(ws, o); o += align256((size_t)np * np * 8);
+    double* logdiag = at<double>(ws, o);
+    pad_lower_kernel<<<592, 256, 0, st>>>(A, (long)lda, n, P, np);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = potri_lower(P, np, Z, np, np, logdiag, info, /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = launch_dgemm(true, true, GemmArgs{Z, np, Z, np, P, np, np, np, np, 1.0, 0.0, 1, KR_GE_M}, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    unpad_symmetric_kernel<<<592, 256, 0, st>>>(P, np, A, (long)lda, n);
+    return cuda_rc(cudaGetLastError());
+}
+
+int gp2d_dgemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int64_t lda,
+               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
+    if (M <= 0 || M % TILE) return -3;
+    if (N <= 0 || N % TILE) return -4;
+    if (K <= 0 || K % BK) return -5;
+    if (!A || (reinterpret_cast<uintptr_t>(A) & 15)) return -7;
+    if ((lda & 1) || lda < (transa ? M : K)) return -8;
+    if (!B || (reinterpret_cast<uintptr_t>(B) & 15)) return -9;
+    if ((ldb & 1) || ldb < (transb ? K : N)) return -10;
+    if (!C || (reinterpret_cast<uintptr_t>(C) & 15)) return -12;
+    if ((ldc & 1) || ldc < N) return -13;
+    // kernel operand conventions: A "MN-major" == transposed storage; B "MN-major" == [k][n] storage
+    return cuda_rc(launch_dgemm(transa != 0, transb == 0,
+                                GemmArgs{A, (long)lda, B, (long)ldb, C, (long)ldc, M, N, K, alpha, beta, 0, KR_FULL},
+                                (cudaStream_t)stream));
 }
 
 size_t gp2d_fit_workspace_bytes(int N) {

@@ -1,0 +1,88 @@
+"""Sharding of the three independent axes of the path across ranks: grid
+points, hyper-parameter restarts, snapshots.  One process per GPU; torch.distributed
+(NCCL over NVLink on GPUs, gloo in the CPU tests) is used only to gather results -- there is
+no collective inside the data path, a single factorisation stays on one GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank, world_size, align=64):
+    """Contiguous [lo, hi) slice of n items for ``rank``; boundaries are multiples of
+    ``align`` (64 grid points = one predict column tile) so every rank runs whole tiles."""
+    units = -(-n // align)
+    per, extra = divmod(units, world_size)
+    lo_u = rank * per + min(rank, extra)
+    hi_u = lo_u + per + (1 if rank < extra else 0)
+    return min(lo_u * align, n), min(hi_u * align, n)
+
+
+def round_robin(n, rank, world_size):
+    """Indices rank, rank+world, ... : restarts and snapshots."""
+    return list(range(rank, n, world_size))
+
+
+def gather_concat(local: torch.Tensor, sizes=None):
+    """all-gather variable-length 1-D tensors and concatenate in rank order."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n_local) for _ in range(ws)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts)
+    buf = torch.zeros(mx, dtype=local.dtype, device=local.device)
+    buf[:local.numel()] = local
+    parts = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(parts, buf)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+def predict_sharded(gp, Xs, include_noise=False):
+    """Grid-sharded prediction: rank r predicts its contiguous tile-aligned slice with the
+    fit state it holds (every rank fits the same snapshot, or receives it by broadcast), then
+    mean/var shards are all-gathered.  Returns (mean[2M], var[2M]) on every rank."""
+    rank, ws = world()
+    Xs = np.asarray(Xs, dtype=np.float64) if not isinstance(Xs, torch.Tensor) else Xs
+    M = Xs.shape[0]
+    lo, hi = shard_range(M, rank, ws)
+    mean, var = gp.predict(Xs[lo:hi], include_noise=include_noise)
+    m = hi - lo
+    if ws == 1:
+        return mean, var
+    mu0, mu1 = gather_concat(mean[:m].contiguous()), gather_concat(mean[m:].contiguous())
+    v0, v1 = gather_concat(var[:m].contiguous()), gather_concat(var[m:].contiguous())
+    return torch.cat([mu0, mu1]), torch.cat([v0, v1])
+
+
+def gather_best(model):
+    """After model.optimize_restarts(..., rank, world): pick the globally best run and load
+    its parameters on every rank.  Exchanges (f_opt, x_opt) only."""
+    rank, ws = world()
+    runs = model.optimization_runs
+    nfree = len(model._free_params())
+    if runs:
+        best = min(runs, key=lambda o: o.f_opt)
+        rec = np.concatenate([[best.f_opt], best.x_opt])
+    else:
+        rec = np.concatenate([[np.inf], np.zeros(nfree)])
+    if ws > 1:
+        dev = model._gp.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(rec, dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(t) for _ in range(ws)]
+        dist.all_gather(allr, t)
+        recs = torch.stack(allr).cpu().numpy()
+        rec = recs[np.argmin(recs[:, 0])]
+    model._set_free(rec[1:])
+    model.parameters_changed()
+    return float(rec[0])

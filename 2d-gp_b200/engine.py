@@ -12,7 +12,7 @@ import torch
 from ._lib import lib, check, Gp2dError
 
 __all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
-           "HelmholtzGP", "fit_predict_host"]
+           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host"]
 
 
 class LinAlgError(np.linalg.LinAlgError):
@@ -109,6 +109,51 @@ def potrf(A, overwrite=False):
     with torch.cuda.device(Ad.device):
         check(lib.gp2d_potrf(_ptr(Ad), n, Ad.stride(0), _ptr(ws), nb, _ptr(info), _stream()), "gp2d_potrf")
     return torch.tril(Ad), int(info.item())
+
+
+def spd_inverse(A):
+    """Inverse of a symmetric positive definite matrix (device tensor); raises LinAlgError."""
+    Ad = as_dev(A).clone()
+    n = Ad.shape[0]
+    nb = lib.gp2d_spd_inverse_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Ad.device)
+    info = torch.zeros(1, dtype=torch.int32, device=Ad.device)
+    with torch.cuda.device(Ad.device):
+        check(lib.gp2d_spd_inverse(_ptr(Ad), n, Ad.stride(0), _ptr(ws), nb, _ptr(info), _stream()),
+              "gp2d_spd_inverse")
+    i = int(info.item())
+    if i > 0:
+        raise LinAlgError("matrix not positive definite (pivot %d)" % i)
+    return Ad
+
+
+def _pad2(t, r, c):
+    if t.shape[0] == r and t.shape[1] == c and t.is_contiguous():
+        return t
+    out = torch.zeros((r, c), dtype=torch.float64, device=t.device)
+    out[:t.shape[0], :t.shape[1]] = t
+    return out
+
+
+def matmul(A, B) -> torch.Tensor:
+    """A @ B in fp64 on the DMMA GEMM kernel (operands zero-padded to the tile sizes)."""
+    Ad = as_dev(A)
+    Bd = as_dev(B, Ad.device)
+    vec = Bd.dim() == 1
+    if vec:
+        Bd = Bd.reshape(-1, 1)
+    M, K = Ad.shape
+    K2, N = Bd.shape
+    if K != K2:
+        raise ValueError("shape mismatch")
+    Mp, Np, Kp = -(-M // 128) * 128, -(-N // 128) * 128, -(-K // 16) * 16
+    Ap, Bp = _pad2(Ad, Mp, Kp), _pad2(Bd, Kp, Np)
+    Cp = torch.empty((Mp, Np), dtype=torch.float64, device=Ad.device)
+    with torch.cuda.device(Ad.device):
+        check(lib.gp2d_dgemm(0, 0, Mp, Np, Kp, 1.0, _ptr(Ap), Ap.stride(0), _ptr(Bp), Bp.stride(0), 0.0,
+                             _ptr(Cp), Cp.stride(0), _stream()), "gp2d_dgemm")
+    out = Cp[:M, :N]
+    return out.reshape(-1) if vec else out
 
 
 # ------------------------------------------------------------------------------------------

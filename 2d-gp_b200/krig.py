@@ -1,0 +1,269 @@
+"""Kriging workflows with the reference's call surface (krig.py), on the CUDA GP engine.
+
+    kriging(st, et, ...)      observation / test split, model construction, pickle + .mat
+    runRestarts(fname, nres)  hyper-parameter restarts (sharded over ranks when distributed)
+    predict(filename, ...)    gridded prediction, one time slice at a time, NetCDF output
+    predictTest / getRMSE     hold-out evaluation
+    getGrid, rmse, getData, boundData
+
+Host preprocessing follows the reference (krig.py:42-86,259-381,648-678) in Python 3; the
+numerical core (covariance, Cholesky, likelihood, prediction) is ``models.GPRegression`` over
+libgp2d.  Deviations, all forced by what the reference tree lacks:
+  * kernelType 2 / 3 / 4 map to nonDivK / nonRotK / myKernel over the horizontal position
+    (y, x): the reference's 3-D ``myKernel2`` is not in its repository;
+  * kernelType 1 (scalar ARD RBF over t,y,x) and ``scikit_prior`` (sklearn scalar RBF) are the
+    next rows of the scope table and raise NotImplementedError;
+  * a vector kernel gives both velocity components from ONE model, stored as
+    ``<output>_combined.pkl`` (``_divFree`` / ``_curlFree``), the names krig.py:398-403 uses.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+import scipy.io as sio
+
+from . import dist as gdist
+from . import models
+from .myKernel import myKernel, nonDivK, nonRotK
+from .printNCFiles import createNC, openNC, writeNC
+from .projection import NAD83
+
+lat0 = 28.8
+lon0 = -88.6
+x_ori, y_ori = NAD83(lon0, lat0)            # krig.py:17-20
+
+_SUFFIX = {2: "_divFree.pkl", 3: "_curlFree.pkl", 4: "_combined.pkl"}
+
+
+# ---- data --------------------------------------------------------------------------------
+def getData(st, et, laser=1, path=None):
+    """time [h], lat, lon, v, u as [time, drifter] and the number of valid points per drifter
+    (krig.py:42-77).  laser=1: the filtered LASER pickle; otherwise the NetCDF of simulated
+    trajectories (read with scipy's NetCDF-3 reader)."""
+    if laser == 1:
+        with open(path or "Filtered_2016_2_7.pkl", "rb") as f:
+            tr = pickle.load(f, encoding="latin1")
+        for name in ("lat", "lon", "u", "v"):          # drifter L_0937 (index 238) is discarded
+            getattr(tr, name)[:, 238] = np.nan
+        time = (tr.time[st:et] - tr.time[0]) / 3600.
+        latt, lont, uob, vob = tr.lat[st:et, :], tr.lon[st:et, :], tr.u[st:et, :], tr.v[st:et, :]
+        valid = np.sum(~np.isnan(lont) & ~np.isnan(latt), axis=0).astype(float)
+        order = np.argsort(valid)[::-1]
+    else:
+        from scipy.io import netcdf_file
+        f = netcdf_file(path or "Simulations/Output.nc", "r", mmap=False)
+        latt = np.array(f.variables["lat"][st:et])
+        lont = np.array(f.variables["lon"][st:et])
+        vob = np.array(f.variables["v"][st:et])
+        uob = np.array(f.variables["u"][st:et])
+        time = np.array(f.variables["time"][st:et]) - f.variables["time"][0]
+        valid = np.zeros(latt.shape[1]) + time.size
+        order = np.arange(latt.shape[1])
+        f.close()
+    return time, latt[:, order], lont[:, order], vob[:, order], uob[:, order], valid[order]
+
+
+def boundData(var, varlim, lat, lon, v, u):
+    """Keep drifters whose initial ``var`` lies in ``varlim`` (krig.py:79-86)."""
+    il = np.where((var[0, :] >= varlim[0]) & (var[0, :] <= varlim[1]))[0]
+    return lat[:, il], lon[:, il], v[:, il], u[:, il]
+
+
+def split_observations(tob, yob, xob, latt, lont, vob, uob, sample_step=5, skip=5):
+    """Observation / test split of krig.kriging (krig.py:300-369): every |sample_step|-th time
+    step and every skip-th drifter are observations, the complement is the test set; points
+    with NaN positions are dropped.  Returns two dicts of column vectors."""
+    fields = {"t": tob, "y": yob, "x": xob, "lat": latt, "lon": lont, "u": uob, "v": vob}
+    nt, nd = tob.shape
+    if (sample_step < 0) or (skip > 1):
+        ss = abs(sample_step)
+        samples = np.arange(0, nt, ss)
+        if skip > 1:
+            testt = np.arange(nt)
+            testd = np.array(sorted(set(range(nd)) - set(range(0, nd, skip))), dtype=int)
+        else:
+            testd = np.arange(nd)
+            testt = np.array(sorted(set(range(nt)) - set(samples)), dtype=int) if ss > 1 else samples
+        obs = {k: np.reshape(a[samples, ::skip], [-1, 1]) for k, a in fields.items()}
+        tst = {k: np.reshape(a[testt[:, None], testd], [-1, 1]) for k, a in fields.items()}
+    else:
+        samples = np.arange(0, xob.size, sample_step)
+        test = np.array(sorted(set(range(xob.size)) - set(samples)), dtype=int)
+        obs = {k: np.reshape(a, [-1])[samples, None] for k, a in fields.items()}
+        tst = {k: np.reshape(a, [-1])[test, None] for k, a in fields.items()}
+    for d in (obs, tst):
+        ok = np.where(~np.isnan(d["x"][:, 0]) & ~np.isnan(d["y"][:, 0]))[0]
+        for k in d:
+            d[k] = d[k][ok]
+    return obs, tst
+
+
+def make_kernel(kernelType):
+    if kernelType == 2:
+        return nonDivK(2, [1, 2], 1.)
+    if kernelType == 3:
+        return nonRotK(2, [1, 2], 1.)
+    if kernelType == 4:
+        return myKernel(2, [1, 2], 1., 1., 0.5)
+    raise NotImplementedError(
+        "kernelType=1 (scalar ARD RBF over t,y,x; krig.py:388) is outside the Helmholtz hot path "
+        "built so far; use kernelType 2 (divergence-free), 3 (curl-free) or 4 (both)")
+
+
+# ---- workflows ---------------------------------------------------------------------------
+def kriging(st, et, lalim=[0, 0], lolim=[0, 0], sample_step=5, skip=5, nKernels=1, output='rbfModel',
+            pkg='GPy', kernelType=4, laser=1, data=None):
+    """Build the (un-optimised) GP model for drifter data between time steps st and et and
+    pickle it, like krig.kriging (krig.py:259-418).  ``data`` may carry the tuple getData
+    returns (time, lat, lon, v, u, valid) to bypass file I/O."""
+    startTime = datetime.now()
+    time, latt, lont, vob, uob, _ = data if data is not None else getData(st, et, laser)
+    if lolim[1] > lolim[0]:
+        latt, lont, vob, uob = boundData(lont, lolim, latt, lont, vob, uob)
+    if lalim[1] > lalim[0]:
+        latt, lont, vob, uob = boundData(latt, lalim, latt, lont, vob, uob)
+    xob, yob = NAD83(lont, latt)
+    tob = np.repeat(np.asarray(time)[:, None], latt.shape[1], axis=1)
+    bad = np.isnan(lont)
+    xob = np.where(bad, np.nan, (xob - x_ori) / 1000.)          # km
+    yob = np.where(bad, np.nan, (yob - y_ori) / 1000.)
+    o, t = split_observations(tob, yob, xob, latt, lont, vob, uob, sample_step, skip)
+    print('number of observations: ' + str(np.size(o["v"])))
+    # From here on, always T, Y, X order; velocities stacked [v; u] (krig.py:376-394)
+    X = np.concatenate([o["t"], o["y"], o["x"]], axis=1)
+    Xt = np.concatenate([t["t"], t["y"], t["x"]], axis=1)
+    obs = np.concatenate([o["v"], o["u"]], axis=0)
+    obst = np.concatenate([t["v"], t["u"]], axis=0)
+    if nKernels != 1:
+        print('nKernels > 1: a sum of identical Helmholtz kernels is one kernel with rescaled '
+              'weights; a single kernel is used')
+    k = make_kernel(kernelType)
+    model = models.GPRegression(X, obs, k)
+    model.pickle(output + _SUFFIX[kernelType])
+    sio.savemat(output + '.mat', {'Xo': X, 'obs': obs, 'Xt': Xt,
+                                  'LL_o': np.concatenate([o["t"], o["lat"], o["lon"]], axis=1),
+                                  'LL_t': np.concatenate([t["t"], t["lat"], t["lon"]], axis=1),
+                                  'test_points': obst})
+    print('End of script, time : ' + str(datetime.now() - startTime))
+    return model
+
+
+def _model_file(fname):
+    for suf in ("",) + tuple(_SUFFIX.values()):
+        p = fname + suf if suf else fname + '.pkl'
+        if os.path.isfile(p):
+            return p
+    raise IOError("no model pickle found for '%s'" % fname)
+
+
+def runRestarts(fname, nres=10, nKernels=2, seed=None, max_iters=1000):
+    """Hyper-parameter fit with ``nres`` restarts (krig.py:430-468).  Under torch.distributed
+    the restarts are sharded round-robin over the ranks and the best run is gathered."""
+    startTime = datetime.now()
+    path = _model_file(fname)
+    model = models.load(path)
+    hyp_old = model.param_array.copy()
+    rank, world = gdist.world()
+    model.optimize_restarts(messages=False, verbose=False, num_restarts=nres, seed=seed, max_iters=max_iters,
+                            rank=rank, world=world, robust=True)
+    gdist.gather_best(model)
+    hyp = model.param_array
+    if rank == 0:
+        model.pickle(path)
+        print('Optimized Hyperparameters =================================================')
+        for name, a, b in zip(model.parameter_names(), hyp_old, hyp):
+            print('%-28s = %s   :   %s' % (name, a, b))
+        print('===========================================================================')
+        print('End of script, time : ' + str(datetime.now() - startTime))
+    return model
+
+
+def getGrid(to, yo, xo, dt=0.5, dx=0.5, xL=40, yL=40):
+    """Regular (t, y, x) grid around the observations, rows ordered time-major then y then x
+    (krig.py:648-678).  Returns Xgrid[nt*ny*nx, 3], tg, yg, xg."""
+    def span(v, L):
+        if (np.max(v) - np.min(v)) > L:
+            return np.mean(v) - L / 2, np.mean(v) + L / 2
+        return np.min(v) - dx, np.max(v) + dx
+    xmin, xmax = span(xo, xL)
+    ymin, ymax = span(yo, yL)
+    xg = np.arange(xmin, xmax, dx)
+    yg = np.arange(ymin, ymax, dx)
+    tg = np.arange(np.min(to), np.max(to), dt)
+    Yg, Tg, Xg = np.meshgrid(yg, tg, xg)
+    return (np.concatenate([np.reshape(Tg, [Tg.size, 1]), np.reshape(Yg, [Yg.size, 1]),
+                            np.reshape(Xg, [Xg.size, 1])], axis=1), tg, yg, xg)
+
+
+def predict(filename, tlim=[0, 0], ylim=[0, 0], xlim=[0, 0], dt=0.5, dx=0.5, xL=40, yL=40, Simul=0,
+            write=True):
+    """Gridded posterior mean and variance, one time slice at a time (krig.py:471-574).  Under
+    torch.distributed each slice's grid points are sharded over the ranks."""
+    startTime = datetime.now()
+    model = models.load(_model_file(filename))
+    hyp = model.param_array
+    if (ylim[0] == ylim[1]) and (xlim[0] == xlim[1]):
+        Xo = sio.loadmat(filename + '.mat')['Xo']
+        if Simul == 1:
+            raise NotImplementedError("the NCOM grid branch needs osprein_2013_8.nc (absent upstream)")
+        Xp, tp, yp, xp = getGrid(Xo[:, 0], Xo[:, 1], Xo[:, 2])
+    else:
+        Xp, tp, yp, xp = getGrid(tlim, ylim, xlim, dt, dx, xL, yL)
+    inc = yp.size * xp.size
+    V, U, VVar, UVar = [], [], [], []
+    for i in range(tp.size):
+        Xp2 = Xp[i * inc:(i + 1) * inc, 1:3]
+        mean, var = gdist.predict_sharded(model._gp, Xp2, include_noise=True)     # GPy adds the noise
+        mean, var = mean.cpu().numpy(), var.cpu().numpy()
+        V.append(mean[:inc]); U.append(mean[inc:]); VVar.append(var[:inc]); UVar.append(var[inc:])
+    shape = [tp.size, yp.size, xp.size]
+    V, U, VVar, UVar = (np.reshape(np.concatenate(a), shape) for a in (V, U, VVar, UVar))
+    if write and gdist.world()[0] == 0:
+        createNC(filename + '.nc', tp, yp, xp, hyp)
+        fi = openNC(filename + '.nc', 'a')
+        for name, arr in (('v', V), ('u', U), ('vvar', VVar), ('uvar', UVar),
+                          ('hyperparam_v', hyp), ('hyperparam_u', hyp)):
+            writeNC(fi, name, arr)
+        fi.close()
+        print('End of script, time : ' + str(datetime.now() - startTime))
+    return Xp, V, U, VVar, UVar
+
+
+def predictTest(filename):
+    """Predict at the held-out test points and save them (krig.py:578-616)."""
+    model = models.load(_model_file(filename))
+    f = sio.loadmat(filename + '.mat')
+    Xt, obst = f['Xt'], f['test_points']
+    mean, var = model.predict(Xt)
+    Nt = Xt.shape[0]
+    out = {'Xt': Xt, 'Vp': mean[:Nt], 'VpVar': var[:Nt], 'Up': mean[Nt:], 'UpVar': var[Nt:], 'test_points': obst}
+    sio.savemat(filename + '_test.mat', out)
+    return out
+
+
+def rmse(ys, y):
+    """Root-mean-square error (krig.py:641-645)."""
+    error = np.reshape(np.asarray(ys) - np.asarray(y), [-1])
+    return np.sqrt(np.mean(np.square(error)))
+
+
+def getRMSE(filename):
+    """RMSE of the v and u predictions at the test points (krig.py:620-635)."""
+    model = models.load(_model_file(filename))
+    f = sio.loadmat(filename + '.mat')
+    Xt, obst = f['Xt'], f['test_points']
+    mean, _ = model.predict(Xt)
+    Nt = Xt.shape[0]
+    rmse_v, rmse_u = rmse(mean[:Nt], obst[:Nt]), rmse(mean[Nt:], obst[Nt:])
+    print(rmse_v)
+    print(rmse_u)
+    return rmse_v, rmse_u
+
+
+def scikit_prior(*args, **kwargs):
+    raise NotImplementedError(
+        "scikit_prior rebuilds a scalar RBF + WhiteKernel model in scikit-learn (krig.py:88-207); the "
+        "scalar-RBF kernel family is the next row of the scope table (SURVEY.md §8f rank 2)")

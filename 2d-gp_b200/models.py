@@ -1,0 +1,215 @@
+"""GPRegression-like model over the CUDA engine: the subset of GPy's model API the reference
+scripts use (GP_plots.py:760-770; krig.py:411-412,438-457,478-483,543-544).
+
+    m = GPRegression(X, Y, kern)            X [N,2]; Y [2N,1] stacked components
+    m.optimize(); m.optimize_restarts(num_restarts=..., messages=False)
+    mean, var = m.predict(Xnew)             [2M,1] each, Gaussian noise included (GPy)
+    m.param_array                           [length_df, length_cf, ratio, noise]  (GP_plots.py:810-813)
+    m.log_likelihood(); m.pickle(path); load(path)
+
+Every objective evaluation is one gp2d_lml_grad call (kernel build + Cholesky + K^-1 +
+gradient reductions on the GPU); only the L-BFGS-B driver (scipy, like paramz) is host code.
+Independent restarts shard across ranks (``optimize_restarts(..., rank, world)``).
+"""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+import scipy.optimize as sopt
+
+from .engine import HelmholtzGP, LinAlgError
+from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase
+from .params import Param
+
+GPY_JITTER = 1e-8       # GPy adds 1e-8 to the diagonal before factorising
+
+
+class _Run:
+    """One optimisation run (GPy keeps these in model.optimization_runs; krig.py:439-457)."""
+
+    def __init__(self, x_opt, f_opt, status, nfev):
+        self.x_opt, self.f_opt, self.status, self.funct_eval = x_opt, f_opt, status, nfev
+
+
+class GPRegression:
+    def __init__(self, X, Y, kernel=None, noise_var=1.0, jitter=GPY_JITTER, reference_compat=None, device=None):
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        if kernel is None:
+            kernel = myKernel(2, [0, 1], 1.0, 1.0, 0.5)
+        if not isinstance(kernel, _HelmholtzBase):
+            raise TypeError("kernel must be myKernel / nonDivK / nonRotK")
+        self.kern = kernel
+        if reference_compat is not None:
+            self.kern.reference_compat = bool(reference_compat)
+        self.X = X[:, self.kern.active_dims] if X.shape[1] != 2 else X
+        self.Y = Y.reshape(-1, 1)
+        if self.Y.shape[0] != 2 * self.X.shape[0]:
+            raise ValueError("Y must stack both velocity components: shape [2N,1] (GP_plots.py:722)")
+        self.Gaussian_noise = Param("Gaussian_noise.variance", noise_var).constrain_positive()
+        self.likelihood = self
+        self.variance = self.Gaussian_noise
+        self.jitter = float(jitter)
+        self.optimization_runs = []
+        self._gp = HelmholtzGP(self.X, self.Y.reshape(-1), *self.kern._theta(), float(self.Gaussian_noise),
+                               jitter=self.jitter, device=device)
+        self._ll = None
+        self.parameters_changed()          # GPy evaluates the likelihood in the constructor
+
+    # ---- parameters -----------------------------------------------------------------------
+    @property
+    def parameters(self):
+        return list(self.kern.parameters) + [self.Gaussian_noise]
+
+    @property
+    def param_array(self):
+        return np.array([float(p) for p in self.parameters])
+
+    def parameter_names(self):
+        return ["%s.%s" % (self.kern.name, p.name) for p in self.kern.parameters] + ["Gaussian_noise.variance"]
+
+    def _free_params(self):
+        return [p for p in self.parameters if p.constraint != "fixed"]
+
+    def _sync(self):
+        self._gp.set_params(*self.kern._theta(), float(self.Gaussian_noise))
+
+    # ---- likelihood ------------------------------------------------------------------------
+    def _grad_natural(self, grad4):
+        """Map d/d(l_df, l_cf, ratio, noise) onto this kernel's own parameters."""
+        k = self.kern
+        if isinstance(k, myKernel):
+            g = [grad4[0], grad4[1], grad4[2]]
+        elif isinstance(k, nonDivK):
+            g = [grad4[0]]
+        else:
+            g = [grad4[1]]
+        return g + [grad4[3]]
+
+    def parameters_changed(self):
+        self._sync()
+        try:
+            self._ll, g = self._gp.lml_and_grad(reference_compat=self.kern.reference_compat)
+        except LinAlgError:
+            self._ll, g = -np.inf, np.zeros(4)
+        for p, gi in zip(self.parameters, self._grad_natural(g)):
+            p.gradient = float(gi)
+        return self._ll
+
+    def log_likelihood(self):
+        return float(self._ll)
+
+    def objective_function(self):
+        return -float(self._ll)
+
+    # ---- optimisation (host driver; paramz uses scipy L-BFGS-B the same way) ---------------
+    def _set_free(self, x):
+        for p, xi in zip(self._free_params(), x):
+            p.from_free(float(xi))
+
+    def _objective(self, x):
+        self._set_free(x)
+        ll = self.parameters_changed()
+        if not np.isfinite(ll):
+            return 1e100, np.zeros(len(x))
+        g = np.array([-p.gradient * p.dvalue_dfree(float(xi)) for p, xi in zip(self._free_params(), x)])
+        return -ll, g
+
+    def optimize(self, optimizer=None, max_iters=1000, messages=False, start=None, **kw):
+        x0 = np.array([p.to_free() for p in self._free_params()]) if start is None else np.asarray(start, float)
+        res = sopt.minimize(self._objective, x0, jac=True, method="L-BFGS-B", options={"maxiter": int(max_iters)})
+        self._set_free(res.x)
+        self.parameters_changed()
+        run = _Run(res.x.copy(), float(res.fun), res.message, int(res.nfev))
+        self.optimization_runs.append(run)
+        if messages:
+            print("optimize: f=%.6f nfev=%d %s" % (res.fun, res.nfev, res.message))
+        return run
+
+    def randomize(self, rng=None):
+        """Draw the unconstrained parameters from N(0,1), as GPy's model.randomize()."""
+        rng = np.random.default_rng() if rng is None else rng
+        self._set_free(rng.standard_normal(len(self._free_params())))
+        self._sync()
+
+    def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, messages=False, max_iters=1000,
+                          seed=None, rank=0, world=1, **kw):
+        """GPy semantics: optimise from the current point, then from random points; keep the
+        best.  ``rank``/``world`` shard the restart indices (restart r runs on rank r % world);
+        use gp2d_b200.dist.gather_best to pick the global winner."""
+        base = np.random.SeedSequence(seed)
+        children = base.spawn(int(num_restarts))
+        init = np.array([p.to_free() for p in self._free_params()])
+        for r in range(int(num_restarts)):
+            if r % world != rank:
+                continue
+            try:
+                if r == 0 and not self.optimization_runs:
+                    self._set_free(init)
+                else:
+                    self.randomize(np.random.default_rng(children[r]))
+                self.optimize(max_iters=max_iters, messages=False)
+                if messages or verbose:
+                    print("Optimization restart %d/%d, f = %s" % (r + 1, num_restarts, self.optimization_runs[-1].f_opt))
+            except Exception:
+                if robust:
+                    continue
+                raise
+        if self.optimization_runs:
+            best = min(self.optimization_runs, key=lambda o: o.f_opt)
+            self._set_free(best.x_opt)
+            self.parameters_changed()
+        return self.optimization_runs
+
+    # ---- prediction ------------------------------------------------------------------------
+    def predict(self, Xnew, full_cov=False, include_likelihood=True):
+        if full_cov:
+            raise NotImplementedError("only marginal variances (the reference never asks for full_cov)")
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        if Xnew.shape[1] != 2:
+            Xnew = Xnew[:, self.kern.active_dims]
+        if not self._gp.fitted:
+            self._sync()
+            self._gp.fit()
+        mean, var = self._gp.predict(Xnew, include_noise=include_likelihood)
+        return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
+
+    # ---- persistence (krig.py:412,438,452) -----------------------------------------------------
+    def _state(self):
+        k = self.kern
+        return {"kernel": type(k).__name__, "active_dims": k.active_dims, "params": self.param_array,
+                "constraints": [p.constraint for p in self.parameters], "reference_compat": k.reference_compat,
+                "X": self.X, "Y": self.Y, "jitter": self.jitter,
+                "runs": [r.__dict__ for r in self.optimization_runs]}
+
+    def pickle(self, path):
+        with open(path, "wb") as f:
+            pickle.dump(self._state(), f, protocol=2)
+
+    def __str__(self):
+        rows = ["  %-28s %g" % (n, v) for n, v in zip(self.parameter_names(), self.param_array)]
+        return "GPRegression  log-likelihood %s\n%s" % (self._ll, "\n".join(rows))
+
+
+def load(path, device=None):
+    """Counterpart of GPy.load (krig.py:438,478-482)."""
+    with open(path, "rb") as f:
+        st = pickle.load(f)
+    p = st["params"]
+    name = st["kernel"]
+    if name == "myKernel":
+        k = myKernel(2, st["active_dims"], p[0], p[1], p[2])
+    elif name == "nonDivK":
+        k = nonDivK(2, st["active_dims"], p[0])
+    else:
+        k = nonRotK(2, st["active_dims"], p[0])
+    k.reference_compat = st.get("reference_compat", False)
+    m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
+    for prm, c in zip(m.parameters, st["constraints"]):
+        prm.constraint = c
+    for d in st["runs"]:
+        r = _Run(None, None, None, None)
+        r.__dict__.update(d)
+        m.optimization_runs.append(r)
+    return m

@@ -67,6 +67,20 @@ int gp2d_kernel_grad(const double* X, int N, const double* X2, int M,
 size_t gp2d_potrf_workspace_bytes(int n);
 int gp2d_potrf(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* info, void* stream);
 
+/* In-place inverse of the row-major SPD matrix A[n,n] (full symmetric result): Cholesky,
+ * L^-1 and K^-1 = L^-T L^-1 on the DMMA pipe.  Replaces np.linalg.inv(K) at
+ * GP_laser.py:118,180 / GP_scripts.py:50 and GPy's dpotri. */
+size_t gp2d_spd_inverse_workspace_bytes(int n);
+int gp2d_spd_inverse(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, fp64, on the DMMA pipe.
+ * op(A) is M x K: A[m*lda + k] (transa = 0) or A[k*lda + m] (transa = 1); op(B) is K x N:
+ * B[k*ldb + n] (transb = 0) or B[n*ldb + k] (transb = 1).  M and N must be multiples of
+ * 128, K of 16, leading dimensions even, pointers 16-byte aligned (callers pad).
+ * Replaces the np.dot calls of GP_scripts.getMean/getCov (GP_scripts.py:44-54). */
+int gp2d_dgemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int64_t lda,
+               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+
 /* ---- GP fit / predict / likelihood ----------------------------------------------- */
 
 /* Fit: build K + (noise+jitter) I, factorise, alpha = K^-1 y,

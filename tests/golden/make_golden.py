@@ -106,8 +106,19 @@ def simlaser(ts, loops):
     print("simlaser_ts%d.npz written: lml=%.10f var in [%.5f, %.5f]" % (ts, lml, var.min(), var.max()))
 
 
+def simlaser_tracks():
+    """Raw track columns (lat, lon, u, v at ts = 0 and 100) so that GP_laser.simLaser can be
+    driven end to end on the GPU box, where simulTracks.pkl is absent."""
+    tr = rs.load_simul_tracks()
+    cols = [0, 100]
+    np.savez_compressed(os.path.join(HERE, "simlaser_tracks.npz"), ts=np.array(cols),
+                        lat=np.asarray(tr.lat)[:, cols], lon=np.asarray(tr.lon)[:, cols],
+                        u=np.asarray(tr.u)[:, cols], v=np.asarray(tr.v)[:, cols])
+
+
 if __name__ == "__main__":
     assert rs.available(), "reference tree not found"
     kernel_small()
     simlaser(0, loops=True)
     simlaser(100, loops=False)
+    simlaser_tracks()
