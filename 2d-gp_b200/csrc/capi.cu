@@ -18,7 +18,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // Private layout of the fit workspace: a pure function of N.
 struct FitLayout {
     int npad;
-    size_t off_A, off_Z, off_logdiag, off_yint, off_w, off_alpha, off_partial, off_X, off_scal, off_info, total;
+    size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_alpha, off_partial, off_X, off_scal, off_info, total;
 };
 
 FitLayout fit_layout(int N) {
@@ -28,6 +28,7 @@ FitLayout fit_layout(int N) {
     size_t o = 0;
     L.off_A = o; o = align256(o + n * n * d);
     L.off_Z = o; o = align256(o + n * n * d);
+    L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
     L.off_logdiag = o; o = align256(o + n * d);
     L.off_yint = o; o = align256(o + n * d);
     L.off_w = o; o = align256(o + n * d);
@@ -133,6 +134,8 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     if (e != cudaSuccess) return e;
     e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
                     /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    if (e != cudaSuccess) return e;
+    e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
     return solve_alpha_lml(Z, L.npad, L.npad, N, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
                            at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
@@ -330,7 +333,7 @@ int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double rat
     FitLayout L = fit_layout(N);
     if (!ws) return -12;
     if (ws_bytes < predict_panel_bytes(L.npad)) return -13;
-    return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Z), L.npad, L.npad, at<double>(fit_ws, L.off_alpha),
+    return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
                                  at<double>(fit_ws, L.off_X), N, make_helm(l_df, l_cf, ratio), Xs, M,
                                  (long)out_stride, var_add, mean, var, (double*)ws, ws_bytes,
                                  (cudaStream_t)stream));

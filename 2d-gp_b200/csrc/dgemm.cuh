@@ -12,6 +12,7 @@
 // pipeline, XOR-swizzled shared memory, DMMA.8x8x4 register tiles.
 #pragma once
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace gp2d {
 
@@ -127,7 +128,110 @@ __global__ void __launch_bounds__(NT, (TS == 64 ? 3 : 1)) dgemm_kernel(GemmArgs 
     }
 }
 
-// host launcher (dgemm.cu)
+
+// ---- warp-specialised 128 x 128 tile kernel (pipeline.cuh) ---------------------------------
+// Same contract as dgemm_kernel<A_MN, B_MN, 256, 128>; 8 consumer warps + 1 producer warp,
+// 6-stage mbarrier ring, no CTA-wide barrier in the k-loop.
+constexpr int GEMM_WS_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES;
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(WS_THREADS, 1) dgemm_ws_kernel(GemmArgs p) {
+    constexpr int TS = TILE;
+    extern __shared__ __align__(16) double smem[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
+    WsBarriers wb{bars, bars + WS_STAGES};
+
+    int tm, tn;
+    if (p.lower_out) {
+        int t = blockIdx.x;
+        tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((long)(tm + 1) * (tm + 2) / 2 <= t) ++tm;
+        while ((long)tm * (tm + 1) / 2 > t) --tm;
+        tn = t - tm * (tm + 1) / 2;
+    } else {
+        int tiles_n = p.N / TS;
+        tm = blockIdx.x / tiles_n;
+        tn = blockIdx.x % tiles_n;
+    }
+    int k0 = 0, k1 = p.K;
+    if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TS);
+    if (p.krule & KR_LE_N) k1 = min(k1, (tn + 1) * TS);
+    if (p.krule & KR_GE_N) k0 = max(k0, tn * TS);
+    if (p.krule & KR_GE_M) k0 = max(k0, tm * TS);
+    const int nk = (k1 - k0) / BK;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    wb.init(tid);
+    __syncthreads();
+
+    if (warp == WS_CONSUMERS / 32) {
+        // ---------------- producer warp ----------------
+        const double* Ag = A_MN ? p.A + (long)k0 * p.lda + (long)tm * TS : p.A + (long)tm * TS * p.lda + k0;
+        const double* Bg = B_MN ? p.B + (long)k0 * p.ldb + (long)tn * TS : p.B + (long)tn * TS * p.ldb + k0;
+        const long a_step = A_MN ? (long)BK * p.lda : BK;
+        const long b_step = B_MN ? (long)BK * p.ldb : BK;
+        int s = 0;
+        unsigned ph = 0;
+        for (int kt = 0; kt < nk; ++kt) {
+            if (kt >= WS_STAGES) mbar_wait(wb.empty + s, ph ^ 1u);
+            double* st = smem + s * WS_STAGE_DOUBLES;
+            ws_load_tile<A_MN>(st, Ag, p.lda, lane);
+            ws_load_tile<B_MN>(st + TILE_DOUBLES, Bg, p.ldb, lane);
+            cp_async_arrive_noinc(wb.full + s);
+            Ag += a_step;
+            Bg += b_step;
+            if (++s == WS_STAGES) { s = 0; ph ^= 1u; }
+        }
+        cp_async_wait_all();
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const int wm = warp & 1, wn = warp >> 1;
+    FragLane<A_MN, 64> fa;
+    FragLane<B_MN, 32> fb;
+    fa.init(wm, lane);
+    fb.init(wn, lane);
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    {
+        int s = 0;
+        unsigned ph = 0;
+        for (int kt = 0; kt < nk; ++kt) {
+            mbar_wait(wb.full + s, ph);
+            const double* st = smem + s * WS_STAGE_DOUBLES;
+            ws_mma_stage<A_MN, B_MN>(st, st + TILE_DOUBLES, fa, fb, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(wb.empty + s);
+            if (++s == WS_STAGES) { s = 0; ph ^= 1u; }
+        }
+    }
+    const int g = lane >> 2, tig = lane & 3;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+        long row = (long)tm * TS + wm * 64 + mb * 8 + g;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            long col = (long)tn * TS + wn * 32 + nb * 8 + 2 * tig;
+            double2* dst = reinterpret_cast<double2*>(p.C + row * p.ldc + col);
+            double2 v;
+            v.x = alpha * acc[mb][nb][0];
+            v.y = alpha * acc[mb][nb][1];
+            if (beta != 0.0) {
+                double2 old = *dst;
+                v.x = fma(beta, old.x, v.x);
+                v.y = fma(beta, old.y, v.y);
+            }
+            *dst = v;
+        }
+    }
+}
+
+// host launcher (linalg.cu)
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& args, cudaStream_t stream);
 cudaError_t dgemm_init();
 // CTA shape used by GEMM / predict launches: 256 (8 warps, 64x32 warp tiles) or 512.

@@ -26,41 +26,49 @@ namespace gp2d {
 // GEMM launcher
 // ------------------------------------------------------------------------------------
 static int g_cta_threads = 256;
-void set_cta_threads(int nt) { g_cta_threads = (nt == 512) ? 512 : 256; }
+void set_cta_threads(int) {}          // single CTA shape since the warp-specialised kernels
 int get_cta_threads() { return g_cta_threads; }
 
-template <bool A_MN, bool B_MN, int NT, int TS>
-static cudaError_t gemm_attr() {
-    return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm_smem_bytes(TS));
+template <bool A_MN, bool B_MN>
+static cudaError_t gemm_attr64() {
+    return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes(64));
 }
-template <int NT, int TS>
-static cudaError_t gemm_attr_all() {
-    cudaError_t e;
-    if ((e = gemm_attr<false, false, NT, TS>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<false, true, NT, TS>()) != cudaSuccess) return e;
-    if ((e = gemm_attr<true, true, NT, TS>()) != cudaSuccess) return e;
-    return gemm_attr<true, false, NT, TS>();
+template <bool A_MN, bool B_MN>
+static cudaError_t gemm_attr_ws() {
+    return cudaFuncSetAttribute(dgemm_ws_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GEMM_WS_SMEM_BYTES);
 }
 
 cudaError_t dgemm_init() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e;
-    if ((e = gemm_attr_all<256, 128>()) != cudaSuccess) return e;
-    if ((e = gemm_attr_all<512, 128>()) != cudaSuccess) return e;
-    if ((e = gemm_attr_all<128, 64>()) != cudaSuccess) return e;
+    if ((e = gemm_attr64<false, false>()) != cudaSuccess) return e;
+    if ((e = gemm_attr64<false, true>()) != cudaSuccess) return e;
+    if ((e = gemm_attr64<true, true>()) != cudaSuccess) return e;
+    if ((e = gemm_attr64<true, false>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_ws<false, false>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_ws<false, true>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_ws<true, true>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_ws<true, false>()) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
 
-template <int NT, int TS>
-static void gemm_launch(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
-    constexpr int SM = gemm_smem_bytes(TS);
-    if (!a_mn && !b_mn) dgemm_kernel<false, false, NT, TS><<<grid, NT, SM, st>>>(a);
-    else if (!a_mn && b_mn) dgemm_kernel<false, true, NT, TS><<<grid, NT, SM, st>>>(a);
-    else if (a_mn && b_mn) dgemm_kernel<true, true, NT, TS><<<grid, NT, SM, st>>>(a);
-    else dgemm_kernel<true, false, NT, TS><<<grid, NT, SM, st>>>(a);
+static void gemm_launch64(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
+    constexpr int SM = gemm_smem_bytes(64);
+    if (!a_mn && !b_mn) dgemm_kernel<false, false, 128, 64><<<grid, 128, SM, st>>>(a);
+    else if (!a_mn && b_mn) dgemm_kernel<false, true, 128, 64><<<grid, 128, SM, st>>>(a);
+    else if (a_mn && b_mn) dgemm_kernel<true, true, 128, 64><<<grid, 128, SM, st>>>(a);
+    else dgemm_kernel<true, false, 128, 64><<<grid, 128, SM, st>>>(a);
+}
+static void gemm_launch_ws(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
+    constexpr int SM = GEMM_WS_SMEM_BYTES;
+    if (!a_mn && !b_mn) dgemm_ws_kernel<false, false><<<grid, WS_THREADS, SM, st>>>(a);
+    else if (!a_mn && b_mn) dgemm_ws_kernel<false, true><<<grid, WS_THREADS, SM, st>>>(a);
+    else if (a_mn && b_mn) dgemm_ws_kernel<true, true><<<grid, WS_THREADS, SM, st>>>(a);
+    else dgemm_ws_kernel<true, false><<<grid, WS_THREADS, SM, st>>>(a);
 }
 
 // 128-tiles below this count leave most of the 148 SMs idle: switch to 64x64 tiles
@@ -78,9 +86,8 @@ cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t s
     if (grid < g_small_tile_threshold) {
         tm *= 2; tn *= 2;
         grid = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
-        gemm_launch<128, 64>(a_mn, b_mn, (unsigned)grid, a, st);
-    } else if (g_cta_threads == 512) gemm_launch<512, 128>(a_mn, b_mn, (unsigned)grid, a, st);
-    else gemm_launch<256, 128>(a_mn, b_mn, (unsigned)grid, a, st);
+        gemm_launch64(a_mn, b_mn, (unsigned)grid, a, st);
+    } else gemm_launch_ws(a_mn, b_mn, (unsigned)grid, a, st);
     return cudaGetLastError();
 }
 
@@ -272,6 +279,40 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
     PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess};
     potri_rec(c, 0, n, need_inv);
     return c.err;
+}
+
+// ------------------------------------------------------------------------------------
+// Z = L^-1 (row-major, lower) -> tile-major copy for the predictive pass: the 128 x 16 tiles of
+// row block li, k-tile kt <= 8 li + 7 are stored contiguously in the order the predict kernel
+// consumes them (tile number 8 li (li+1)/2 + kt), each already in the XOR-swizzled
+// shared-memory image (kmaj_off), so one 16 KB bulk copy brings a whole operand stage.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_lower_tiles_kernel(const double* __restrict__ Z, long ldz, double* __restrict__ Zt) {
+    int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((long)I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const double* src = Z + (long)I * TILE * ldz + (long)J * TILE;
+    double* dst = Zt + (8 * ((size_t)I * (I + 1) / 2) + 8 * (size_t)J) * TILE_DOUBLES;
+#pragma unroll 4
+    for (int q = threadIdx.x; q < TILE * 64; q += 256) {
+        const int r = q >> 6, c = q & 63, kt = c >> 3, ch = c & 7;
+        const double2 v = *reinterpret_cast<const double2*>(src + (long)r * ldz + 2 * c);
+        *reinterpret_cast<double2*>(dst + (size_t)kt * TILE_DOUBLES + r * BK + ((ch ^ ((r & 3) << 1)) << 1)) = v;
+    }
+}
+
+size_t packed_tiles_doubles(int npad) {
+    const size_t nb = (size_t)npad / TILE;
+    return 8 * (nb * (nb + 1) / 2) * (size_t)TILE_DOUBLES;
+}
+
+cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st) {
+    const int nb = npad / TILE;
+    pack_lower_tiles_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(Z, ldz, Zt);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------

@@ -18,6 +18,10 @@ cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, const do
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st);
 cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st);
+// Tile-major, pre-swizzled copy of the lower triangle of Z (what predict_fused streams with
+// bulk copies): tile (row block li, k-tile kt) is number 8 li (li+1)/2 + kt, 2048 doubles each.
+size_t packed_tiles_doubles(int npad);
+cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st);
 
 // kernel_build.cu -------------------------------------------------------------------------
 // Reference (component-major block) layout, arbitrary N, M, ld: K[2N, 2M].  X2 == nullptr
@@ -37,7 +41,7 @@ int grad_sums_block_partials(int N, int M);
 // predict.cu ------------------------------------------------------------------------------
 // scratch: one [npad x 128] K* panel per resident CTA (at most one CTA per SM is launched;
 // fewer panels only reduce the grid).
-cudaError_t predict_fused(const double* Z, long ldz, int npad, const double* alpha_int,
+cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           const double* X, int N, const HelmParams& hp, const double* Xs, int M,
                           long out_stride, double var_add, double* mean, double* var,
                           double* scratch, size_t scratch_bytes, cudaStream_t st);

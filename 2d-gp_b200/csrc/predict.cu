@@ -19,11 +19,12 @@
 #include "common.cuh"
 #include "dgemm.cuh"
 #include "linalg.h"
+#include "pipeline.cuh"
 
 namespace gp2d {
 
 struct PredictArgs {
-    const double* Z; long ldz; int npad;
+    const double* Zt; int npad;     // L^-1 as pre-swizzled 128 x 16 tiles, row block major (linalg.h)
     const double* alpha;          // interleaved, zero padded to npad
     const double* X; int N;
     HelmParams hp;
@@ -35,28 +36,44 @@ struct PredictArgs {
     int ntiles;
 };
 
-constexpr int P_STAGES = 4;
-constexpr int PRED_SMEM_BYTES = P_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB
+// shared memory: operand ring | mbarriers | epilogue scratch (column sums, mean partials)
+constexpr int PRED_RED_DOUBLES = 2 * TILE + 4 * 64 * 2 + 8 * WS_CONSUMERS;
+constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) predict_kernel(PredictArgs p) {
-    constexpr int MB = mblocks(NT), WM = warps_m(NT), OS = NT / 64;
+// 8 consumer warps (phase 1 + DMMA) and one producer warp (cp.async ring), see pipeline.cuh.
+__global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
+    constexpr int WM = 2, OS = WS_CONSUMERS / 64;
     extern __shared__ __align__(16) double smem[];
-    double* As = smem;
-    double* Bs = smem + P_STAGES * TILE_DOUBLES;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
+    WsBarriers wb{bars, bars + WS_STAGES};
+    double* sh_css = reinterpret_cast<double*>(bars + 2 * WS_STAGES);   // [WM][128]
+    double* sh_mu = sh_css + WM * TILE;                                 // [OS][64][2]
+    double* sh_acc = sh_mu + OS * 64 * 2;                               // [8][256] per-thread running column sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp % WM, wn = warp / WM;
+    const bool producer = warp == WS_CONSUMERS / 32;
+    const int wm = warp & 1, wn = warp >> 1;
     const int gjl = tid & 63, os = tid >> 6;
     const int nb = p.npad / TILE;
     const int total = 8 * (nb * (nb + 1) / 2);
     double* panel = p.scratch + (size_t)blockIdx.x * p.npad * TILE;
 
+    FragLane<false, 64> fa;
+    FragLane<true, 32> fb;
+    fa.init(wm, lane);
+    fb.init(wn, lane);
+    wb.init(tid, 1);
+    __syncthreads();
+
+    int rs = 0;            // ring cursor; both roles walk the same sequence of stages
+    unsigned rph = 0;
+    long fills = 0;
+
     for (int ct = blockIdx.x; ct < p.ntiles; ct += gridDim.x) {
         const int gp0 = ct * 64;
-        // ---------------- phase 1: K* panel + mean -----------------------------------------
+        // ---------------- phase 1 (consumer warps): K* panel + mean ------------------------
         double mu0 = 0.0, mu1 = 0.0;
-        {
+        if (!producer) {
             const int gj = gp0 + gjl;
             const bool gvalid = gj < p.M;
             const double gx = gvalid ? p.Xs[2 * (long)gj] : 0.0;
@@ -71,74 +88,92 @@ __global__ void __launch_bounds__(NT, 1) predict_kernel(PredictArgs p) {
                     mu0 = fma(k11, a0, fma(k12, a1, mu0));
                     mu1 = fma(k12, a0, fma(k22, a1, mu1));
                 }
-                double* r0 = panel + (size_t)(2 * o) * TILE + 2 * gjl;
-                *reinterpret_cast<double2*>(r0) = make_double2(k11, k12);
-                *reinterpret_cast<double2*>(r0 + TILE) = make_double2(k12, k22);
+                // rows k = 2o, 2o+1 of the MN-major tile image: 16-byte chunk gjl, swizzled by k & 3
+                double* r0 = panel + (size_t)(2 * o) * TILE;
+                const int sw = (o & 1) << 2;
+                *reinterpret_cast<double2*>(r0 + 2 * (gjl ^ sw)) = make_double2(k11, k12);
+                *reinterpret_cast<double2*>(r0 + TILE + 2 * (gjl ^ (sw | 2))) = make_double2(k12, k22);
             }
+            fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
         }
-        __syncthreads();      // panel (global) visible to every thread of the CTA
-
-        // ---------------- phase 2: column sums of (Z K*^T)^2 -------------------------------
-        double acc[MB][4][2];
-        double css[4][2];
-#pragma unroll
-        for (int i = 0; i < MB; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) css[j][0] = css[j][1] = 0.0;
-
-        int ci = 0, ckt = 0, li = 0, lkt = 0;      // compute / load cursors (row block, k tile)
-        auto load_AB = [&](int stage) {
-            if (li < nb) {
-                load_tile_async<false, NT>(As + stage * TILE_DOUBLES,
-                                           p.Z + (long)li * TILE * p.ldz + lkt * BK, p.ldz, tid);
-                load_tile_async<true, NT>(Bs + stage * TILE_DOUBLES, panel + (size_t)lkt * BK * TILE, TILE, tid);
-                if (++lkt == 8 * (li + 1)) { lkt = 0; ++li; }
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int s = 0; s < P_STAGES - 1; ++s) load_AB(s);
-
-        for (int it = 0; it < total; ++it) {
-            cp_async_wait<P_STAGES - 2>();
-            __syncthreads();
-            load_AB((it + P_STAGES - 1) % P_STAGES);
-            mma_stage<false, true, MB>(As + (it % P_STAGES) * TILE_DOUBLES, Bs + (it % P_STAGES) * TILE_DOUBLES,
-                                       wm, wn, lane, acc);
-            if (++ckt == 8 * (ci + 1)) {
-                ckt = 0; ++ci;
-#pragma unroll
-                for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        css[j][0] = fma(acc[mb][j][0], acc[mb][j][0], css[j][0]);
-                        css[j][1] = fma(acc[mb][j][1], acc[mb][j][1], css[j][1]);
-                        acc[mb][j][0] = acc[mb][j][1] = 0.0;
-                    }
-            }
+        __syncthreads();      // panel (global) visible to the producer; previous tile's reduce done
+        if (!producer) {
+            sh_mu[(os * 64 + gjl) * 2 + 0] = mu0;
+            sh_mu[(os * 64 + gjl) * 2 + 1] = mu1;
         }
-        cp_async_wait<0>();
-        __syncthreads();      // all panel / smem reads done: both may be reused below
 
-        // reduce css over the 8 row groups of a warp (lane>>2) and the M-warps; mu over the
-        // obs slots.  Fixed order: results do not depend on the grid partition.
-        double* sh_css = smem;               // [WM][128]
-        double* sh_mu = smem + WM * TILE;    // [OS][64][2]
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double v = css[j][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if ((lane >> 2) == 0) sh_css[wm * TILE + wn * 32 + j * 8 + 2 * (lane & 3) + e] = v;
+        if (producer) {
+            // ---------------- phase 2, producer: one thread, two 16 KB bulk copies per stage ----
+            // stage `it` of a column tile pairs Z tile number `it` (tiles are stored in exactly
+            // this order) with panel tile lkt
+            if (lane == 0) {
+                fence_proxy_async();
+                int li = 0, lkt = 0;
+                const double* zt = p.Zt;
+                for (int it = 0; it < total; ++it) {
+                    if (fills >= WS_STAGES) mbar_wait(wb.empty + rs, rph ^ 1u);
+                    double* st = smem + rs * WS_STAGE_DOUBLES;
+                    mbar_arrive_expect_tx(wb.full + rs, 2 * TILE_DOUBLES * (unsigned)sizeof(double));
+                    bulk_g2s(st, zt, TILE_DOUBLES * (unsigned)sizeof(double), wb.full + rs);
+                    bulk_g2s(st + TILE_DOUBLES, panel + (size_t)lkt * TILE_DOUBLES, TILE_DOUBLES * (unsigned)sizeof(double),
+                             wb.full + rs);
+                    zt += TILE_DOUBLES;
+                    ++fills;
+                    if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
+                    if (++lkt == 8 * (li + 1)) { lkt = 0; ++li; }
+                }
             }
-        sh_mu[(os * 64 + gjl) * 2 + 0] = mu0;
-        sh_mu[(os * 64 + gjl) * 2 + 1] = mu1;
-        __syncthreads();
+            __syncwarp();
+        } else {
+            // ---------------- phase 2, consumers: column sums of (Z K*^T)^2 -------------------
+            // the running sums of squares live in thread-private shared-memory slots (touched once
+            // per row block), so the k-loop keeps only the 128 accumulator registers
+            double acc[8][4][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sh_acc[q * WS_CONSUMERS + tid] = 0.0;
+            int ci = 0, ckt = 0;
+            for (int it = 0; it < total; ++it) {
+                mbar_wait(wb.full + rs, rph);
+                const double* st = smem + rs * WS_STAGE_DOUBLES;
+                ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wb.empty + rs);
+                if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
+                if (++ckt == 8 * (ci + 1)) {
+                    ckt = 0; ++ci;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double v = sh_acc[(2 * j + e) * WS_CONSUMERS + tid];
+#pragma unroll
+                            for (int mb = 0; mb < 8; ++mb) {
+                                v = fma(acc[mb][j][e], acc[mb][j][e], v);
+                                acc[mb][j][e] = 0.0;
+                            }
+                            sh_acc[(2 * j + e) * WS_CONSUMERS + tid] = v;
+                        }
+                }
+            }
+            // reduce css over the 8 row groups of a warp (lane>>2); the M-warps and the obs
+            // slots of mu are summed below.  Fixed order: results do not depend on the grid
+            // partition.
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double v = sh_acc[(2 * j + e) * WS_CONSUMERS + tid];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if ((lane >> 2) == 0) sh_css[wm * TILE + wn * 32 + j * 8 + 2 * (lane & 3) + e] = v;
+                }
+        }
+        __syncthreads();      // partials visible; every cp.async of this tile has been consumed
         if (tid < TILE) {
             const int pj = tid >> 1, c = tid & 1;
             const int j = gp0 + pj;
@@ -155,7 +190,7 @@ __global__ void __launch_bounds__(NT, 1) predict_kernel(PredictArgs p) {
                 p.mean[(long)c * p.out_stride + j] = m;
             }
         }
-        __syncthreads();      // sh_* consumed before the next tile's cp.async overwrites smem
+        // the next tile's partials are written only after its first __syncthreads
     }
 }
 
@@ -172,21 +207,19 @@ int predict_max_ctas() {
     return sms;
 }
 
-cudaError_t predict_fused(const double* Z, long ldz, int npad, const double* alpha_int,
+cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           const double* X, int N, const HelmParams& hp, const double* Xs, int M,
                           long out_stride, double var_add, double* mean, double* var,
                           double* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
     static bool init = false;
     if (!init) {
-        cudaError_t e = cudaFuncSetAttribute(predict_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(predict_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         init = true;
     }
     PredictArgs a;
-    a.Z = Z; a.ldz = ldz; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
+    a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
     a.kss = hp.w_df + hp.w_cf;           // ratio/l_df^2 + (1-ratio)/l_cf^2   (myKernel.py:55-57)
     a.var_add = var_add; a.mean = mean; a.var = var;
@@ -200,8 +233,7 @@ cudaError_t predict_fused(const double* Z, long ldz, int npad, const double* alp
     // balance the tail: every CTA gets ceil(ntiles/grid) or one fewer tiles
     long per = (a.ntiles + grid - 1) / grid;
     grid = (a.ntiles + per - 1) / per;
-    if (get_cta_threads() == 512) predict_kernel<512><<<(unsigned)grid, 512, PRED_SMEM_BYTES, st>>>(a);
-    else predict_kernel<256><<<(unsigned)grid, 256, PRED_SMEM_BYTES, st>>>(a);
+    predict_kernel<<<(unsigned)grid, WS_THREADS, PRED_SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
 
