@@ -26,18 +26,20 @@ FitLayout fit_layout(int N) {
     L.npad = round_up(2 * N, TILE);
     const size_t n = (size_t)L.npad, d = sizeof(double);
     size_t o = 0;
+    // scratch of the factorisation / likelihood
     L.off_A = o; o = align256(o + n * n * d);
     L.off_Z = o; o = align256(o + n * n * d);
-    L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
     L.off_logdiag = o; o = align256(o + n * d);
     L.off_yint = o; o = align256(o + n * d);
     L.off_w = o; o = align256(o + n * d);
-    L.off_alpha = o; o = align256(o + n * d);
     size_t nchunks = (n + 255) / 256;
     size_t part = nchunks * n;
     size_t gp = 4 * (size_t)lml_grad_partials(L.npad);
     if (gp > part) part = gp;
     L.off_partial = o; o = align256(o + part * d);
+    // what gp2d_predict reads, contiguous so that it can be shipped to another GPU in one piece
+    L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
+    L.off_alpha = o; o = align256(o + n * d);
     L.off_X = o; o = align256(o + 2 * (size_t)N * d);
     L.off_scal = o; o = align256(o + 16 * d);
     L.off_info = o; o = align256(o + 16);
@@ -278,6 +280,16 @@ int gp2d_dgemm(int transa, int transb, int M, int N, int K, double alpha, const 
 size_t gp2d_fit_workspace_bytes(int N) {
     if (N <= 0) return 0;
     return fit_layout(N).total;
+}
+
+int gp2d_fit_predict_state(int N, size_t* offset, size_t* bytes) {
+    if (N <= 0) return -1;
+    if (!offset) return -2;
+    if (!bytes) return -3;
+    FitLayout L = fit_layout(N);
+    *offset = L.off_Zt;
+    *bytes = L.total - L.off_Zt;
+    return 0;
 }
 
 int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, double ratio,

@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == WS_CONSUMERS / 32;
-    const int wm = warp & 1, wn = warp >> 1;
+    // warps w and w+4 share a scheduler: give them different row halves (wm), so that when one
+    // of them has nothing to do in a stage (see `skip` below) the other gets the whole FP64 pipe
+    const int wm = (warp >> 2) & 1, wn = warp & 3;
     const int gjl = tid & 63, os = tid >> 6;
     const int nb = p.npad / TILE;
     const int total = 8 * (nb * (nb + 1) / 2);
@@ -136,10 +138,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) sh_acc[q * WS_CONSUMERS + tid] = 0.0;
             int ci = 0, ckt = 0;
+            const int nvalid = 2 * p.N;
             for (int it = 0; it < total; ++it) {
                 mbar_wait(wb.full + rs, rph);
                 const double* st = smem + rs * WS_STAGE_DOUBLES;
-                ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                // this warp's 64 rows of Z are exactly zero in this k-tile when the tile lies right
+                // of the diagonal (upper half of a diagonal block) and contribute nothing when they
+                // are identity padding (the matching panel rows are zero): skip the DMMAs
+                const int row0 = ci * TILE + wm * 64;
+                const bool skip = (ckt * BK > row0 + 63) || (row0 >= nvalid);
+                if (!skip) ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(wb.empty + rs);
                 if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }

@@ -48,6 +48,19 @@ def gather_concat(local: torch.Tensor, sizes=None):
     return torch.cat([p[:c] for p, c in zip(parts, counts)])
 
 
+def broadcast_fit(gp, src=0, chunk_bytes=1 << 30):
+    """Ship the fit state of rank ``src`` (L^-1 tiles, alpha, X: HelmholtzGP.predict_state) to
+    every rank, so that one factorisation serves grid shards on all GPUs (the factorisation
+    itself is never distributed).  Broadcast in <= 1 GiB pieces."""
+    rank, ws = world()
+    if ws == 1:
+        return
+    state = gp.predict_state()
+    for lo in range(0, state.numel(), chunk_bytes):
+        dist.broadcast(state[lo:lo + chunk_bytes], src=src)
+    gp.fitted = True
+
+
 def predict_sharded(gp, Xs, include_noise=False):
     """Grid-sharded prediction: rank r predicts its contiguous tile-aligned slice with the
     fit state it holds (every rank fits the same snapshot, or receives it by broadcast), then

@@ -206,6 +206,14 @@ class HelmholtzGP:
         self.lml = float(self._scal[0].item())
         return self.lml
 
+    def predict_state(self) -> torch.Tensor:
+        """Byte view of the part of the fit workspace that predict() reads (one contiguous range);
+        dist.broadcast_fit ships it to the ranks that predict other grid shards."""
+        import ctypes as C
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(lib.gp2d_fit_predict_state(self.N, C.byref(off), C.byref(nb)), "gp2d_fit_predict_state")
+        return self.ws[off.value:off.value + nb.value]
+
     def alpha(self) -> torch.Tensor:
         """K^-1 y in the caller's stacked order."""
         out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)

@@ -313,7 +313,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": K * (1 + potri_launches(npad // 128) + 5 + 1),
+            "gpu_launches": K * (1 + potri_launches(npad // 128) + 1 + 5 + 1),   # build, potri tree, pack, alpha/LML, predict
             "roofline": {
                 "kernel": "predict_kernel (fused K* generation + Z K*^T DMMA + mean/variance)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,

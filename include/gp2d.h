@@ -95,6 +95,12 @@ int gp2d_fit(const double* X, int N, const double* y,
              void* ws, size_t ws_bytes, double* alpha_out, double* lml_out, int* info,
              void* stream);
 
+/* The part of a fit workspace that gp2d_predict reads (L^-1 tiles, alpha, X, LML, info) is one
+ * contiguous byte range [offset, offset + bytes): copy or broadcast it into a workspace of the
+ * same N on another GPU and gp2d_predict works there (grid shards of one snapshot on several
+ * GPUs; the factorisation itself stays on one GPU). */
+int gp2d_fit_predict_state(int N, size_t* offset, size_t* bytes);
+
 /* Predict at Xs[M,2] from a fit state: mean[c*out_stride + j], var[c*out_stride + j],
  * c in {0,1}, j in [0,M).  var = k** - |L^-1 k*|^2 clamped at 0, plus var_add (pass the
  * noise variance to reproduce GPy's predict, 0 for sklearn/GP_laser).

@@ -253,6 +253,23 @@ def test_lml_grad_vs_oracle():
         np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-10)
 
 
+def test_predict_state_ships_to_another_workspace():
+    """What dist.broadcast_fit relies on: the byte range gp2d_fit_predict_state names is all that
+    gp2d_predict reads, so a copy of it in a fresh workspace predicts bit-identically."""
+    X, y = synthetic.drifter_snapshot(300, config_id=7)
+    Xs = synthetic.prediction_grid(X, 23, 11)
+    a = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+    a.fit()
+    m0, v0 = a.predict(Xs)
+    b = gp.HelmholtzGP(X * 0 + 5.0, y * 0, 1.3, 3.1, 0.2, 0.05)      # different data, never fitted
+    b.ws.fill_(255)
+    b.predict_state().copy_(a.predict_state())
+    b.fitted = True
+    m1, v1 = b.predict(Xs)
+    assert torch.equal(m0, m1) and torch.equal(v0, v1)
+    assert a.predict_state().numel() < a.ws.numel() // 2
+
+
 def test_not_positive_definite_raises():
     X = np.zeros((40, 2))                     # coincident points, no noise -> singular
     y = np.ones(80)

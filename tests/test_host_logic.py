@@ -189,6 +189,19 @@ class _FakeGP:
         return torch.cat([m0, m1]), torch.cat([v0, v1])
 
 
+class _FakeFit:
+    """Carries a byte buffer like HelmholtzGP.predict_state()."""
+
+    def __init__(self, rank, nbytes):
+        self.buf = torch.full((nbytes,), 7 if rank == 0 else 0, dtype=torch.uint8)
+        if rank == 0:
+            self.buf[::3] = 1
+        self.fitted = rank == 0
+
+    def predict_state(self):
+        return self.buf
+
+
 class _Run:
     def __init__(self, f, x):
         self.f_opt, self.x_opt = f, np.asarray(x, float)
@@ -233,8 +246,12 @@ def _worker(rank, world, port, out_dir):
         runs = [_Run(5.0 - rank * 3.0 + i, [rank, i, 7.0]) for i in range(2)]
         model = _FakeModel(runs)
         best = gdist.gather_best(model)
+        # one factorisation, shipped to the other rank in pieces
+        fitst = _FakeFit(rank, 1000)
+        gdist.broadcast_fit(fitst, src=0, chunk_bytes=384)
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), got=got.numpy(), mean=mean.numpy(), var=var.numpy(),
-                 best=best, loaded=model.loaded, shard=np.array(gdist.shard_range(200, rank, world)))
+                 best=best, loaded=model.loaded, shard=np.array(gdist.shard_range(200, rank, world)),
+                 state=fitst.buf.numpy(), fitted=fitst.fitted)
     finally:
         dist.destroy_process_group()
 
@@ -251,5 +268,7 @@ def test_gloo_world2_gathers(tmp_path):
         np.testing.assert_array_equal(r[k]["var"], v_ref.numpy())
         assert float(r[k]["best"]) == 2.0                                # rank 1's first run
         np.testing.assert_array_equal(r[k]["loaded"], [1.0, 0.0, 7.0])
+    np.testing.assert_array_equal(r[1]["state"], r[0]["state"])
+    assert r[0]["state"][0] == 1 and r[0]["state"][1] == 7 and bool(r[1]["fitted"])
     np.testing.assert_array_equal(r[0]["shard"], [0, 128])
     np.testing.assert_array_equal(r[1]["shard"], [128, 200])
