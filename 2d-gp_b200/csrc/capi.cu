@@ -324,10 +324,7 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
 
 size_t gp2d_predict_workspace_bytes(int N, int M) {
     if (N <= 0 || M <= 0) return 256;
-    long tiles = ((long)M + 63) / 64;
-    long ctas = predict_max_ctas();
-    if (tiles < ctas) ctas = tiles;
-    return align256((size_t)ctas * predict_panel_bytes(round_up(2 * N, TILE)));
+    return align256(predict_scratch_bytes(round_up(2 * N, TILE), M));
 }
 
 int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, const double* Xs,

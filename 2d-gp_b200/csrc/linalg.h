@@ -46,6 +46,7 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           long out_stride, double var_add, double* mean, double* var,
                           double* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t predict_panel_bytes(int npad);
+size_t predict_scratch_bytes(int npad, int M);      // full parallelism on the current device
 int predict_max_ctas();
 
 // grad.cu ---------------------------------------------------------------------------------

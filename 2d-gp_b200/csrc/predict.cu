@@ -33,22 +33,32 @@ struct PredictArgs {
     double kss, var_add;
     double* mean; double* var;
     double* scratch;              // gridDim.x panels of npad x 128 doubles
-    int ntiles;
+    double* partial;              // [ntiles][8 groups][128] column sums (nsplit > 1)
+    int ntiles, nsplit;
 };
 
-// shared memory: operand ring | mbarriers | epilogue scratch (column sums, mean partials)
-constexpr int PRED_RED_DOUBLES = 2 * TILE + 4 * 64 * 2 + 8 * WS_CONSUMERS;
+// Row-block groups.  The column sums of V^2 are ALWAYS formed as sum_{g=0..7} (group g), where
+// group g owns the row blocks {16 b + g, 16 b + 15 - g : b = 0, 1, ...} (pairs of equal total
+// cost in the triangle).  A work item is (column tile, split s of nsplit in {1,2,4,8}) and covers
+// the groups [s 8/nsplit, (s+1) 8/nsplit): with few column tiles (small grids) the row blocks of
+// one tile are spread over several CTAs, and because the grouping and the order of the final
+// sum never change, the result is bit-identical for every nsplit and every grid partition.
+constexpr int PRED_GROUPS = 8;
+
+// shared memory: operand ring | mbarriers | group column sums [8][2][128] | mean partials [4][64][2]
+constexpr int PRED_MAX_ROWBLOCKS = 1024;          // npad <= 131072
+constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_ROWBLOCKS / 2;
 constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
-// 8 consumer warps (phase 1 + DMMA) and one producer warp (cp.async ring), see pipeline.cuh.
+// 8 consumer warps (phase 1 + DMMA) and one producer warp (bulk-copy ring), see pipeline.cuh.
 __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
     constexpr int WM = 2, OS = WS_CONSUMERS / 64;
     extern __shared__ __align__(16) double smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
     WsBarriers wb{bars, bars + WS_STAGES};
-    double* sh_css = reinterpret_cast<double*>(bars + 2 * WS_STAGES);   // [WM][128]
-    double* sh_mu = sh_css + WM * TILE;                                 // [OS][64][2]
-    double* sh_acc = sh_mu + OS * 64 * 2;                               // [8][256] per-thread running column sums
+    double* sh_grp = reinterpret_cast<double*>(bars + 2 * WS_STAGES);   // [8][WM][128]
+    double* sh_mu = sh_grp + PRED_GROUPS * WM * TILE;                   // [OS][64][2]
+    int* sh_rb = reinterpret_cast<int*>(sh_mu + OS * 64 * 2);           // row blocks of the item: li | group << 16
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == WS_CONSUMERS / 32;
@@ -57,7 +67,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
     const int wm = (warp >> 2) & 1, wn = warp & 3;
     const int gjl = tid & 63, os = tid >> 6;
     const int nb = p.npad / TILE;
-    const int total = 8 * (nb * (nb + 1) / 2);
+    const int gper = PRED_GROUPS / p.nsplit;
     double* panel = p.scratch + (size_t)blockIdx.x * p.npad * TILE;
 
     FragLane<false, 64> fa;
@@ -71,7 +81,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
     unsigned rph = 0;
     long fills = 0;
 
-    for (int ct = blockIdx.x; ct < p.ntiles; ct += gridDim.x) {
+    for (int item = blockIdx.x; item < p.ntiles * p.nsplit; item += gridDim.x) {
+        const int ct = item / p.nsplit, split = item - ct * p.nsplit;
+        const int g0 = split * gper, g1 = g0 + gper;
         const int gp0 = ct * 64;
         // ---------------- phase 1 (consumer warps): K* panel + mean ------------------------
         double mu0 = 0.0, mu1 = 0.0;
@@ -98,7 +110,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
             }
             fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
         }
-        __syncthreads();      // panel (global) visible to the producer; previous tile's reduce done
+        // the item's row blocks in processing order (both roles walk this list)
+        int nrb = 0;
+        for (int g = g0; g < g1; ++g)
+            for (int base = 0; base < nb; base += 2 * PRED_GROUPS) {
+                const int la = base + g, lb = base + 2 * PRED_GROUPS - 1 - g;
+                if (la < nb) { if (tid == 0) sh_rb[nrb] = la | (g << 16); ++nrb; }
+                if (lb < nb) { if (tid == 0) sh_rb[nrb] = lb | (g << 16); ++nrb; }
+            }
+        __syncthreads();      // panel (global) visible to the producer; previous item's reduce done
         if (!producer) {
             sh_mu[(os * 64 + gjl) * 2 + 0] = mu0;
             sh_mu[(os * 64 + gjl) * 2 + 1] = mu1;
@@ -106,100 +126,121 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
 
         if (producer) {
             // ---------------- phase 2, producer: one thread, two 16 KB bulk copies per stage ----
-            // stage `it` of a column tile pairs Z tile number `it` (tiles are stored in exactly
-            // this order) with panel tile lkt
             if (lane == 0) {
                 fence_proxy_async();
-                int li = 0, lkt = 0;
-                const double* zt = p.Zt;
-                for (int it = 0; it < total; ++it) {
-                    if (fills >= WS_STAGES) mbar_wait(wb.empty + rs, rph ^ 1u);
-                    double* st = smem + rs * WS_STAGE_DOUBLES;
-                    mbar_arrive_expect_tx(wb.full + rs, 2 * TILE_DOUBLES * (unsigned)sizeof(double));
-                    bulk_g2s(st, zt, TILE_DOUBLES * (unsigned)sizeof(double), wb.full + rs);
-                    bulk_g2s(st + TILE_DOUBLES, panel + (size_t)lkt * TILE_DOUBLES, TILE_DOUBLES * (unsigned)sizeof(double),
-                             wb.full + rs);
-                    zt += TILE_DOUBLES;
-                    ++fills;
-                    if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
-                    if (++lkt == 8 * (li + 1)) { lkt = 0; ++li; }
+                for (int q = 0; q < nrb; ++q) {
+                    const int li = sh_rb[q] & 0xffff;
+                    // tiles of row block li are stored contiguously from tile 8 li (li+1)/2
+                    const double* zt = p.Zt + (size_t)(4 * li * (li + 1)) * TILE_DOUBLES;
+                    const int nkt = 8 * (li + 1);
+                    for (int lkt = 0; lkt < nkt; ++lkt) {
+                        if (fills >= WS_STAGES) mbar_wait(wb.empty + rs, rph ^ 1u);
+                        double* st = smem + rs * WS_STAGE_DOUBLES;
+                        mbar_arrive_expect_tx(wb.full + rs, 2 * TILE_DOUBLES * (unsigned)sizeof(double));
+                        bulk_g2s(st, zt, TILE_DOUBLES * (unsigned)sizeof(double), wb.full + rs);
+                        bulk_g2s(st + TILE_DOUBLES, panel + (size_t)lkt * TILE_DOUBLES,
+                                 TILE_DOUBLES * (unsigned)sizeof(double), wb.full + rs);
+                        zt += TILE_DOUBLES;
+                        ++fills;
+                        if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
+                    }
                 }
             }
             __syncwarp();
         } else {
             // ---------------- phase 2, consumers: column sums of (Z K*^T)^2 -------------------
-            // the running sums of squares live in thread-private shared-memory slots (touched once
-            // per row block), so the k-loop keeps only the 128 accumulator registers
             double acc[8][4][2];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            // lane (lane>>2)==0 of warp (wm, wn) owns the 8 columns wn*32 + j*8 + 2*(lane&3) + e of
+            // every group slot of its wm: it zeroes and accumulates them (no other writer)
+            const int mycol = wm * TILE + wn * 32 + 2 * (lane & 3);
+            if ((lane >> 2) == 0) {
+                for (int g = 0; g < PRED_GROUPS; ++g)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) sh_acc[q * WS_CONSUMERS + tid] = 0.0;
-            int ci = 0, ckt = 0;
-            const int nvalid = 2 * p.N;
-            for (int it = 0; it < total; ++it) {
-                mbar_wait(wb.full + rs, rph);
-                const double* st = smem + rs * WS_STAGE_DOUBLES;
-                // this warp's 64 rows of Z are exactly zero in this k-tile when the tile lies right
-                // of the diagonal (upper half of a diagonal block) and contribute nothing when they
-                // are identity padding (the matching panel rows are zero): skip the DMMAs
-                const int row0 = ci * TILE + wm * 64;
-                const bool skip = (ckt * BK > row0 + 63) || (row0 >= nvalid);
-                if (!skip) ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(wb.empty + rs);
-                if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
-                if (++ckt == 8 * (ci + 1)) {
-                    ckt = 0; ++ci;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            double v = sh_acc[(2 * j + e) * WS_CONSUMERS + tid];
-#pragma unroll
-                            for (int mb = 0; mb < 8; ++mb) {
-                                v = fma(acc[mb][j][e], acc[mb][j][e], v);
-                                acc[mb][j][e] = 0.0;
-                            }
-                            sh_acc[(2 * j + e) * WS_CONSUMERS + tid] = v;
-                        }
-                }
+                    for (int j = 0; j < 4; ++j) {
+                        sh_grp[g * WM * TILE + mycol + j * 8] = 0.0;
+                        sh_grp[g * WM * TILE + mycol + j * 8 + 1] = 0.0;
+                    }
             }
-            // reduce css over the 8 row groups of a warp (lane>>2); the M-warps and the obs
-            // slots of mu are summed below.  Fixed order: results do not depend on the grid
-            // partition.
+            const int nvalid = 2 * p.N;
+            for (int q = 0; q < nrb; ++q) {
+                    {
+                        const int li = sh_rb[q] & 0xffff, g = sh_rb[q] >> 16;
+                        const int nkt = 8 * (li + 1);
+                        const int row0 = li * TILE + wm * 64;
+                        for (int ckt = 0; ckt < nkt; ++ckt) {
+                            mbar_wait(wb.full + rs, rph);
+                            const double* st = smem + rs * WS_STAGE_DOUBLES;
+                            // this warp's 64 rows of Z are exactly zero in this k-tile when the tile lies
+                            // right of the diagonal (upper half of a diagonal block) and contribute nothing
+                            // when they are identity padding (the matching panel rows are zero)
+                            const bool skip = (ckt * BK > row0 + 63) || (row0 >= nvalid);
+                            if (!skip) ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(wb.empty + rs);
+                            if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
+                        }
+                        // fold this row block: squares summed over the 8 blocks of the thread, then over
+                        // the 8 row lanes (fixed order), then into the group slot
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    double v = sh_acc[(2 * j + e) * WS_CONSUMERS + tid];
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    if ((lane >> 2) == 0) sh_css[wm * TILE + wn * 32 + j * 8 + 2 * (lane & 3) + e] = v;
-                }
+                            for (int e = 0; e < 2; ++e) {
+                                double v = 0.0;
+#pragma unroll
+                                for (int mb = 0; mb < 8; ++mb) {
+                                    v = fma(acc[mb][j][e], acc[mb][j][e], v);
+                                    acc[mb][j][e] = 0.0;
+                                }
+                                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                                if ((lane >> 2) == 0) sh_grp[g * WM * TILE + mycol + j * 8 + e] += v;
+                            }
+                    }
+            }
         }
-        __syncthreads();      // partials visible; every cp.async of this tile has been consumed
+        __syncthreads();      // group sums visible; every bulk copy of this item has been consumed
         if (tid < TILE) {
             const int pj = tid >> 1, c = tid & 1;
             const int j = gp0 + pj;
-            if (j < p.M) {
-                double ss = 0.0;
-#pragma unroll
-                for (int w = 0; w < WM; ++w) ss += sh_css[w * TILE + tid];
-                double v = p.kss - ss;
-                v = v < 0.0 ? 0.0 : v;
-                p.var[(long)c * p.out_stride + j] = v + p.var_add;
+            if (p.nsplit == 1) {
+                if (j < p.M) {
+                    double ss = 0.0;
+                    for (int g = 0; g < PRED_GROUPS; ++g) ss += sh_grp[g * WM * TILE + tid] + sh_grp[g * WM * TILE + TILE + tid];
+                    double v = p.kss - ss;
+                    v = v < 0.0 ? 0.0 : v;
+                    p.var[(long)c * p.out_stride + j] = v + p.var_add;
+                }
+            } else {
+                for (int g = g0; g < g1; ++g)
+                    p.partial[((size_t)ct * PRED_GROUPS + g) * TILE + tid] =
+                        sh_grp[g * WM * TILE + tid] + sh_grp[g * WM * TILE + TILE + tid];
+            }
+            if (split == 0 && j < p.M) {
                 double m = 0.0;
 #pragma unroll
                 for (int o = 0; o < OS; ++o) m += sh_mu[(o * 64 + pj) * 2 + c];
                 p.mean[(long)c * p.out_stride + j] = m;
             }
         }
-        // the next tile's partials are written only after its first __syncthreads
+        // the next item's shared-memory partials are written only after its first __syncthreads
     }
+}
+
+// nsplit > 1: var = k** - sum_g partial[tile][g][col], same order as the in-kernel sum
+__global__ void __launch_bounds__(TILE) predict_finish_kernel(PredictArgs p) {
+    const int ct = blockIdx.x, tid = threadIdx.x;
+    const int j = ct * 64 + (tid >> 1), c = tid & 1;
+    if (j >= p.M) return;
+    double ss = 0.0;
+    for (int g = 0; g < PRED_GROUPS; ++g) ss += p.partial[((size_t)ct * PRED_GROUPS + g) * TILE + tid];
+    double v = p.kss - ss;
+    v = v < 0.0 ? 0.0 : v;
+    p.var[(long)c * p.out_stride + j] = v + p.var_add;
 }
 
 size_t predict_panel_bytes(int npad) { return (size_t)npad * TILE * sizeof(double); }
@@ -213,6 +254,32 @@ int predict_max_ctas() {
             sms = 148;
     }
     return sms;
+}
+
+// Split of the row blocks of one column tile over CTAs: the smallest nsplit in {1,2,4,8} whose
+// number of rounds ceil(ntiles nsplit / SMs) / nsplit is within 3 % of the best.
+int predict_choose_split(long ntiles) {
+    const long sms = predict_max_ctas();
+    double best = 1e300;
+    double r[4];
+    for (int i = 0; i < 4; ++i) {
+        const long s = 1L << i;
+        r[i] = (double)((ntiles * s + sms - 1) / sms) / (double)s;
+        if (r[i] < best) best = r[i];
+    }
+    for (int i = 0; i < 4; ++i)
+        if (r[i] <= best * 1.03) return 1 << i;
+    return 1;
+}
+
+size_t predict_partial_bytes(long ntiles) { return (size_t)ntiles * PRED_GROUPS * TILE * sizeof(double); }
+
+size_t predict_scratch_bytes(int npad, int M) {
+    const long ntiles = ((long)M + 63) / 64;
+    const int ns = predict_choose_split(ntiles);
+    long ctas = predict_max_ctas();
+    if (ntiles * ns < ctas) ctas = ntiles * ns;
+    return (size_t)ctas * predict_panel_bytes(npad) + (ns > 1 ? predict_partial_bytes(ntiles) : 0);
 }
 
 cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
@@ -231,17 +298,26 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
     a.kss = hp.w_df + hp.w_cf;           // ratio/l_df^2 + (1-ratio)/l_cf^2   (myKernel.py:55-57)
     a.var_add = var_add; a.mean = mean; a.var = var;
-    a.scratch = scratch;
     a.ntiles = (M + 63) / 64;
-    long panels = (long)(scratch_bytes / predict_panel_bytes(npad));
-    long grid = a.ntiles;
+    // scratch = [partial sums (nsplit > 1)] [one K* panel per CTA]; a buffer too small for the
+    // partials falls back to nsplit = 1, fewer panels only shrink the grid
+    a.nsplit = predict_choose_split(a.ntiles);
+    size_t pb = predict_partial_bytes(a.ntiles);
+    if (a.nsplit > 1 && scratch_bytes < pb + predict_panel_bytes(npad)) a.nsplit = 1;
+    if (a.nsplit == 1) pb = 0;
+    a.partial = scratch;
+    a.scratch = scratch + pb / sizeof(double);
+    long panels = (long)((scratch_bytes - pb) / predict_panel_bytes(npad));
+    const long items = (long)a.ntiles * a.nsplit;
+    long grid = items;
     if (grid > predict_max_ctas()) grid = predict_max_ctas();
     if (grid > panels) grid = panels;
     if (grid <= 0) return cudaErrorInvalidValue;
-    // balance the tail: every CTA gets ceil(ntiles/grid) or one fewer tiles
-    long per = (a.ntiles + grid - 1) / grid;
-    grid = (a.ntiles + per - 1) / per;
+    // balance the tail: every CTA gets ceil(items/grid) or one fewer items
+    long per = (items + grid - 1) / grid;
+    grid = (items + per - 1) / per;
     predict_kernel<<<(unsigned)grid, WS_THREADS, PRED_SMEM_BYTES, st>>>(a);
+    if (a.nsplit > 1) predict_finish_kernel<<<a.ntiles, TILE, 0, st>>>(a);
     return cudaGetLastError();
 }
 

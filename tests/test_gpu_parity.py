@@ -253,6 +253,39 @@ def test_lml_grad_vs_oracle():
         np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-10)
 
 
+@pytest.mark.parametrize("N", [100, 700, 1100])
+def test_predict_row_block_split_invariance(N):
+    """Small grids spread the row blocks of a column tile over several CTAs (nsplit up to 8); the
+    grouping and summation order are fixed, so any grid size gives the same bits, and the oracle
+    agrees."""
+    X, y = synthetic.drifter_snapshot(N, config_id=8, seed_offset=N)
+    big = synthetic.prediction_grid(X, 160, 120)                 # 19 200 points: 300 tiles
+    m = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+    m.fit()
+    mb, vb = m.predict(big)
+    Mb = big.shape[0]
+    for M in (1, 63, 64, 65, 640, 2601, 9472):
+        mm, vv = m.predict(big[:M])
+        assert torch.equal(mm, torch.cat([mb[:M], mb[Mb:Mb + M]])), M
+        assert torch.equal(vv, torch.cat([vb[:M], vb[Mb:Mb + M]])), M
+    # a scratch buffer too small for the split falls back to one CTA per tile: same bits
+    from gp2d_b200.engine import _ptr, _stream
+    M = 640
+    Xsd = gp.as_dev(big[:M])
+    small = torch.empty(8 * 128 * (((2 * N + 127) // 128) * 128), dtype=torch.uint8, device=DEV)   # exactly one K* panel
+    mean = torch.empty(2 * M, dtype=torch.float64, device=DEV)
+    var = torch.empty(2 * M, dtype=torch.float64, device=DEV)
+    rc = lib.gp2d_predict(_ptr(m.ws), N, 1.3, 3.1, 0.2, _ptr(Xsd), M, M, 0.0, _ptr(mean), _ptr(var), _ptr(small),
+                          small.numel(), _stream())
+    assert rc == 0
+    assert torch.equal(mean, torch.cat([mb[:M], mb[Mb:Mb + M]])) and torch.equal(var, torch.cat([vb[:M], vb[Mb:Mb + M]]))
+    f = orc.fit(X, y, 1.3, 3.1, 0.2, 0.05)
+    mo, vo = orc.predict(X, f, 1.3, 3.1, 0.2, big[:2601])
+    mm, vv = m.predict(big[:2601])
+    np.testing.assert_allclose(mm.cpu().numpy(), mo, rtol=1e-8, atol=1e-9 * np.abs(mo).max())
+    np.testing.assert_allclose(vv.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+
+
 def test_predict_state_ships_to_another_workspace():
     """What dist.broadcast_fit relies on: the byte range gp2d_fit_predict_state names is all that
     gp2d_predict reads, so a copy of it in a fresh workspace predicts bit-identically."""
