@@ -21,9 +21,11 @@ struct FitLayout {
     size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_alpha, off_partial, off_X, off_scal, off_info, total;
 };
 
-FitLayout fit_layout(int N) {
+// n: scalar observations; x_doubles: size of the copy of the observation points;
+// grad_doubles: partial-sum doubles the likelihood-gradient reduction needs
+FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doubles) {
     FitLayout L;
-    L.npad = round_up(2 * N, TILE);
+    L.npad = round_up((int)n_scalar, TILE);
     const size_t n = (size_t)L.npad, d = sizeof(double);
     size_t o = 0;
     // scratch of the factorisation / likelihood
@@ -34,17 +36,24 @@ FitLayout fit_layout(int N) {
     L.off_w = o; o = align256(o + n * d);
     size_t nchunks = (n + 255) / 256;
     size_t part = nchunks * n;
-    size_t gp = 4 * (size_t)lml_grad_partials(L.npad);
-    if (gp > part) part = gp;
+    if (grad_doubles > part) part = grad_doubles;
     L.off_partial = o; o = align256(o + part * d);
     // what gp2d_predict reads, contiguous so that it can be shipped to another GPU in one piece
     L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
     L.off_alpha = o; o = align256(o + n * d);
-    L.off_X = o; o = align256(o + 2 * (size_t)N * d);
-    L.off_scal = o; o = align256(o + 16 * d);
+    L.off_X = o; o = align256(o + x_doubles * d);
+    L.off_scal = o; o = align256(o + 32 * d);
     L.off_info = o; o = align256(o + 16);
     L.total = o;
     return L;
+}
+
+FitLayout fit_layout(int N) {
+    return fit_layout_general(2 * (size_t)N, 2 * (size_t)N, 4 * (size_t)lml_grad_partials(round_up(2 * N, TILE)));
+}
+
+FitLayout rbf_layout(int N, int D) {
+    return fit_layout_general((size_t)N, (size_t)N * D, (size_t)rbf_lml_grad_partial_doubles(round_up(N, TILE)));
 }
 
 template <class T>
@@ -139,7 +148,7 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
-    return solve_alpha_lml(Z, L.npad, L.npad, N, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+    return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
                            at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
                            at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
 }
@@ -324,7 +333,7 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
 
 size_t gp2d_predict_workspace_bytes(int N, int M) {
     if (N <= 0 || M <= 0) return 256;
-    return align256(predict_scratch_bytes(round_up(2 * N, TILE), M));
+    return align256(predict_scratch_bytes(round_up(2 * N, TILE), M, 64));
 }
 
 int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, const double* Xs,
@@ -375,6 +384,167 @@ int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l
                         reference_compat != 0, at<double>(ws, L.off_partial), scal + 1, st);
     if (e != cudaSuccess) return cuda_rc(e);
     e = cudaMemcpyAsync(out5, scal, 5 * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
+/* ---- scalar ARD-RBF sum family --------------------------------------------------------------- */
+
+namespace {
+cudaError_t rbf_fit_core(const double* X, int N, const double* y, const RbfParams& rp, double diag_add, void* ws,
+                         const FitLayout& L, cudaStream_t st) {
+    double* A = at<double>(ws, L.off_A);
+    double* Z = at<double>(ws, L.off_Z);
+    cudaError_t e;
+    e = cudaMemcpyAsync(at<double>(ws, L.off_X), X, (size_t)N * rp.D * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = rbf_build_padded_lower(X, N, rp, diag_add, A, L.npad, L.npad, st);
+    if (e != cudaSuccess) return e;
+    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
+                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    if (e != cudaSuccess) return e;
+    e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
+    if (e != cudaSuccess) return e;
+    return solve_alpha_lml(Z, L.npad, L.npad, N, 1, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+                           at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
+                           at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+}
+}  // namespace
+
+int gp2d_rbf_kernel_build(const double* X, int N, const double* X2, int M, int D, int Q, const double* var,
+                          const double* ls, double diag_add, double* K, int64_t ldk, void* stream) {
+    if (!X) return -1;
+    if (N < 0) return -2;
+    if (M < 0 || (X2 == nullptr && M != N)) return -4;
+    RbfParams rp;
+    if (!make_rbf(D, Q, var, ls, &rp)) return -5;
+    if (!K && N > 0 && M > 0) return -10;
+    if (ldk < M) return -11;
+    return cuda_rc(rbf_build(X, N, X2, M, rp, diag_add, K, (long)ldk, (cudaStream_t)stream));
+}
+
+size_t gp2d_rbf_kernel_grad_workspace_bytes(int N, int M) {
+    if (N <= 0 || M <= 0) return 256;
+    return align256(sizeof(double) * RBF_NG * ((size_t)rbf_grad_partials(N, M) + 1));
+}
+
+int gp2d_rbf_kernel_grad(const double* X, int N, const double* X2, int M, int D, int Q, const double* var,
+                         const double* ls, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                         double* out, void* stream) {
+    if (!X) return -1;
+    if (N <= 0) return -2;
+    if (M <= 0 || (X2 == nullptr && M != N)) return -4;
+    RbfParams rp;
+    if (!make_rbf(D, Q, var, ls, &rp)) return -5;
+    if (!dL_dK) return -9;
+    if (ld < M) return -10;
+    if (!ws || ws_bytes < gp2d_rbf_kernel_grad_workspace_bytes(N, M)) return -12;
+    if (!out) return -13;
+    return cuda_rc(rbf_grad_sums(X, N, X2, M, rp, dL_dK, (long)ld, (double*)ws,
+                                 (int)(ws_bytes / (RBF_NG * sizeof(double))), out, (cudaStream_t)stream));
+}
+
+size_t gp2d_rbf_fit_workspace_bytes(int N, int D) {
+    if (N <= 0 || D < 1 || D > RBF_MAXD) return 0;
+    return rbf_layout(N, D).total;
+}
+
+int gp2d_rbf_fit_predict_state(int N, int D, size_t* offset, size_t* bytes) {
+    if (N <= 0) return -1;
+    if (D < 1 || D > RBF_MAXD) return -2;
+    if (!offset) return -3;
+    if (!bytes) return -4;
+    FitLayout L = rbf_layout(N, D);
+    *offset = L.off_Zt;
+    *bytes = L.total - L.off_Zt;
+    return 0;
+}
+
+int gp2d_rbf_fit(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
+                 double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out, double* lml_out,
+                 int* info, void* stream) {
+    if (!X) return -1;
+    if (N <= 0) return -2;
+    if (!y) return -4;
+    RbfParams rp;
+    if (!make_rbf(D, Q, var, ls, &rp)) return -5;
+    if (!(noise >= 0.0)) return -8;
+    if (!(jitter >= 0.0)) return -9;
+    FitLayout L = rbf_layout(N, D);
+    if (!ws) return -10;
+    if (ws_bytes < L.total) return -11;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = rbf_fit_core(X, N, y, rp, noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (alpha_out) {
+        e = cudaMemcpyAsync(alpha_out, at<double>(ws, L.off_alpha), (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (lml_out) {
+        e = cudaMemcpyAsync(lml_out, at<double>(ws, L.off_scal), sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
+size_t gp2d_rbf_predict_workspace_bytes(int N, int M) {
+    if (N <= 0 || M <= 0) return 256;
+    return align256(predict_scratch_bytes(round_up(N, TILE), M, 128));
+}
+
+int gp2d_rbf_predict(const void* fit_ws, int N, int D, int Q, const double* var, const double* ls,
+                     const double* Xs, int M, double var_add, double* mean, double* variance, void* ws,
+                     size_t ws_bytes, void* stream) {
+    if (!fit_ws) return -1;
+    if (N <= 0) return -2;
+    RbfParams rp;
+    if (!make_rbf(D, Q, var, ls, &rp)) return -3;
+    if (M < 0) return -8;
+    if (M == 0) return 0;
+    if (!Xs) return -7;
+    if (!mean) return -10;
+    if (!variance) return -11;
+    FitLayout L = rbf_layout(N, D);
+    if (!ws) return -12;
+    if (ws_bytes < predict_panel_bytes(L.npad)) return -13;
+    return cuda_rc(predict_fused_rbf(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
+                                     at<double>(fit_ws, L.off_X), N, rp, Xs, M, var_add, mean, variance,
+                                     (double*)ws, ws_bytes, (cudaStream_t)stream));
+}
+
+int gp2d_rbf_lml_grad(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
+                      double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream) {
+    if (!X) return -1;
+    if (N <= 0) return -2;
+    if (!y) return -4;
+    RbfParams rp;
+    if (!make_rbf(D, Q, var, ls, &rp)) return -5;
+    if (!(noise >= 0.0)) return -8;
+    if (!(jitter >= 0.0)) return -9;
+    FitLayout L = rbf_layout(N, D);
+    if (!ws) return -10;
+    if (ws_bytes < L.total) return -11;
+    if (!out) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = rbf_fit_core(X, N, y, rp, noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* Z = at<double>(ws, L.off_Z);
+    double* Kinv = at<double>(ws, L.off_A);
+    e = launch_dgemm(true, true, GemmArgs{Z, L.npad, Z, L.npad, Kinv, L.npad, L.npad, L.npad, L.npad, 1.0, 0.0, 1, KR_GE_M}, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* scal = at<double>(ws, L.off_scal);
+    e = rbf_lml_grad_reduce(Kinv, L.npad, L.npad, at<double>(ws, L.off_alpha), at<double>(ws, L.off_X), N, rp,
+                            at<double>(ws, L.off_partial), scal + 1, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemcpyAsync(out, scal, (size_t)(2 + Q * (1 + D)) * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (info) {
         e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);

@@ -67,4 +67,72 @@ cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double*
     return cudaGetLastError();
 }
 
+// ---- scalar ARD-RBF sum ----------------------------------------------------------------------
+// out[Q (1 + D) + 1] = d LML / d(var_q, l_{q,d})_q, d LML / d noise, from Kinv (lower tiles, plain
+// observation order, padded) and alpha.  One CTA per 128 x 128 lower tile.
+__global__ void __launch_bounds__(256)
+rbf_lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                    const double* __restrict__ X, int N, RbfParams rp, double* __restrict__ partial) {
+    __shared__ double sh[(RBF_NG + 1) * 32];
+    int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((long)I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int j = J * TILE + (threadIdx.x & 127), half = threadIdx.x >> 7;
+    double acc[RBF_NG + 1];
+#pragma unroll
+    for (int q = 0; q <= RBF_NG; ++q) acc[q] = 0.0;
+    if (j < N) {
+        double b[RBF_MAXD];
+        rbf_load_point(X, j, rp.D, b);
+        const double aj = alpha[j];
+        for (int ii = half; ii < TILE; ii += 2) {
+            const int i = I * TILE + ii;
+            if (i >= N || i < j) continue;
+            double a[RBF_MAXD];
+            rbf_load_point(X, i, rp.D, a);
+            const double W = 0.5 * (alpha[i] * aj - Kinv[(long)i * ld + j]);
+            double g[RBF_NG];
+#pragma unroll
+            for (int q = 0; q < RBF_NG; ++q) g[q] = 0.0;
+            rbf_grad_terms(rp, a, b, (i == j) ? W : 2.0 * W, g);
+#pragma unroll
+            for (int q = 0; q < RBF_NG; ++q) acc[q] += g[q];
+            if (i == j) acc[RBF_NG] += W;
+        }
+    }
+    block_reduce<RBF_NG + 1>(acc, sh);
+    if (threadIdx.x == 0) {
+        double* o = partial + (RBF_NG + 1) * (long)blockIdx.x;
+#pragma unroll
+        for (int q = 0; q <= RBF_NG; ++q) o[q] = acc[q];
+    }
+}
+
+__global__ void rbf_lml_grad_compact_kernel(const double* __restrict__ full, int Q, int D, double* __restrict__ out) {
+    const int t = threadIdx.x, np = Q * (1 + D);
+    if (t < np) {
+        const int q = t / (1 + D), r = t % (1 + D);
+        out[t] = full[q * (1 + RBF_MAXD) + r];
+    } else if (t == np) {
+        out[np] = full[RBF_NG];
+    }
+}
+
+int rbf_lml_grad_partial_doubles(int npad) {
+    const int T = npad / TILE;
+    return (RBF_NG + 1) * (T * (T + 1) / 2 + 1);
+}
+
+cudaError_t rbf_lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha, const double* X, int N,
+                                const RbfParams& rp, double* partial, double* out, cudaStream_t st) {
+    const int T = npad / TILE, count = T * (T + 1) / 2;
+    double* full = partial + (size_t)(RBF_NG + 1) * count;
+    rbf_lml_grad_kernel<<<count, 256, 0, st>>>(Kinv, ld, alpha, X, N, rp, partial);
+    final_reduce_kernel<RBF_NG + 1><<<1, 1024, 0, st>>>(partial, count, full);
+    rbf_lml_grad_compact_kernel<<<1, 32, 0, st>>>(full, rp.Q, rp.D, out);
+    return cudaGetLastError();
+}
+
 }  // namespace gp2d

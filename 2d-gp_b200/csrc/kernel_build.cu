@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "linalg.h"
 #include "reduce.cuh"
+#include "rbf.cuh"
 
 namespace gp2d {
 
@@ -104,6 +105,132 @@ cudaError_t build_interleaved_lower(const double* X, int N, const HelmParams& hp
                                     double* K, long ldk, int npad, cudaStream_t st) {
     const int T = npad / TILE;
     build_interleaved_kernel<<<T * (T + 1) / 2, 256, 0, st>>>(X, N, hp, diag_add, K, ldk);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// scalar ARD-RBF sum (rbf.cuh): K[N,M] row-major.  CTA = 128 columns x 32 rows; a thread owns 2
+// adjacent columns x 8 rows.  PADDED: internal lower 128x128 tiles with identity padding.
+// ---------------------------------------------------------------------------------------
+template <bool PADDED>
+__global__ void __launch_bounds__(256)
+rbf_build_kernel(const double* __restrict__ X, int N, const double* __restrict__ X2, int M, RbfParams rp,
+                 double diag_add, int symmetric, double* __restrict__ K, long ldk) {
+    int bi, bj;
+    if (PADDED) {
+        int t = blockIdx.x;
+        int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+        while ((long)I * (I + 1) / 2 > t) --I;
+        bj = t - I * (I + 1) / 2;
+        bi = I * 4 + blockIdx.y;             // 4 row slabs of 32 per 128-tile
+    } else {
+        bj = blockIdx.x;
+        bi = blockIdx.y;
+    }
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int j0 = bj * 128 + tx * 2;
+    const int i0 = bi * 32 + ty * 8;
+    if (!PADDED && j0 >= M) return;
+    const bool v0 = j0 < M, v1 = j0 + 1 < M;
+    double b0[RBF_MAXD], b1[RBF_MAXD];
+    rbf_load_point(X2, v0 ? j0 : 0, rp.D, b0);
+    rbf_load_point(X2, v1 ? j0 + 1 : 0, rp.D, b1);
+#pragma unroll 2
+    for (int r = 0; r < 8; ++r) {
+        const int i = i0 + r;
+        if (!PADDED && i >= N) break;
+        double k0 = 0.0, k1 = 0.0;
+        if (i < N) {
+            double a[RBF_MAXD];
+            rbf_load_point(X, i, rp.D, a);
+            if (v0) k0 = rbf_eval(rp, a, b0);
+            if (v1) k1 = rbf_eval(rp, a, b1);
+            if (symmetric) {
+                if (i == j0) k0 += diag_add;
+                if (i == j0 + 1) k1 += diag_add;
+            }
+        } else {                              // padding rows: identity
+            k0 = (i == j0) ? 1.0 : 0.0;
+            k1 = (i == j0 + 1) ? 1.0 : 0.0;
+        }
+        if (PADDED) {
+            *reinterpret_cast<double2*>(K + (long)i * ldk + j0) = make_double2(k0, k1);
+        } else {
+            double* o = K + (long)i * ldk + j0;
+            o[0] = k0;
+            if (v1) o[1] = k1;
+        }
+    }
+}
+
+cudaError_t rbf_build(const double* X, int N, const double* X2, int M, const RbfParams& rp, double diag_add,
+                      double* K, long ldk, cudaStream_t st) {
+    if (N <= 0 || M <= 0) return cudaSuccess;
+    const int symmetric = (X2 == nullptr);
+    if (symmetric) X2 = X;
+    dim3 grid((M + 127) / 128, (N + 31) / 32);
+    rbf_build_kernel<false><<<grid, 256, 0, st>>>(X, N, X2, M, rp, diag_add, symmetric, K, ldk);
+    return cudaGetLastError();
+}
+
+cudaError_t rbf_build_padded_lower(const double* X, int N, const RbfParams& rp, double diag_add, double* K,
+                                   long ldk, int npad, cudaStream_t st) {
+    const int T = npad / TILE;
+    rbf_build_kernel<true><<<dim3(T * (T + 1) / 2, 4), 256, 0, st>>>(X, N, X, N, rp, diag_add, 1, K, ldk);
+    return cudaGetLastError();
+}
+
+// sum(dK/dtheta * dL_dK) for theta = (var_q, l_{q,0..D-1})_q : out[Q (1 + D)], dL_dK is [N, M]
+//   dK/dvar_q = k_q / var_q ;  dK/dl_{q,d} = k_q * delta_d^2 / l_{q,d}^3        (GPy RBF, ARD)
+__global__ void __launch_bounds__(256)
+rbf_grad_sums_kernel(const double* __restrict__ X, int N, const double* __restrict__ X2, int M, RbfParams rp,
+                     const double* __restrict__ W, long ld, double* __restrict__ partial) {
+    __shared__ double sh[RBF_NG * 32];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int j = blockIdx.x * 64 + tx;
+    double acc[RBF_NG];
+#pragma unroll
+    for (int q = 0; q < RBF_NG; ++q) acc[q] = 0.0;
+    if (j < M) {
+        double b[RBF_MAXD];
+        rbf_load_point(X2, j, rp.D, b);
+        for (int r = 0; r < 8; ++r) {
+            const int i = blockIdx.y * 32 + ty * 8 + r;
+            if (i >= N) break;
+            double a[RBF_MAXD];
+            rbf_load_point(X, i, rp.D, a);
+            rbf_grad_terms(rp, a, b, W[(long)i * ld + j], acc);
+        }
+    }
+    block_reduce<RBF_NG>(acc, sh);
+    if (threadIdx.x == 0) {
+        double* o = partial + RBF_NG * ((long)blockIdx.y * gridDim.x + blockIdx.x);
+#pragma unroll
+        for (int q = 0; q < RBF_NG; ++q) o[q] = acc[q];
+    }
+}
+
+__global__ void rbf_grad_compact_kernel(const double* __restrict__ full, int Q, int D, double* __restrict__ out) {
+    const int t = threadIdx.x;
+    if (t < Q * (1 + D)) {
+        const int q = t / (1 + D), r = t % (1 + D);
+        out[t] = full[q * (1 + RBF_MAXD) + r];
+    }
+}
+
+int rbf_grad_partials(int N, int M) { return ((M + 63) / 64) * ((N + 31) / 32); }
+
+cudaError_t rbf_grad_sums(const double* X, int N, const double* X2, int M, const RbfParams& rp, const double* dL_dK,
+                          long ld, double* partial, int partial_cap, double* out, cudaStream_t st) {
+    if (X2 == nullptr) X2 = X;
+    dim3 grid((M + 63) / 64, (N + 31) / 32);
+    const int count = grid.x * grid.y;
+    if (count + 1 > partial_cap) return cudaErrorInvalidValue;
+    double* full = partial + (size_t)RBF_NG * count;
+    rbf_grad_sums_kernel<<<grid, 256, 0, st>>>(X, N, X2, M, rp, dL_dK, ld, partial);
+    final_reduce_kernel<RBF_NG><<<1, 1024, 0, st>>>(partial, count, full);
+    rbf_grad_compact_kernel<<<1, 32, 0, st>>>(full, rp.Q, rp.D, out);
     return cudaGetLastError();
 }
 

@@ -318,11 +318,16 @@ cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cu
 // ------------------------------------------------------------------------------------
 // vectors: y -> interleaved, w = Z y, alpha = Z^T w, LML
 // ------------------------------------------------------------------------------------
-__global__ void interleave_kernel(const double* __restrict__ y, int N, double* __restrict__ yi, int npad) {
+// ncomp = 2: stacked [u; v] -> pair-interleaved; ncomp = 1: scalar observations, zero padded
+__global__ void interleave_kernel(const double* __restrict__ y, int N, int ncomp, double* __restrict__ yi, int npad) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npad) return;
-    int i = p >> 1, c = p & 1;
-    yi[p] = (i < N) ? y[(long)c * N + i] : 0.0;
+    if (ncomp == 2) {
+        int i = p >> 1, c = p & 1;
+        yi[p] = (i < N) ? y[(long)c * N + i] : 0.0;
+    } else {
+        yi[p] = (p < N) ? y[p] : 0.0;
+    }
 }
 
 __global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double* __restrict__ x) {
@@ -368,9 +373,9 @@ __global__ void colsum_partials_kernel(const double* __restrict__ partial, int n
     out[j] = s;
 }
 
-// out[0] = -0.5 w'w - sum logdiag - N log(2 pi)      (n = 2N observations)
+// out[0] = -0.5 w'w - sum logdiag - (n/2) log(2 pi)      (n scalar observations)
 __global__ void lml_kernel(const double* __restrict__ w, const double* __restrict__ logdiag, int npad,
-                           int N, double* __restrict__ out) {
+                           double half_n, double* __restrict__ out) {
     __shared__ double sh[2][32];
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < npad; i += blockDim.x) { a = fma(w[i], w[i], a); b += logdiag[i]; }
@@ -382,19 +387,19 @@ __global__ void lml_kernel(const double* __restrict__ w, const double* __restric
     if (threadIdx.x == 0) {
         double sa = 0.0, sb = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { sa += sh[0][i]; sb += sh[1][i]; }
-        out[0] = -0.5 * sa - sb - (double)N * 1.8378770664093454836;   // log(2 pi)
+        out[0] = -0.5 * sa - sb - half_n * 1.8378770664093454836;   // log(2 pi)
     }
 }
 
-cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, const double* y_block,
+cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st) {
-    interleave_kernel<<<(npad + 255) / 256, 256, 0, st>>>(y_block, N, y_int, npad);
+    interleave_kernel<<<(npad + 255) / 256, 256, 0, st>>>(y_block, N, ncomp, y_int, npad);
     trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, st>>>(Z, ldz, y_int, w, npad);
     int nchunks = (npad + TRMVT_ROWS - 1) / TRMVT_ROWS;
     trmvT_partial_kernel<<<dim3(npad / 128, nchunks), 128, 0, st>>>(Z, ldz, w, partial, npad);
     colsum_partials_kernel<<<(npad + 255) / 256, 256, 0, st>>>(partial, nchunks, npad, alpha_int);
-    lml_kernel<<<1, 1024, 0, st>>>(w, logdiag, npad, N, lml_out);
+    lml_kernel<<<1, 1024, 0, st>>>(w, logdiag, npad, 0.5 * ncomp * (double)N, lml_out);
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "helmholtz.cuh"
+#include "rbf.cuh"
 
 namespace gp2d {
 
@@ -12,9 +13,10 @@ namespace gp2d {
 // log(L_ii); *info the 1-based index of the first non-positive pivot, else 0.
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
                         bool need_inv, bool keep_L, double* W, cudaStream_t st);
-// alpha = Z^T Z y and LML from Z, logdiag.  y_block is the caller's [u;v] vector (2N);
-// everything else is internal (interleaved, padded to npad).
-cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, const double* y_block,
+// alpha = Z^T Z y and LML from Z, logdiag.  y_block is the caller's vector: stacked [u;v] of
+// length 2N (ncomp = 2) or N scalar observations (ncomp = 1); everything else is internal
+// (pair-interleaved for ncomp = 2, padded to npad).
+cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st);
 cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st);
@@ -38,6 +40,17 @@ cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int
                                    int partial_cap, double* out3, cudaStream_t st);
 int grad_sums_block_partials(int N, int M);
 
+// scalar ARD-RBF sum (rbf.cuh): K[N,M] row-major; internal padded lower tiles; sum(dK/dtheta * dL_dK)
+// with out[Q (1 + D)] ordered (var_q, l_{q,0..D-1}) per component; partial holds
+// (rbf_grad_partials + 1) * RBF_MAXQ * (1 + RBF_MAXD) doubles.
+cudaError_t rbf_build(const double* X, int N, const double* X2, int M, const RbfParams& rp, double diag_add,
+                      double* K, long ldk, cudaStream_t st);
+cudaError_t rbf_build_padded_lower(const double* X, int N, const RbfParams& rp, double diag_add, double* K,
+                                   long ldk, int npad, cudaStream_t st);
+int rbf_grad_partials(int N, int M);
+cudaError_t rbf_grad_sums(const double* X, int N, const double* X2, int M, const RbfParams& rp, const double* dL_dK,
+                          long ld, double* partial, int partial_cap, double* out, cudaStream_t st);
+
 // predict.cu ------------------------------------------------------------------------------
 // scratch: one [npad x 128] K* panel per resident CTA (at most one CTA per SM is launched;
 // fewer panels only reduce the grid).
@@ -46,7 +59,11 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           long out_stride, double var_add, double* mean, double* var,
                           double* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t predict_panel_bytes(int npad);
-size_t predict_scratch_bytes(int npad, int M);      // full parallelism on the current device
+size_t predict_scratch_bytes(int npad, int M, int pts_per_tile);   // full parallelism on the current device
+// scalar ARD-RBF sum: alpha and the tiles are in plain observation order (npad = N rounded up to 128)
+cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, const double* X, int N,
+                              const RbfParams& rp, const double* Xs, int M, double var_add, double* mean,
+                              double* var, double* scratch, size_t scratch_bytes, cudaStream_t st);
 int predict_max_ctas();
 
 // grad.cu ---------------------------------------------------------------------------------
@@ -55,5 +72,9 @@ cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double*
                             const double* X, int N, const HelmParams& hp, int compat,
                             double* partial, double* out4, cudaStream_t st);
 int lml_grad_partials(int npad);
+// scalar ARD-RBF sum: out[Q (1 + D) + 1] = d LML / d(var_q, l_{q,0..D-1})_q, then d LML / d noise
+int rbf_lml_grad_partial_doubles(int npad);
+cudaError_t rbf_lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha, const double* X, int N,
+                                const RbfParams& rp, double* partial, double* out, cudaStream_t st);
 
 }  // namespace gp2d

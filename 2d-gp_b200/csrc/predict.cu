@@ -23,11 +23,14 @@
 
 namespace gp2d {
 
+enum : int { FAM_HELM = 0, FAM_RBF = 1 };
+
 struct PredictArgs {
     const double* Zt; int npad;     // L^-1 as pre-swizzled 128 x 16 tiles, row block major (linalg.h)
-    const double* alpha;          // interleaved, zero padded to npad
-    const double* X; int N;
+    const double* alpha;          // internal order (pair-interleaved for the vector kernel), zero padded to npad
+    const double* X; int N;       // observation points [N,2] (Helmholtz) or [N,D] (RBF)
     HelmParams hp;
+    RbfParams rp;
     const double* Xs; int M;
     long out_stride;              // component stride of mean/var
     double kss, var_add;
@@ -51,7 +54,11 @@ constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_
 constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
 // 8 consumer warps (phase 1 + DMMA) and one producer warp (bulk-copy ring), see pipeline.cuh.
+// FAM selects the covariance family of phase 1: the matrix-valued Helmholtz kernel (a column tile
+// is 64 grid points x 2 components) or the scalar ARD-RBF sum (a column tile is 128 grid points).
+template <int FAM>
 __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
+    constexpr int PTS = FAM == FAM_HELM ? 64 : 128;      // grid points per column tile
     constexpr int WM = 2, OS = WS_CONSUMERS / 64;
     extern __shared__ __align__(16) double smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
@@ -84,10 +91,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
     for (int item = blockIdx.x; item < p.ntiles * p.nsplit; item += gridDim.x) {
         const int ct = item / p.nsplit, split = item - ct * p.nsplit;
         const int g0 = split * gper, g1 = g0 + gper;
-        const int gp0 = ct * 64;
+        const int gp0 = ct * PTS;
         // ---------------- phase 1 (consumer warps): K* panel + mean ------------------------
         double mu0 = 0.0, mu1 = 0.0;
-        if (!producer) {
+        if (!producer && FAM == FAM_RBF) {
+            // thread (gjl, os): grid points gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel
+            // row), observations os, os + 4, ...
+            const int gj = gp0 + 2 * gjl;
+            const bool v0 = gj < p.M, v1 = gj + 1 < p.M;
+            double b0[RBF_MAXD], b1[RBF_MAXD];
+            rbf_load_point(p.Xs, v0 ? gj : 0, p.rp.D, b0);
+            rbf_load_point(p.Xs, v1 ? gj + 1 : 0, p.rp.D, b1);
+#pragma unroll 2
+            for (int o = os; o < p.npad; o += OS) {
+                double k0 = 0.0, k1 = 0.0;
+                if (o < p.N) {
+                    double a[RBF_MAXD];
+                    rbf_load_point(p.X, o, p.rp.D, a);
+                    if (v0) k0 = rbf_eval(p.rp, a, b0);
+                    if (v1) k1 = rbf_eval(p.rp, a, b1);
+                    const double al = p.alpha[o];
+                    mu0 = fma(k0, al, mu0);
+                    mu1 = fma(k1, al, mu1);
+                }
+                *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
+            }
+            fence_proxy_async();
+        }
+        if (!producer && FAM == FAM_HELM) {
             const int gj = gp0 + gjl;
             const bool gvalid = gj < p.M;
             const double gx = gvalid ? p.Xs[2 * (long)gj] : 0.0;
@@ -165,7 +196,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
                         sh_grp[g * WM * TILE + mycol + j * 8 + 1] = 0.0;
                     }
             }
-            const int nvalid = 2 * p.N;
+            const int nvalid = FAM == FAM_HELM ? 2 * p.N : p.N;
             for (int q = 0; q < nrb; ++q) {
                     {
                         const int li = sh_rb[q] & 0xffff, g = sh_rb[q] >> 16;
@@ -205,15 +236,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
         }
         __syncthreads();      // group sums visible; every bulk copy of this item has been consumed
         if (tid < TILE) {
+            // column tid of the tile: Helmholtz (point tid>>1, component tid&1), RBF point tid
             const int pj = tid >> 1, c = tid & 1;
-            const int j = gp0 + pj;
+            const int j = FAM == FAM_HELM ? gp0 + pj : gp0 + tid;
+            const long oidx = FAM == FAM_HELM ? (long)c * p.out_stride + j : (long)j;
             if (p.nsplit == 1) {
                 if (j < p.M) {
                     double ss = 0.0;
                     for (int g = 0; g < PRED_GROUPS; ++g) ss += sh_grp[g * WM * TILE + tid] + sh_grp[g * WM * TILE + TILE + tid];
                     double v = p.kss - ss;
                     v = v < 0.0 ? 0.0 : v;
-                    p.var[(long)c * p.out_stride + j] = v + p.var_add;
+                    p.var[oidx] = v + p.var_add;
                 }
             } else {
                 for (int g = g0; g < g1; ++g)
@@ -224,7 +257,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
                 double m = 0.0;
 #pragma unroll
                 for (int o = 0; o < OS; ++o) m += sh_mu[(o * 64 + pj) * 2 + c];
-                p.mean[(long)c * p.out_stride + j] = m;
+                p.mean[oidx] = m;
             }
         }
         // the next item's shared-memory partials are written only after its first __syncthreads
@@ -232,15 +265,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
 }
 
 // nsplit > 1: var = k** - sum_g partial[tile][g][col], same order as the in-kernel sum
+template <int FAM>
 __global__ void __launch_bounds__(TILE) predict_finish_kernel(PredictArgs p) {
     const int ct = blockIdx.x, tid = threadIdx.x;
-    const int j = ct * 64 + (tid >> 1), c = tid & 1;
+    const int c = tid & 1;
+    const int j = FAM == FAM_HELM ? ct * 64 + (tid >> 1) : ct * 128 + tid;
+    const long oidx = FAM == FAM_HELM ? (long)c * p.out_stride + j : (long)j;
     if (j >= p.M) return;
     double ss = 0.0;
     for (int g = 0; g < PRED_GROUPS; ++g) ss += p.partial[((size_t)ct * PRED_GROUPS + g) * TILE + tid];
     double v = p.kss - ss;
     v = v < 0.0 ? 0.0 : v;
-    p.var[(long)c * p.out_stride + j] = v + p.var_add;
+    p.var[oidx] = v + p.var_add;
 }
 
 size_t predict_panel_bytes(int npad) { return (size_t)npad * TILE * sizeof(double); }
@@ -274,40 +310,33 @@ int predict_choose_split(long ntiles) {
 
 size_t predict_partial_bytes(long ntiles) { return (size_t)ntiles * PRED_GROUPS * TILE * sizeof(double); }
 
-size_t predict_scratch_bytes(int npad, int M) {
-    const long ntiles = ((long)M + 63) / 64;
+size_t predict_scratch_bytes(int npad, int M, int pts_per_tile) {
+    const long ntiles = ((long)M + pts_per_tile - 1) / pts_per_tile;
     const int ns = predict_choose_split(ntiles);
     long ctas = predict_max_ctas();
     if (ntiles * ns < ctas) ctas = ntiles * ns;
     return (size_t)ctas * predict_panel_bytes(npad) + (ns > 1 ? predict_partial_bytes(ntiles) : 0);
 }
 
-cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
-                          const double* X, int N, const HelmParams& hp, const double* Xs, int M,
-                          long out_stride, double var_add, double* mean, double* var,
-                          double* scratch, size_t scratch_bytes, cudaStream_t st) {
-    if (M <= 0) return cudaSuccess;
+template <int FAM>
+static cudaError_t predict_launch(PredictArgs& a, double* scratch, size_t scratch_bytes, cudaStream_t st) {
     static bool init = false;
     if (!init) {
-        cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(predict_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         init = true;
     }
-    PredictArgs a;
-    a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
-    a.Xs = Xs; a.M = M; a.out_stride = out_stride;
-    a.kss = hp.w_df + hp.w_cf;           // ratio/l_df^2 + (1-ratio)/l_cf^2   (myKernel.py:55-57)
-    a.var_add = var_add; a.mean = mean; a.var = var;
-    a.ntiles = (M + 63) / 64;
+    constexpr int PTS = FAM == FAM_HELM ? 64 : 128;
+    a.ntiles = (a.M + PTS - 1) / PTS;
     // scratch = [partial sums (nsplit > 1)] [one K* panel per CTA]; a buffer too small for the
     // partials falls back to nsplit = 1, fewer panels only shrink the grid
     a.nsplit = predict_choose_split(a.ntiles);
     size_t pb = predict_partial_bytes(a.ntiles);
-    if (a.nsplit > 1 && scratch_bytes < pb + predict_panel_bytes(npad)) a.nsplit = 1;
+    if (a.nsplit > 1 && scratch_bytes < pb + predict_panel_bytes(a.npad)) a.nsplit = 1;
     if (a.nsplit == 1) pb = 0;
     a.partial = scratch;
     a.scratch = scratch + pb / sizeof(double);
-    long panels = (long)((scratch_bytes - pb) / predict_panel_bytes(npad));
+    long panels = (long)((scratch_bytes - pb) / predict_panel_bytes(a.npad));
     const long items = (long)a.ntiles * a.nsplit;
     long grid = items;
     if (grid > predict_max_ctas()) grid = predict_max_ctas();
@@ -316,9 +345,34 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
     // balance the tail: every CTA gets ceil(items/grid) or one fewer items
     long per = (items + grid - 1) / grid;
     grid = (items + per - 1) / per;
-    predict_kernel<<<(unsigned)grid, WS_THREADS, PRED_SMEM_BYTES, st>>>(a);
-    if (a.nsplit > 1) predict_finish_kernel<<<a.ntiles, TILE, 0, st>>>(a);
+    predict_kernel<FAM><<<(unsigned)grid, WS_THREADS, PRED_SMEM_BYTES, st>>>(a);
+    if (a.nsplit > 1) predict_finish_kernel<FAM><<<a.ntiles, TILE, 0, st>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
+                          const double* X, int N, const HelmParams& hp, const double* Xs, int M,
+                          long out_stride, double var_add, double* mean, double* var,
+                          double* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    PredictArgs a{};
+    a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
+    a.Xs = Xs; a.M = M; a.out_stride = out_stride;
+    a.kss = hp.w_df + hp.w_cf;           // ratio/l_df^2 + (1-ratio)/l_cf^2   (myKernel.py:55-57)
+    a.var_add = var_add; a.mean = mean; a.var = var;
+    return predict_launch<FAM_HELM>(a, scratch, scratch_bytes, st);
+}
+
+cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, const double* X, int N,
+                              const RbfParams& rp, const double* Xs, int M, double var_add, double* mean,
+                              double* var, double* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    PredictArgs a{};
+    a.Zt = Zt; a.npad = npad; a.alpha = alpha; a.X = X; a.N = N; a.rp = rp;
+    a.Xs = Xs; a.M = M; a.out_stride = M;
+    a.kss = rp.kss;
+    a.var_add = var_add; a.mean = mean; a.var = var;
+    return predict_launch<FAM_RBF>(a, scratch, scratch_bytes, st);
 }
 
 }  // namespace gp2d

@@ -12,7 +12,7 @@ import torch
 from ._lib import lib, check, Gp2dError
 
 __all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
-           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host"]
+           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host", "rbf_K", "rbf_grad_sums", "ScalarGP"]
 
 
 class LinAlgError(np.linalg.LinAlgError):
@@ -253,6 +253,160 @@ class HelmholtzGP:
             raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         self.lml = float(host[0])
         return self.lml, host[1:5].copy()
+
+
+# ------------------------------------------------------------------------------------------
+# scalar ARD-RBF sum family (krig.py:174-181,388,405-407)
+# ------------------------------------------------------------------------------------------
+def _rbf_params(variances, lengthscales, D):
+    """Host arrays var[Q], ls[Q*D] for the C ABI (kept alive by the caller during the call)."""
+    var = np.ascontiguousarray(np.atleast_1d(np.asarray(variances, dtype=np.float64)))
+    ls = np.asarray(lengthscales, dtype=np.float64)
+    Q = var.size
+    if ls.ndim == 0:
+        ls = np.full((Q, D), float(ls))
+    ls = np.atleast_2d(ls)
+    if ls.shape == (Q, 1) and D > 1:
+        ls = np.repeat(ls, D, axis=1)
+    if ls.shape != (Q, D):
+        raise ValueError("lengthscales must be [Q,D] = [%d,%d]" % (Q, D))
+    return var, np.ascontiguousarray(ls), Q
+
+
+def _coords(X, device=None) -> torch.Tensor:
+    t = as_dev(X, device)
+    if t.dim() != 2 or not (1 <= t.shape[1] <= 4):
+        raise ValueError("inputs must be [N,D] with 1 <= D <= 4")
+    return t
+
+
+def rbf_K(X, X2, variances, lengthscales, diag_add=0.0, out=None) -> torch.Tensor:
+    """[N,M] sum of ARD squared-exponential kernels (device tensor)."""
+    Xd = _coords(X)
+    X2d = None if X2 is None else _coords(X2, Xd.device)
+    N, D = Xd.shape
+    M = N if X2d is None else X2d.shape[0]
+    var, ls, Q = _rbf_params(variances, lengthscales, D)
+    if out is None:
+        out = torch.empty((N, M), dtype=torch.float64, device=Xd.device)
+    if N and M:
+        with torch.cuda.device(Xd.device):
+            check(lib.gp2d_rbf_kernel_build(_ptr(Xd), N, _ptr(X2d), M, D, Q, var.ctypes.data, ls.ctypes.data, diag_add,
+                                            _ptr(out), out.stride(0), _stream()), "gp2d_rbf_kernel_build")
+    return out
+
+
+def rbf_grad_sums(dL_dK, X, X2, variances, lengthscales) -> torch.Tensor:
+    """sum(dK/dtheta * dL_dK), theta ordered (variance_q, lengthscale_q[0..D-1]) per component."""
+    Xd = _coords(X)
+    X2d = None if X2 is None else _coords(X2, Xd.device)
+    N, D = Xd.shape
+    M = N if X2d is None else X2d.shape[0]
+    var, ls, Q = _rbf_params(variances, lengthscales, D)
+    W = as_dev(dL_dK, Xd.device)
+    if tuple(W.shape) != (N, M):
+        raise ValueError("dL_dK must be [N,M]")
+    nb = lib.gp2d_rbf_kernel_grad_workspace_bytes(N, M)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    out = torch.empty(Q * (1 + D), dtype=torch.float64, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        check(lib.gp2d_rbf_kernel_grad(_ptr(Xd), N, _ptr(X2d), M, D, Q, var.ctypes.data, ls.ctypes.data, _ptr(W),
+                                       W.stride(0), _ptr(ws), nb, _ptr(out), _stream()), "gp2d_rbf_kernel_grad")
+    return out
+
+
+class ScalarGP:
+    """Fit state of one scalar GP (sum of ARD-RBF kernels + white noise) on one GPU; same life
+    cycle as HelmholtzGP: fit() / predict() / lml_and_grad() through gp2d_rbf_*."""
+
+    def __init__(self, X, y, variances, lengthscales, noise, jitter=0.0, device=None):
+        self.X = _coords(X, device)
+        self.N, self.D = int(self.X.shape[0]), int(self.X.shape[1])
+        self.y = as_dev(y, self.X.device).reshape(-1)
+        if self.y.numel() != self.N:
+            raise ValueError("y must hold one observation per row of X")
+        self.set_params(variances, lengthscales, noise)
+        self.jitter = float(jitter)
+        self.ws_bytes = lib.gp2d_rbf_fit_workspace_bytes(self.N, self.D)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.X.device)
+        self._scal = torch.zeros(32, dtype=torch.float64, device=self.X.device)
+        self._info = torch.zeros(1, dtype=torch.int32, device=self.X.device)
+        self._pws = None
+        self.lml = None
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def set_params(self, variances, lengthscales, noise):
+        self.var, self.ls, self.Q = _rbf_params(variances, lengthscales, self.D)
+        self.noise = float(noise)
+        self.fitted = False
+
+    def fit_async(self, alpha_out=None):
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_rbf_fit(_ptr(self.X), self.N, self.D, _ptr(self.y), self.Q, self.var.ctypes.data,
+                                   self.ls.ctypes.data, self.noise, self.jitter, _ptr(self.ws), self.ws_bytes,
+                                   _ptr(alpha_out), _ptr(self._scal), _ptr(self._info), _stream()), "gp2d_rbf_fit")
+        self.fitted = True
+
+    def fit(self):
+        self.fit_async()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(self._scal[0].item())
+        return self.lml
+
+    def alpha(self) -> torch.Tensor:
+        out = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        self.fit_async(alpha_out=out)
+        return out
+
+    def predict_state(self) -> torch.Tensor:
+        import ctypes as C
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(lib.gp2d_rbf_fit_predict_state(self.N, self.D, C.byref(off), C.byref(nb)), "gp2d_rbf_fit_predict_state")
+        return self.ws[off.value:off.value + nb.value]
+
+    def predict(self, Xs, include_noise=False, out_mean=None, out_var=None):
+        """mean[M], var[M] as device tensors; include_noise adds the white-noise variance (what
+        sklearn's predict(return_std=True) with a WhiteKernel and GPy's predict both return)."""
+        if not self.fitted:
+            self.fit()
+        Xsd = _coords(Xs, self.device)
+        if Xsd.shape[1] != self.D:
+            raise ValueError("prediction points must have %d columns" % self.D)
+        M = int(Xsd.shape[0])
+        mean = out_mean if out_mean is not None else torch.empty(M, dtype=torch.float64, device=self.device)
+        var = out_var if out_var is not None else torch.empty(M, dtype=torch.float64, device=self.device)
+        if M:
+            with torch.cuda.device(self.device):
+                nb = lib.gp2d_rbf_predict_workspace_bytes(self.N, M)
+                if self._pws is None or self._pws.numel() < nb:
+                    self._pws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+                check(lib.gp2d_rbf_predict(_ptr(self.ws), self.N, self.D, self.Q, self.var.ctypes.data,
+                                           self.ls.ctypes.data, _ptr(Xsd), M, self.noise if include_noise else 0.0,
+                                           _ptr(mean), _ptr(var), _ptr(self._pws), self._pws.numel(), _stream()),
+                      "gp2d_rbf_predict")
+        return mean, var
+
+    def lml_and_grad(self):
+        """(LML, grad) with grad over (variance_q, lengthscale_q[..])_q then the noise variance."""
+        ng = self.Q * (1 + self.D) + 1
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_rbf_lml_grad(_ptr(self.X), self.N, self.D, _ptr(self.y), self.Q, self.var.ctypes.data,
+                                        self.ls.ctypes.data, self.noise, self.jitter, _ptr(self.ws), self.ws_bytes,
+                                        _ptr(self._scal), _ptr(self._info), _stream()), "gp2d_rbf_lml_grad")
+        self.fitted = True
+        host = self._scal[:1 + ng].cpu().numpy()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(host[0])
+        return self.lml, host[1:1 + ng].copy()
 
 
 def fit_predict_host(X, y, l_df, l_cf, ratio, noise, Xs, jitter=0.0, include_noise=False):

@@ -11,8 +11,9 @@ numerical core (covariance, Cholesky, likelihood, prediction) is ``models.GPRegr
 libgp2d.  Deviations, all forced by what the reference tree lacks:
   * kernelType 2 / 3 / 4 map to nonDivK / nonRotK / myKernel over the horizontal position
     (y, x): the reference's 3-D ``myKernel2`` is not in its repository;
-  * kernelType 1 (scalar ARD RBF over t,y,x) and ``scikit_prior`` (sklearn scalar RBF) are the
-    next rows of the scope table and raise NotImplementedError;
+  * kernelType 1 (scalar ARD RBF over t,y,x; krig.py:388) builds one scalar model per velocity
+    component (``_v.pkl`` / ``_u.pkl``) on the GPU RBF family; ``scikit_prior`` rebuilds the
+    optimised kernel through the scikit-learn look-alike (sklearn_like.py) as krig.py:174-194;
   * a vector kernel gives both velocity components from ONE model, stored as
     ``<output>_combined.pkl`` (``_divFree`` / ``_curlFree``), the names krig.py:398-403 uses.
 """
@@ -27,7 +28,9 @@ import scipy.io as sio
 
 from . import dist as gdist
 from . import models
+from .kern import RBF
 from .myKernel import myKernel, nonDivK, nonRotK
+from .sklearn_like import GaussianProcessRegressor, kernels
 from .printNCFiles import createNC, openNC, writeNC
 from .projection import NAD83
 
@@ -102,20 +105,20 @@ def split_observations(tob, yob, xob, latt, lont, vob, uob, sample_step=5, skip=
 
 
 def make_kernel(kernelType):
+    if kernelType == 1:
+        return RBF(input_dim=3, ARD=True)                      # krig.py:388
     if kernelType == 2:
         return nonDivK(2, [1, 2], 1.)
     if kernelType == 3:
         return nonRotK(2, [1, 2], 1.)
     if kernelType == 4:
         return myKernel(2, [1, 2], 1., 1., 0.5)
-    raise NotImplementedError(
-        "kernelType=1 (scalar ARD RBF over t,y,x; krig.py:388) is outside the Helmholtz hot path "
-        "built so far; use kernelType 2 (divergence-free), 3 (curl-free) or 4 (both)")
+    raise ValueError("kernelType must be 1 (scalar ARD RBF), 2 (divergence-free), 3 (curl-free) or 4 (both)")
 
 
 # ---- workflows ---------------------------------------------------------------------------
 def kriging(st, et, lalim=[0, 0], lolim=[0, 0], sample_step=5, skip=5, nKernels=1, output='rbfModel',
-            pkg='GPy', kernelType=4, laser=1, data=None):
+            pkg='GPy', kernelType=1, laser=1, data=None):
     """Build the (un-optimised) GP model for drifter data between time steps st and et and
     pickle it, like krig.kriging (krig.py:259-418).  ``data`` may carry the tuple getData
     returns (time, lat, lon, v, u, valid) to bypass file I/O."""
@@ -137,12 +140,26 @@ def kriging(st, et, lalim=[0, 0], lolim=[0, 0], sample_step=5, skip=5, nKernels=
     Xt = np.concatenate([t["t"], t["y"], t["x"]], axis=1)
     obs = np.concatenate([o["v"], o["u"]], axis=0)
     obst = np.concatenate([t["v"], t["u"]], axis=0)
-    if nKernels != 1:
-        print('nKernels > 1: a sum of identical Helmholtz kernels is one kernel with rescaled '
-              'weights; a single kernel is used')
-    k = make_kernel(kernelType)
-    model = models.GPRegression(X, obs, k)
-    model.pickle(output + _SUFFIX[kernelType])
+    k2 = make_kernel(kernelType)
+    if kernelType == 1:
+        # scalar kernels: k = k2 + k2 + ... (krig.py:405-407), one model per component, and the
+        # .mat keeps the two-column [v, u] layout of krig.py:378-382
+        k = k2.copy()
+        for _ in range(nKernels - 1):
+            k = k + k2
+        model = []
+        for comp, suffix in ((o["v"], '_v.pkl'), (o["u"], '_u.pkl')):
+            mdl = models.GPRegression(X, comp, k.copy())
+            mdl.pickle(output + suffix)
+            model.append(mdl)
+        obs = np.concatenate([o["v"], o["u"]], axis=1)
+        obst = np.concatenate([t["v"], t["u"]], axis=1)
+    else:
+        if nKernels != 1:
+            print('nKernels > 1: a sum of identical Helmholtz kernels is one kernel with rescaled '
+                  'weights; a single kernel is used')
+        model = models.GPRegression(X, obs, k2)
+        model.pickle(output + _SUFFIX[kernelType])
     sio.savemat(output + '.mat', {'Xo': X, 'obs': obs, 'Xt': Xt,
                                   'LL_o': np.concatenate([o["t"], o["lat"], o["lon"]], axis=1),
                                   'LL_t': np.concatenate([t["t"], t["lat"], t["lon"]], axis=1),
@@ -161,7 +178,8 @@ def _model_file(fname):
 
 def runRestarts(fname, nres=10, nKernels=2, seed=None, max_iters=1000):
     """Hyper-parameter fit with ``nres`` restarts (krig.py:430-468).  Under torch.distributed
-    the restarts are sharded round-robin over the ranks and the best run is gathered."""
+    the restarts are sharded round-robin over the ranks and the best run is gathered.  For the
+    scalar models of kernelType=1 pass the per-component name (``<output>_v`` / ``<output>_u``)."""
     startTime = datetime.now()
     path = _model_file(fname)
     model = models.load(path)
@@ -203,6 +221,8 @@ def predict(filename, tlim=[0, 0], ylim=[0, 0], xlim=[0, 0], dt=0.5, dx=0.5, xL=
     """Gridded posterior mean and variance, one time slice at a time (krig.py:471-574).  Under
     torch.distributed each slice's grid points are sharded over the ranks."""
     startTime = datetime.now()
+    if os.path.isfile(filename + '_v.pkl') and os.path.isfile(filename + '_u.pkl'):
+        return _predict_scalar(filename, tlim, ylim, xlim, dt, dx, xL, yL, write, startTime)
     model = models.load(_model_file(filename))
     hyp = model.param_array
     if (ylim[0] == ylim[1]) and (xlim[0] == xlim[1]):
@@ -232,14 +252,65 @@ def predict(filename, tlim=[0, 0], ylim=[0, 0], xlim=[0, 0], dt=0.5, dx=0.5, xL=
     return Xp, V, U, VVar, UVar
 
 
+def _predict_scalar(filename, tlim, ylim, xlim, dt, dx, xL, yL, write, startTime):
+    """krig.predict for the scalar models: model_v and model_u predicted slice by slice
+    (krig.py:478-483,541-557)."""
+    model_v = models.load(filename + '_v.pkl')
+    model_u = models.load(filename + '_u.pkl')
+    if (ylim[0] == ylim[1]) and (xlim[0] == xlim[1]):
+        Xo = sio.loadmat(filename + '.mat')['Xo']
+        Xp, tp, yp, xp = getGrid(Xo[:, 0], Xo[:, 1], Xo[:, 2])
+    else:
+        Xp, tp, yp, xp = getGrid(tlim, ylim, xlim, dt, dx, xL, yL)
+    inc = yp.size * xp.size
+    shape = [tp.size, yp.size, xp.size]
+    out = {}
+    for name, mdl in (('v', model_v), ('u', model_u)):
+        mean, var = [], []
+        for i in range(tp.size):
+            mu, vv = mdl.predict(Xp[i * inc:(i + 1) * inc])
+            mean.append(mu[:, 0]); var.append(vv[:, 0])
+        out[name] = np.reshape(np.concatenate(mean), shape)
+        out[name + 'var'] = np.reshape(np.concatenate(var), shape)
+    if write and gdist.world()[0] == 0:
+        createNC(filename + '.nc', tp, yp, xp, model_v.param_array)
+        fi = openNC(filename + '.nc', 'a')
+        for name in ('v', 'u', 'vvar', 'uvar'):
+            writeNC(fi, name, out[name])
+        writeNC(fi, 'hyperparam_v', model_v.param_array)
+        writeNC(fi, 'hyperparam_u', model_u.param_array)
+        fi.close()
+        print('End of script, time : ' + str(datetime.now() - startTime))
+    return Xp, out['v'], out['u'], out['vvar'], out['uvar']
+
+
+def _predict_points(filename, Xt):
+    """Mean / variance of (v, u) at arbitrary (t, y, x) rows from whichever models ``filename``
+    names: one vector-valued model or the scalar pair ``_v.pkl`` / ``_u.pkl``."""
+    Nt = Xt.shape[0]
+    if os.path.isfile(filename + '_v.pkl') and os.path.isfile(filename + '_u.pkl'):
+        mv, vv = models.load(filename + '_v.pkl').predict(Xt)
+        mu, vu = models.load(filename + '_u.pkl').predict(Xt)
+        return mv, vv, mu, vu
+    mean, var = models.load(_model_file(filename)).predict(Xt)
+    return mean[:Nt], var[:Nt], mean[Nt:], var[Nt:]
+
+
+def _test_columns(obst, Nt):
+    """Test observations as (v, u) columns: stacked [v; u] for the vector models, two columns for
+    the scalar ones (krig.py:378-394)."""
+    obst = np.asarray(obst)
+    if obst.shape[1] == 2:
+        return obst[:, 0:1], obst[:, 1:2]
+    return obst[:Nt], obst[Nt:]
+
+
 def predictTest(filename):
     """Predict at the held-out test points and save them (krig.py:578-616)."""
-    model = models.load(_model_file(filename))
     f = sio.loadmat(filename + '.mat')
     Xt, obst = f['Xt'], f['test_points']
-    mean, var = model.predict(Xt)
-    Nt = Xt.shape[0]
-    out = {'Xt': Xt, 'Vp': mean[:Nt], 'VpVar': var[:Nt], 'Up': mean[Nt:], 'UpVar': var[Nt:], 'test_points': obst}
+    Vp, VpVar, Up, UpVar = _predict_points(filename, Xt)
+    out = {'Xt': Xt, 'Vp': Vp, 'VpVar': VpVar, 'Up': Up, 'UpVar': UpVar, 'test_points': obst}
     sio.savemat(filename + '_test.mat', out)
     return out
 
@@ -252,18 +323,82 @@ def rmse(ys, y):
 
 def getRMSE(filename):
     """RMSE of the v and u predictions at the test points (krig.py:620-635)."""
-    model = models.load(_model_file(filename))
     f = sio.loadmat(filename + '.mat')
     Xt, obst = f['Xt'], f['test_points']
-    mean, _ = model.predict(Xt)
-    Nt = Xt.shape[0]
-    rmse_v, rmse_u = rmse(mean[:Nt], obst[:Nt]), rmse(mean[Nt:], obst[Nt:])
+    Vp, _, Up, _ = _predict_points(filename, Xt)
+    vt, ut = _test_columns(obst, Xt.shape[0])
+    rmse_v, rmse_u = rmse(Vp, vt), rmse(Up, ut)
     print(rmse_v)
     print(rmse_u)
     return rmse_v, rmse_u
 
 
-def scikit_prior(*args, **kwargs):
-    raise NotImplementedError(
-        "scikit_prior rebuilds a scalar RBF + WhiteKernel model in scikit-learn (krig.py:88-207); the "
-        "scalar-RBF kernel family is the next row of the scope table (SURVEY.md §8f rank 2)")
+def scikit_prior(filename0, varname='v', dt=0, tlim=6, radar='', xlim=[0, 0], ylim=[0, 0], dx=0, ind=0, xrange=3):
+    """Prediction with the optimised hyper-parameters through the scikit-learn formulation
+    (krig.py:88-207): window the observations around the target time / region, rebuild
+    ``HP[0]*RBF([..]) (+ HP[4]*RBF([..])) + WhiteKernel(noise)`` from the pickled model's
+    ``param_array``, fit with fixed hyper-parameters, predict mean and standard deviation on the
+    grid and append them to a NetCDF file.  Returns (outFile, U, Uvar)."""
+    startTime = datetime.now()
+    if "res" in filename0:                                  # <dir>res<k>/<name>: data live in <dir>
+        dir0, a = filename0.split("res")
+        _, fname0 = a.split("/")
+        fname0 = dir0 + fname0
+    else:
+        fname0 = filename0
+    fm = sio.loadmat(fname0 + '.mat')
+    print('Longitude limits:', xlim)
+    print('Latitude limits :', ylim)
+    if radar != '':
+        raise NotImplementedError("the radar-grid branch needs the radar NetCDF files (absent upstream)")
+    if (xlim[1] > xlim[0]) and (ylim[1] > ylim[0]):
+        X, tcenter, yg, xg = getGrid([dt, dt + 1], ylim, xlim, 1, dx)
+        filename = filename0 + '_cyc'
+    else:                                                    # pre-existing grid (NetCDF written by predict)
+        from scipy.io import netcdf_file
+        f = netcdf_file(filename0 + '.nc', 'r', mmap=False)
+        xg, yg, tg = np.array(f.variables['x'][:]), np.array(f.variables['y'][:]), np.array(f.variables['time'][:])
+        f.close()
+        it = dt
+        tcenter = np.array([tg[it]])
+        Yg, Tg, Xg = np.meshgrid(yg, tg, xg)
+        X = np.concatenate([np.reshape(Tg, [Tg.size, 1]), np.reshape(Yg, [Yg.size, 1]), np.reshape(Xg, [Xg.size, 1])], axis=1)
+        filename = filename0
+        inc = yg.size * xg.size
+        X = X[inc * it:inc * it + inc, :]
+    filename = filename + '_' + str(np.round(tcenter[0], decimals=2)) + 'h_scikit_'
+    outFile = filename + str(ind) + '.nc'
+    # observations inside the time / longitude window (krig.py:146-157)
+    to, tt = fm['Xo'][:, 0], fm['Xt'][:, 0]
+    xo, xt = fm['Xo'][:, 2], fm['Xt'][:, 2]
+    ito = np.where((to >= tcenter - tlim) & (to <= tcenter + tlim) & (xo >= xlim[0] - xrange) & (xo <= xlim[1] + xrange))[0]
+    itt = np.where((tt >= tcenter - tlim) & (tt <= tcenter + tlim) & (xt >= xlim[0] - xrange) & (xt <= xlim[1] + xrange))[0]
+    XT = np.concatenate([fm['Xo'][ito, :], fm['Xt'][itt, :]], axis=0)
+    print('Number of observation points: ', np.size(XT, 0))
+    obs, obst = fm['obs'][ito, :], fm['test_points'][itt, :]
+    model = models.load(fname0 + '_' + varname + '.pkl')
+    HP = model.param_array
+    col = 1 if varname == 'u' else 0
+    u = np.concatenate([obs[:, col], obst[:, col]])[:, None]
+    N = HP.size - 1
+    noise = HP[-1]
+    print('noise = ' + str(HP[-1]))
+    k = HP[0] * kernels.RBF(length_scale=[HP[1], HP[2], HP[3]])
+    if N > 5:
+        k = k + HP[4] * kernels.RBF(length_scale=[HP[5], HP[6], HP[7]])
+    k = k + kernels.WhiteKernel(noise_level=noise)
+    print(k)
+    model_u = GaussianProcessRegressor(kernel=k, optimizer=None)
+    model_u.fit(XT, u)
+    U, Ustd = model_u.predict(X, return_std=True)
+    U = np.reshape(U, [tcenter.size, yg.size, xg.size])
+    Ustd = np.reshape(Ustd, [tcenter.size, yg.size, xg.size])
+    if not os.path.isfile(outFile):
+        createNC(outFile, tcenter, yg, xg, HP)
+    fi = openNC(outFile, 'a')
+    writeNC(fi, varname, U)
+    writeNC(fi, varname + 'var', Ustd ** 2)
+    writeNC(fi, 'hyperparam_' + varname, HP)
+    fi.close()
+    print('End of script, time : ' + str(datetime.now() - startTime))
+    return outFile, U, Ustd ** 2

@@ -18,7 +18,8 @@ import pickle
 import numpy as np
 import scipy.optimize as sopt
 
-from .engine import HelmholtzGP, LinAlgError
+from .engine import HelmholtzGP, LinAlgError, ScalarGP
+from .kern import RBF, Add, _ScalarKern
 from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase
 from .params import Param
 
@@ -38,22 +39,31 @@ class GPRegression:
         Y = np.asarray(Y, dtype=np.float64)
         if kernel is None:
             kernel = myKernel(2, [0, 1], 1.0, 1.0, 0.5)
-        if not isinstance(kernel, _HelmholtzBase):
-            raise TypeError("kernel must be myKernel / nonDivK / nonRotK")
+        if not isinstance(kernel, (_HelmholtzBase, _ScalarKern)):
+            raise TypeError("kernel must be myKernel / nonDivK / nonRotK or an RBF (sum)")
         self.kern = kernel
-        if reference_compat is not None:
-            self.kern.reference_compat = bool(reference_compat)
-        self.X = X[:, self.kern.active_dims] if X.shape[1] != 2 else X
+        self.scalar = isinstance(kernel, _ScalarKern)
         self.Y = Y.reshape(-1, 1)
-        if self.Y.shape[0] != 2 * self.X.shape[0]:
-            raise ValueError("Y must stack both velocity components: shape [2N,1] (GP_plots.py:722)")
         self.Gaussian_noise = Param("Gaussian_noise.variance", noise_var).constrain_positive()
         self.likelihood = self
         self.variance = self.Gaussian_noise
         self.jitter = float(jitter)
         self.optimization_runs = []
-        self._gp = HelmholtzGP(self.X, self.Y.reshape(-1), *self.kern._theta(), float(self.Gaussian_noise),
-                               jitter=self.jitter, device=device)
+        if self.scalar:
+            # scalar GP over (t, y, x): one model per velocity component (krig.py:409-412)
+            self.X = self.kern._slice(X)
+            if self.Y.shape[0] != self.X.shape[0]:
+                raise ValueError("Y must hold one observation per row of X: shape [N,1]")
+            self._gp = ScalarGP(self.X, self.Y.reshape(-1), *self.kern.rbf_params(), float(self.Gaussian_noise),
+                                jitter=self.jitter, device=device)
+        else:
+            if reference_compat is not None:
+                self.kern.reference_compat = bool(reference_compat)
+            self.X = X[:, self.kern.active_dims] if X.shape[1] != 2 else X
+            if self.Y.shape[0] != 2 * self.X.shape[0]:
+                raise ValueError("Y must stack both velocity components: shape [2N,1] (GP_plots.py:722)")
+            self._gp = HelmholtzGP(self.X, self.Y.reshape(-1), *self.kern._theta(), float(self.Gaussian_noise),
+                                   jitter=self.jitter, device=device)
         self._ll = None
         self.parameters_changed()          # GPy evaluates the likelihood in the constructor
 
@@ -67,13 +77,18 @@ class GPRegression:
         return np.array([float(p) for p in self.parameters])
 
     def parameter_names(self):
+        if self.scalar:
+            return self.kern.parameter_names() + ["Gaussian_noise.variance"]
         return ["%s.%s" % (self.kern.name, p.name) for p in self.kern.parameters] + ["Gaussian_noise.variance"]
 
     def _free_params(self):
         return [p for p in self.parameters if p.constraint != "fixed"]
 
     def _sync(self):
-        self._gp.set_params(*self.kern._theta(), float(self.Gaussian_noise))
+        if self.scalar:
+            self._gp.set_params(*self.kern.rbf_params(), float(self.Gaussian_noise))
+        else:
+            self._gp.set_params(*self.kern._theta(), float(self.Gaussian_noise))
 
     # ---- likelihood ------------------------------------------------------------------------
     def _grad_natural(self, grad4):
@@ -89,6 +104,16 @@ class GPRegression:
 
     def parameters_changed(self):
         self._sync()
+        if self.scalar:
+            try:
+                self._ll, g = self._gp.lml_and_grad()
+                self.kern._scatter_gradient(g[:-1])
+                self.Gaussian_noise.gradient = float(g[-1])
+            except LinAlgError:
+                self._ll = -np.inf
+                for p in self.parameters:
+                    p.gradient = 0.0
+            return self._ll
         try:
             self._ll, g = self._gp.lml_and_grad(reference_compat=self.kern.reference_compat)
         except LinAlgError:
@@ -167,7 +192,9 @@ class GPRegression:
         if full_cov:
             raise NotImplementedError("only marginal variances (the reference never asks for full_cov)")
         Xnew = np.asarray(Xnew, dtype=np.float64)
-        if Xnew.shape[1] != 2:
+        if self.scalar:
+            Xnew = self.kern._slice(Xnew)
+        elif Xnew.shape[1] != 2:
             Xnew = Xnew[:, self.kern.active_dims]
         if not self._gp.fitted:
             self._sync()
@@ -178,10 +205,16 @@ class GPRegression:
     # ---- persistence (krig.py:412,438,452) -----------------------------------------------------
     def _state(self):
         k = self.kern
-        return {"kernel": type(k).__name__, "active_dims": k.active_dims, "params": self.param_array,
-                "constraints": [p.constraint for p in self.parameters], "reference_compat": k.reference_compat,
-                "X": self.X, "Y": self.Y, "jitter": self.jitter,
-                "runs": [r.__dict__ for r in self.optimization_runs]}
+        st = {"kernel": type(k).__name__, "active_dims": k.active_dims, "params": self.param_array,
+              "constraints": [p.constraint for p in self.parameters],
+              "X": self.X, "Y": self.Y, "jitter": self.jitter,
+              "runs": [r.__dict__ for r in self.optimization_runs]}
+        if self.scalar:
+            st["parts"] = [{"input_dim": p.input_dim, "ARD": p.ARD, "name": p.name} for p in k.parts_list()]
+            st["active_dims"] = list(range(self.X.shape[1]))      # X is stored already sliced
+        else:
+            st["reference_compat"] = k.reference_compat
+        return st
 
     def pickle(self, path):
         with open(path, "wb") as f:
@@ -198,6 +231,22 @@ def load(path, device=None):
         st = pickle.load(f)
     p = st["params"]
     name = st["kernel"]
+    if "parts" in st:
+        parts, o = [], 0
+        for d in st["parts"]:
+            nl = d["input_dim"] if d["ARD"] else 1
+            parts.append(RBF(d["input_dim"], p[o], p[o + 1:o + 1 + nl], ARD=d["ARD"], active_dims=st["active_dims"],
+                             name=d["name"]))
+            o += 1 + nl
+        k = parts[0] if len(parts) == 1 else Add(parts)
+        m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
+        for prm, c in zip(m.parameters, st["constraints"]):
+            prm.constraint = c
+        for d in st["runs"]:
+            r = _Run(None, None, None, None)
+            r.__dict__.update(d)
+            m.optimization_runs.append(r)
+        return m
     if name == "myKernel":
         k = myKernel(2, st["active_dims"], p[0], p[1], p[2])
     elif name == "nonDivK":

@@ -79,19 +79,21 @@ class Param:
     def from_free(self, x):
         c = self.constraint
         if c == "positive":
-            self.value = x if x > _LIM else math.log1p(math.exp(x)) if x > -_LIM else math.exp(x)
+            # GPy's Logexp clips its argument the same way: the value never underflows to 0
+            x = max(x, -_LIM)
+            self.value = x if x > _LIM else math.log1p(math.exp(x))
         elif isinstance(c, tuple):
             lo, hi = c[1], c[2]
-            self.value = lo + (hi - lo) / (1.0 + math.exp(-x))
+            self.value = lo + (hi - lo) / (1.0 + math.exp(-min(max(x, -_LIM), _LIM)))
         elif c != "fixed":
             self.value = float(x)
 
     def dvalue_dfree(self, x):
         c = self.constraint
         if c == "positive":
-            return 1.0 if x > _LIM else 1.0 / (1.0 + math.exp(-x))
+            return 1.0 if x > _LIM else 1.0 / (1.0 + math.exp(-max(x, -_LIM)))
         if isinstance(c, tuple):
             lo, hi = c[1], c[2]
-            s = 1.0 / (1.0 + math.exp(-x))
+            s = 1.0 / (1.0 + math.exp(-min(max(x, -_LIM), _LIM)))
             return (hi - lo) * s * (1.0 - s)
         return 1.0

@@ -3,8 +3,9 @@
     python -m gp2d_b200.runKrig <1-based job index>
 
 The index selects (T, dt, skip, nK) from the same hard-coded tables; the model is built by
-krig.kriging.  The Helmholtz (divergence-free + curl-free) kernel is requested explicitly
-because the reference default (scalar RBF) is not part of the GPU path yet.
+krig.kriging with the reference's default kernelType=1 (sum of nK scalar ARD-RBF kernels, one model
+per velocity component).  GP2D_KERNEL_TYPE=2|3|4 selects the divergence-free / curl-free /
+combined Helmholtz kernel instead; GP2D_LASER=1 reads the LASER pickle instead of the simulations.
 """
 import os
 import sys
@@ -29,7 +30,7 @@ def main(argv=None):
     outFile = outDir + '/' + outFile
     print(outFile)
     return krig.kriging(st, et, sample_step=-int(dt[ind]), skip=int(skp[ind]), nKernels=int(nK[ind]),
-                        output=outFile, laser=laser, kernelType=4)
+                        output=outFile, laser=laser, kernelType=int(os.environ.get("GP2D_KERNEL_TYPE", "1")))
 
 
 if __name__ == "__main__":

@@ -2,11 +2,12 @@
 
     python -m gp2d_b200.runPredict <1-based job index>
 
-The reference maps the index to a prediction time (idt0 = 8, 12, 16, 20 in units of
-tg = arange(12, 36, 0.5)) and a velocity component, then calls krig.scikit_prior (scalar
-RBF in scikit-learn).  The vector-valued kernel predicts both components at once, so the
-component half of the index range repeats the same work; the grid limits are the reference's.
-"""
+The index selects a prediction time (idt0 = 8, 12, 16, 20 in units of tg = arange(12, 36, 0.5))
+and a velocity component (first half of the index range 'v', second half 'u'), then calls
+krig.scikit_prior with the reference's grid limits -- the scalar ARD-RBF model rebuilt with the
+optimised hyper-parameters and predicted on the GPU.  GP2D_PREDICT_DIR overrides the directory
+of the model files (the reference hard-codes 'outputs_proposal/skip2_day1/')."""
+import os
 import sys
 
 import numpy as np
@@ -21,11 +22,15 @@ def main(argv=None):
     tg = np.arange(12, 36, 0.5)
     if ind >= idt0.size:
         ind = ind - idt0.size
+        var = 'u'
+    else:
+        var = 'v'
     print('Part ', ind + 1, ' of ', idt0.size, '.')
     idt = idt0[ind]
     ylim, xlim, dx = [1, 15], [-5, 15], 0.1
-    outFile = 'outputs_proposal/skip2_day1/' + 'rbfModel_T' + str(T) + '_dt' + str(dt) + '_nK' + str(nK)
-    return krig.predict(outFile, tlim=[tg[idt], tg[idt] + 1], ylim=ylim, xlim=xlim, dt=1, dx=dx)
+    outDir = os.environ.get("GP2D_PREDICT_DIR", 'outputs_proposal/skip2_day1/')
+    outFile = outDir + '/' + 'rbfModel_T' + str(T) + '_dt' + str(dt) + '_nK' + str(nK)
+    return krig.scikit_prior(outFile, varname=var, dt=tg[idt], tlim=8, radar='', xlim=xlim, ylim=ylim, dx=dx)
 
 
 if __name__ == "__main__":

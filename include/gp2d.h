@@ -125,6 +125,41 @@ int gp2d_lml_grad(const double* X, int N, const double* y,
                   int reference_compat, void* ws, size_t ws_bytes, double* out5, int* info,
                   void* stream);
 
+/* ---- scalar ARD-RBF sum family --------------------------------------------------------------
+ * k(x,x') = sum_{q<Q} var[q] exp(-1/2 sum_{d<D} ((x_d - x'_d) / ls[q*D+d])^2), D <= 4, Q <= 4,
+ * scalar observations y[N].  var[Q] and ls[Q*D] are HOST arrays (read before the call returns);
+ * all other pointers are device pointers as above.  This is GPy.kern.RBF(input_dim=3, ARD=True)
+ * summed nKernels times (krig.py:388,405-407) and scikit-learn's HP[0]*RBF([..]) + HP[4]*RBF([..])
+ * (krig.py:174-178); the white-noise term (WhiteKernel krig.py:179 / GPy Gaussian_noise) is the
+ * `noise` argument of the fit and `var_add` of the prediction.  Matrices are plain [N,M]
+ * row-major. */
+int gp2d_rbf_kernel_build(const double* X, int N, const double* X2, int M, int D, int Q, const double* var,
+                          const double* ls, double diag_add, double* K, int64_t ldk, void* stream);
+
+/* out[Q*(1+D)] = sum(dK/dtheta * dL_dK), theta ordered (var_q, ls[q*D .. q*D+D-1]) per component:
+ * GPy's RBF.update_gradients_full with ARD. */
+size_t gp2d_rbf_kernel_grad_workspace_bytes(int N, int M);
+int gp2d_rbf_kernel_grad(const double* X, int N, const double* X2, int M, int D, int Q, const double* var,
+                         const double* ls, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                         double* out, void* stream);
+
+/* Fit / predict / likelihood, same contracts as gp2d_fit, gp2d_predict, gp2d_lml_grad.
+ * Replaces GPRegression(X, vo, RBF+RBF...) (krig.py:409-412), GaussianProcessRegressor(kernel=k,
+ * optimizer=None).fit(XT,u) (krig.py:182-185) and .predict(X, return_std=True) (krig.py:194; pass
+ * var_add = noise: WhiteKernel is part of sklearn's predictive variance, and of GPy's).
+ * gp2d_rbf_lml_grad: out[2 + Q*(1+D)] = (LML, d/dtheta as in gp2d_rbf_kernel_grad, d/dnoise). */
+size_t gp2d_rbf_fit_workspace_bytes(int N, int D);
+int gp2d_rbf_fit_predict_state(int N, int D, size_t* offset, size_t* bytes);
+int gp2d_rbf_fit(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
+                 double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out, double* lml_out,
+                 int* info, void* stream);
+size_t gp2d_rbf_predict_workspace_bytes(int N, int M);
+int gp2d_rbf_predict(const void* fit_ws, int N, int D, int Q, const double* var, const double* ls,
+                     const double* Xs, int M, double var_add, double* mean, double* variance, void* ws,
+                     size_t ws_bytes, void* stream);
+int gp2d_rbf_lml_grad(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
+                      double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream);
+
 /* ---- host-buffer convenience (allocates, copies, synchronises) -------------------- */
 
 /* Whole fit + predict with HOST pointers on the current device; returns info (> 0) or an

@@ -23,6 +23,7 @@ __all__ = [
     "helmholtz_K", "helmholtz_Kdiag", "helmholtz_dK", "kernel_grad_sums",
     "fit", "predict", "lml", "lml_and_grad", "fit_predict_inverse_form",
     "haversine_km", "simlaser_inputs", "rbf_ard_K", "LOG_2PI",
+    "rbf_sum_K", "rbf_sum_dK", "rbf_kernel_grad_sums", "rbf_fit", "rbf_predict", "rbf_lml_and_grad",
 ]
 
 LOG_2PI = math.log(2.0 * math.pi)
@@ -227,6 +228,79 @@ def fit_predict_inverse_form(X, y, l_df, l_cf, ratio, noise, Xs, ks_cf_weight=No
     kss = helmholtz_Kdiag(1, l_df, l_cf, ratio)[0]
     var = kss - np.einsum("ij,ij->i", Ks @ Ki, Ks)
     return mean, var
+
+
+# --------------------------------------------------------------------------------------
+# scalar ARD-RBF sum family: the reference's production kernels.  GPy.kern.RBF(input_dim=3,
+# ARD=True) summed nKernels times (krig.py:388,405-407); sklearn HP[0]*RBF([..]) + HP[4]*RBF([..])
+# + WhiteKernel(noise) (krig.py:174-181).  Pinned against live scikit-learn in
+# tests/golden/make_golden_sklearn.py / tests/test_oracle_golden.py.
+# --------------------------------------------------------------------------------------
+def rbf_sum_K(X, X2, variances, lengthscales):
+    """sum_q variances[q] * exp(-1/2 sum_d ((x_d - x'_d)/lengthscales[q][d])^2)."""
+    ls = np.atleast_2d(np.asarray(lengthscales, dtype=np.float64))
+    K = 0.0
+    for v, l in zip(np.atleast_1d(variances), ls):
+        K = K + rbf_ard_K(X, X2, float(v), l)
+    return K
+
+
+def rbf_sum_dK(X, X2, variances, lengthscales):
+    """List of dK/dtheta, theta ordered (variance_q, lengthscale_q[0..D-1]) per component: GPy's
+    RBF ARD gradients dK/dvar = K_q/var, dK/dl_d = K_q * (x_d - x'_d)^2 / l_d^3."""
+    X = np.asarray(X, dtype=np.float64)
+    X2 = X if X2 is None else np.asarray(X2, dtype=np.float64)
+    ls = np.atleast_2d(np.asarray(lengthscales, dtype=np.float64))
+    out = []
+    for v, l in zip(np.atleast_1d(variances), ls):
+        Kq = rbf_ard_K(X, X2, float(v), l)
+        out.append(Kq / float(v))
+        for d in range(X.shape[1]):
+            diff = X[:, d][:, None] - X2[:, d][None, :]
+            out.append(Kq * diff * diff / l[d] ** 3)
+    return out
+
+
+def rbf_kernel_grad_sums(dL_dK, X, X2, variances, lengthscales):
+    return np.array([np.sum(d * dL_dK) for d in rbf_sum_dK(X, X2, variances, lengthscales)])
+
+
+def rbf_fit(X, y, variances, lengthscales, noise, jitter=0.0):
+    """Cholesky fit of the scalar GP (sklearn _gpr.py:350-367 with alpha=jitter; GPy adds 1e-8)."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = rbf_sum_K(X, None, variances, lengthscales)
+    n = K.shape[0]
+    K[np.diag_indices(n)] += noise + jitter
+    L = sla.cholesky(K, lower=True, check_finite=False)
+    alpha = sla.cho_solve((L, True), y, check_finite=False)
+    val = -0.5 * float(y @ alpha) - float(np.sum(np.log(np.diag(L)))) - 0.5 * n * LOG_2PI
+    return {"L": L, "alpha": alpha, "lml": val}
+
+
+def rbf_predict(X, fitres, variances, lengthscales, Xs, var_add=0.0, chunk=4096):
+    """mean = K* alpha, var = k** - colsumsq(L^-1 K*^T) clamped at 0, + var_add (the WhiteKernel /
+    Gaussian-noise variance both sklearn's predict(return_std) and GPy's predict include)."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    M = Xs.shape[0]
+    mean, var = np.empty(M), np.empty(M)
+    kss = float(np.sum(variances))
+    for s in range(0, M, chunk):
+        e = min(M, s + chunk)
+        Ks = rbf_sum_K(Xs[s:e], X, variances, lengthscales)
+        mean[s:e] = Ks @ fitres["alpha"]
+        V = sla.solve_triangular(fitres["L"], Ks.T, lower=True, check_finite=False)
+        var[s:e] = kss - np.einsum("ij,ij->j", V, V)
+    return mean, np.where(var < 0.0, 0.0, var) + var_add
+
+
+def rbf_lml_and_grad(X, y, variances, lengthscales, noise, jitter=0.0):
+    """LML and its gradient over (variance_q, lengthscale_q[..])_q then noise."""
+    f = rbf_fit(X, y, variances, lengthscales, noise, jitter)
+    n = f["L"].shape[0]
+    Kinv = sla.cho_solve((f["L"], True), np.eye(n), check_finite=False)
+    dL_dK = 0.5 * (np.outer(f["alpha"], f["alpha"]) - Kinv)
+    g = rbf_kernel_grad_sums(dL_dK, X, None, variances, lengthscales)
+    return f["lml"], np.concatenate([g, [np.trace(dL_dK)]])
 
 
 # --------------------------------------------------------------------------------------

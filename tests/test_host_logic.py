@@ -36,6 +36,19 @@ def test_param_transform_roundtrip_and_derivative(make, vals):
         assert p.dvalue_dfree(x) == pytest.approx((hi - lo) / (2 * h), rel=1e-5, abs=1e-10)
 
 
+def test_param_transforms_do_not_overflow():
+    p = Param("v", 1.0).constrain_positive()
+    p.from_free(-754.0)
+    assert p.value > 0 and np.isfinite(p.dvalue_dfree(-754.0))
+    p.from_free(800.0)
+    assert p.value == 800.0 and p.dvalue_dfree(800.0) == 1.0
+    r = Param("r", 0.5).constrain_bounded(0, 1)
+    r.from_free(-5000.0)
+    assert 0 < r.value < 1e-10 and np.isfinite(r.dvalue_dfree(-5000.0))
+    r.from_free(5000.0)
+    assert r.value <= 1.0 and np.isfinite(r.dvalue_dfree(5000.0))
+
+
 def test_param_behaves_like_a_float():
     p = Param("length_df", np.array([2.5]))
     assert float(p) == 2.5 and p[0] == 2.5

@@ -155,3 +155,45 @@ def test_live_reference_slices_agree_with_oracle():
     gs = rs.gp_scripts()
     np.testing.assert_allclose(orc.helmholtz_K(X, X2, 1.1, 2.7, 0.35),
                                gs["myKernel"](X, X2, 1.1, 2.7, 0.35), atol=1e-15)
+
+
+# ---- scalar ARD-RBF sum family: oracle pinned against live scikit-learn (krig.py:174-194) --------
+def _hp_split(HP):
+    """HP as krig.scikit_prior reads a GPy param_array: [var, l_t, l_y, l_x](, [var, l_t, l_y, l_x]), noise."""
+    Q = (HP.size - 1) // 4
+    var = [HP[4 * q] for q in range(Q)]
+    ls = [HP[4 * q + 1:4 * q + 4] for q in range(Q)]
+    return var, ls, float(HP[-1])
+
+
+@pytest.mark.parametrize("name", ["sklearn_rbf1", "sklearn_rbf2"])
+def test_rbf_oracle_matches_scikit_learn(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    var, ls, noise = _hp_split(g["HP"])
+    XT, u, Xg = g["XT"], g["u"], g["Xg"]
+    np.testing.assert_allclose(orc.rbf_sum_K(XT[:40], Xg[:30], var, ls), g["ref_K_signal"], rtol=1e-13, atol=1e-16)
+    Ktr = orc.rbf_sum_K(XT[:50], None, var, ls) + noise * np.eye(50)
+    np.testing.assert_allclose(Ktr, g["ref_K_train"], rtol=1e-13, atol=1e-16)
+    f = orc.rbf_fit(XT, u, var, ls, noise, jitter=float(g["sklearn_alpha"]))
+    assert abs(f["lml"] - float(g["ref_lml"])) <= 1e-9 * abs(float(g["ref_lml"]))
+    mean, v = orc.rbf_predict(XT, f, var, ls, Xg, var_add=noise)       # WhiteKernel is in sklearn's variance
+    np.testing.assert_allclose(mean, g["ref_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(v, g["ref_var"], rtol=1e-8)
+    # sklearn differentiates w.r.t. log(theta): d/dlog(theta) = theta * d/dtheta
+    lml, grad = orc.rbf_lml_and_grad(XT, u, var, ls, noise, jitter=float(g["sklearn_alpha"]))
+    theta = np.exp(g["ref_theta"])
+    np.testing.assert_allclose(grad * theta, g["ref_grad_logtheta"], rtol=1e-7, atol=1e-8)
+
+
+def test_rbf_kernel_gradient_matches_central_differences(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sklearn_rbf2.npz"))
+    var, ls, _ = _hp_split(g["HP"])
+    X, X2 = g["XT"][:30], g["Xg"][:20]
+    W = np.random.default_rng(1).normal(size=(30, 20))
+    got = orc.rbf_kernel_grad_sums(W, X, X2, var, ls)
+    theta = np.concatenate([[var[q]] + list(ls[q]) for q in range(2)])
+
+    def f(th):
+        return np.sum(orc.rbf_sum_K(X, X2, [th[0], th[4]], [th[1:4], th[5:8]]) * W)
+    fd = np.array([(f(theta + 1e-6 * e) - f(theta - 1e-6 * e)) / 2e-6 for e in np.eye(8)])
+    np.testing.assert_allclose(got, fd, rtol=1e-6, atol=1e-8)

@@ -235,5 +235,5 @@ def test_krig_workflow(tmp_path):
     assert res["Vp"].shape[0] == mat["Xt"].shape[0]
     rv, ru = krig.getRMSE(out)
     assert 0 < rv < 0.5 and 0 < ru < 0.5
-    with pytest.raises(NotImplementedError):
-        krig.make_kernel(1)
+    with pytest.raises(ValueError):
+        krig.make_kernel(5)
