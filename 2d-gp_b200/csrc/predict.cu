@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
     const int gjl = tid & 63, os = tid >> 6;
     const int nb = p.npad / TILE;
     const int gper = PRED_GROUPS / p.nsplit;
-    double* panel = p.scratch + (size_t)blockIdx.x * p.npad * TILE;
+    double* panel = p.scratch + (size_t)blockIdx.x * ((size_t)p.npad * TILE + 20480 / sizeof(double));
 
     FragLane<false, 64> fa;
     FragLane<true, 32> fb;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
             const double gx = gvalid ? p.Xs[2 * (long)gj] : 0.0;
             const double gy = gvalid ? p.Xs[2 * (long)gj + 1] : 0.0;
             const int nobs_pad = p.npad >> 1;
-#pragma unroll 2
+#pragma unroll 4
             for (int o = os; o < nobs_pad; o += OS) {
                 double k11 = 0.0, k12 = 0.0, k22 = 0.0;
                 if (gvalid && o < p.N) {
@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(TILE) predict_finish_kernel(PredictArgs p) {
     p.var[oidx] = v + p.var_add;
 }
 
-size_t predict_panel_bytes(int npad) { return (size_t)npad * TILE * sizeof(double); }
+// + 20 KB: consecutive panels must not sit at the same offset modulo a power of two (every CTA
+// streams its panel at the same pace; identical low address bits would pile onto the same L2 slices)
+size_t predict_panel_bytes(int npad) { return (size_t)npad * TILE * sizeof(double) + 20480; }
 
 int predict_max_ctas() {
     static int sms = 0;

@@ -272,7 +272,7 @@ def test_predict_row_block_split_invariance(N):
     from gp2d_b200.engine import _ptr, _stream
     M = 640
     Xsd = gp.as_dev(big[:M])
-    small = torch.empty(8 * 128 * (((2 * N + 127) // 128) * 128), dtype=torch.uint8, device=DEV)   # exactly one K* panel
+    small = torch.empty(8 * 128 * (((2 * N + 127) // 128) * 128) + 20480, dtype=torch.uint8, device=DEV)   # exactly one K* panel
     mean = torch.empty(2 * M, dtype=torch.float64, device=DEV)
     var = torch.empty(2 * M, dtype=torch.float64, device=DEV)
     rc = lib.gp2d_predict(_ptr(m.ws), N, 1.3, 3.1, 0.2, _ptr(Xsd), M, M, 0.0, _ptr(mean), _ptr(var), _ptr(small),
