@@ -158,29 +158,88 @@ class GPRegression:
         self._set_free(rng.standard_normal(len(self._free_params())))
         self._sync()
 
+    def _clone(self):
+        """Independent model on the same data and device (own fit workspace), for concurrent restarts."""
+        m = GPRegression(self.X, self.Y, self.kern.copy(), noise_var=float(self.Gaussian_noise), jitter=self.jitter,
+                         device=self._gp.device)
+        for a, b in zip(m.parameters, self.parameters):
+            a.constraint = b.constraint
+        return m
+
+    def _one_restart(self, r, init, child, max_iters):
+        if r == 0:
+            self._set_free(init)
+        else:
+            self.randomize(np.random.default_rng(child))
+        return self.optimize(max_iters=max_iters, messages=False)
+
     def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, messages=False, max_iters=1000,
-                          seed=None, rank=0, world=1, **kw):
+                          seed=None, rank=0, world=1, parallel=1, **kw):
         """GPy semantics: optimise from the current point, then from random points; keep the
         best.  ``rank``/``world`` shard the restart indices (restart r runs on rank r % world);
-        use gp2d_b200.dist.gather_best to pick the global winner."""
+        use gp2d_b200.dist.gather_best to pick the global winner.  ``parallel`` > 1 runs that many
+        restarts of this rank concurrently, each on its own CUDA stream and workspace: one
+        small-n factorisation is a latency-bound chain of kernels that leaves most SMs idle, so
+        independent restarts overlap almost for free.  Restart r always starts from the point
+        drawn from seed-sequence child r, so the set of runs does not depend on the sharding."""
+        import torch
         base = np.random.SeedSequence(seed)
         children = base.spawn(int(num_restarts))
         init = np.array([p.to_free() for p in self._free_params()])
-        for r in range(int(num_restarts)):
-            if r % world != rank:
-                continue
-            try:
-                if r == 0 and not self.optimization_runs:
-                    self._set_free(init)
-                else:
-                    self.randomize(np.random.default_rng(children[r]))
-                self.optimize(max_iters=max_iters, messages=False)
-                if messages or verbose:
-                    print("Optimization restart %d/%d, f = %s" % (r + 1, num_restarts, self.optimization_runs[-1].f_opt))
-            except Exception:
-                if robust:
-                    continue
-                raise
+        first = not self.optimization_runs
+        mine = [r for r in range(int(num_restarts)) if r % world == rank]
+        results = {}
+
+        def work(model, todo):
+            for r in todo:
+                try:
+                    rr = r if first else max(r, 1)           # only the very first restart starts from the current point
+                    results[r] = model._one_restart(rr, init, children[r], max_iters)
+                    if messages or verbose:
+                        print("Optimization restart %d/%d, f = %s" % (r + 1, num_restarts, results[r].f_opt))
+                except Exception:
+                    if not robust:
+                        raise
+
+        parallel = max(1, min(int(parallel), len(mine)))
+        if parallel == 1:
+            keep = len(self.optimization_runs)
+            work(self, mine)
+            del self.optimization_runs[keep:]
+        else:
+            import queue
+            import threading
+            workers = [self] + [self._clone() for _ in range(parallel - 1)]
+            errors = []
+            pending = queue.SimpleQueue()
+            for r in mine:
+                pending.put(r)
+
+            def pull():                   # restarts differ a lot in length: hand them out one by one
+                while True:
+                    try:
+                        yield pending.get_nowait()
+                    except queue.Empty:
+                        return
+
+            def run(model, todo):
+                try:
+                    with torch.cuda.device(self._gp.device), torch.cuda.stream(torch.cuda.Stream(self._gp.device)):
+                        keep = len(model.optimization_runs)
+                        work(model, todo)
+                        del model.optimization_runs[keep:]
+                        torch.cuda.current_stream().synchronize()
+                except Exception as e:          # re-raised in the caller's thread
+                    errors.append(e)
+            torch.cuda.current_stream().synchronize()
+            threads = [threading.Thread(target=run, args=(w, pull())) for w in workers]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+        self.optimization_runs += [results[r] for r in sorted(results)]
         if self.optimization_runs:
             best = min(self.optimization_runs, key=lambda o: o.f_opt)
             self._set_free(best.x_opt)

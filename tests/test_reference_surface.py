@@ -198,6 +198,11 @@ def test_restart_sharding_is_a_partition():
     a, b = run(0, 2), run(1, 2)
     assert len(a) == 2 and len(b) == 2
     np.testing.assert_allclose(sorted(a + b), sorted(full), rtol=1e-9, atol=1e-9)
+    # concurrent restarts on separate streams / workspaces: the same runs, in restart order
+    m = models.GPRegression(X, y[:, None], myKernel.myKernel(2, [0, 1], 1.0, 1.0, 0.5))
+    m.optimize_restarts(num_restarts=4, verbose=False, seed=11, max_iters=25, parallel=3)
+    np.testing.assert_allclose([r.f_opt for r in m.optimization_runs], full, rtol=1e-9, atol=1e-9)
+    assert m.objective_function() == pytest.approx(min(full), rel=1e-9, abs=1e-9)
 
 
 # ---- krig workflows (krig.py:259-418,430-468,471-574,578-645) ----------------------------------------------

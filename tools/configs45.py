@@ -28,6 +28,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--restarts", type=int, default=8)
 ap.add_argument("--n-fit", type=int, default=2000)
 ap.add_argument("--maxiter", type=int, default=100)
+ap.add_argument("--parallel", type=int, default=4, help="concurrent restarts per GPU (own stream + workspace each)")
 ap.add_argument("--snapshots", type=int, default=8)
 ap.add_argument("--n-snap", type=int, default=8192)
 args = ap.parse_args()
@@ -66,7 +67,8 @@ for _ in range(5):
 t_eval = (time.perf_counter() - t0) / 5
 sync()
 t0 = time.perf_counter()
-model.optimize_restarts(num_restarts=args.restarts, verbose=False, seed=4, max_iters=args.maxiter, rank=rank, world=world)
+model.optimize_restarts(num_restarts=args.restarts, verbose=False, seed=4, max_iters=args.maxiter, rank=rank, world=world,
+                        parallel=args.parallel)
 best = gdist.gather_best(model)
 sync()
 t_restarts = tmax(time.perf_counter() - t0)
@@ -75,7 +77,7 @@ nf = torch.tensor([nfev], dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(nf)
 out["restarts"] = {
-    "N": args.n_fit, "restarts": args.restarts, "maxiter": args.maxiter, "lml_grad_eval_ms": t_eval * 1e3,
+    "N": args.n_fit, "restarts": args.restarts, "maxiter": args.maxiter, "parallel_per_gpu": args.parallel, "lml_grad_eval_ms": t_eval * 1e3,
     "wall_s": t_restarts, "restarts_per_s": args.restarts / t_restarts, "objective_evaluations": int(nf.item()),
     "best_objective": best, "theta": model.param_array.tolist()}
 
