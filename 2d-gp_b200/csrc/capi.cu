@@ -622,6 +622,8 @@ int gp2d_dbg_set_cta_threads(int nt) { set_cta_threads(nt); return get_cta_threa
 
 int gp2d_dbg_set_small_tile_threshold(int t) { set_small_tile_threshold(t); return t; }
 
+int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; }
+
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,
                   void* stream) {

@@ -71,23 +71,47 @@ static void gemm_launch_ws(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& 
     else dgemm_ws_kernel<true, false><<<grid, WS_THREADS, SM, st>>>(a);
 }
 
-// 128-tiles below this count leave most of the 148 SMs idle: switch to 64x64 tiles
-static int g_small_tile_threshold = 296;
+// Tile shape per launch.  Measured per 16-deep k-step on B200 (tools/explore.py gemm_small):
+//   128-tile warp-specialised kernel: 2.23 us per wave of 148 CTAs (one CTA per SM);
+//   64-tile kernel: 0.82 / 1.20 / 1.65 us with 1 / 2 / 3 CTAs resident per SM, 1.65 us per wave of
+//   3 x 148 beyond that.
+// The cheaper estimate wins: small problems and awkward wave counts (e.g. 300 tiles = 2.03 waves)
+// go to the 64-tile kernel, everything else to the 128-tile one.  A non-negative override forces
+// 128-tiles at or above that many 128-tiles (0: always, huge: never) -- tests use it.
+static int g_small_tile_threshold = -1;
 void set_small_tile_threshold(int t) { g_small_tile_threshold = t; }
+
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+static bool use_tile64(long t128, long t64) {
+    if (g_small_tile_threshold >= 0) return t128 < g_small_tile_threshold;
+    const long sms = num_sms();
+    const double est128 = 2.23 * (double)((t128 + sms - 1) / sms);
+    const long c = (t64 + sms - 1) / sms;
+    const double est64 = c <= 1 ? 0.82 : c == 2 ? 1.20 : c == 3 ? 1.65 : 1.65 * (double)((t64 + 3 * sms - 1) / (3 * sms));
+    return est64 < est128;
+}
 
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t st) {
     if (a.M % TILE || a.N % TILE || a.K % BK || a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
     if ((a.lda & 1) || (a.ldb & 1) || (a.ldc & 1)) return cudaErrorInvalidValue;
     cudaError_t e = dgemm_init();
     if (e != cudaSuccess) return e;
-    long tm = a.M / TILE, tn = a.N / TILE;
+    const long tm = a.M / TILE, tn = a.N / TILE;
     if (a.lower_out && tm != tn) return cudaErrorInvalidValue;
-    long grid = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
-    if (grid < g_small_tile_threshold) {
-        tm *= 2; tn *= 2;
-        grid = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
-        gemm_launch64(a_mn, b_mn, (unsigned)grid, a, st);
-    } else gemm_launch_ws(a_mn, b_mn, (unsigned)grid, a, st);
+    const long t128 = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
+    const long t64 = a.lower_out ? (2 * tm) * (2 * tm + 1) / 2 : 4 * tm * tn;
+    if (use_tile64(t128, t64)) gemm_launch64(a_mn, b_mn, (unsigned)t64, a, st);
+    else gemm_launch_ws(a_mn, b_mn, (unsigned)t128, a, st);
     return cudaGetLastError();
 }
 
@@ -214,6 +238,36 @@ __global__ void copy2d_kernel(const double* __restrict__ src, long lds, double* 
     }
 }
 
+// Side streams: at every node the GEMM U = T * Z11 (first half of the inverse update) depends only
+// on T and Z11, so it runs beside the SYRK and the whole recursion into A22 -- a chain of small,
+// latency-bound kernels that leaves most SMs idle.  One side stream and two events per recursion
+// depth (at most one side GEMM is outstanding per depth), per host thread; events are re-recorded
+// freely because a stream wait captures the record that precedes it.
+constexpr int POTRI_MAX_DEPTH = 12;
+struct PotriSide {
+    cudaStream_t stream[POTRI_MAX_DEPTH];
+    cudaEvent_t forked[POTRI_MAX_DEPTH], joined[POTRI_MAX_DEPTH];
+    int device = -1;
+    bool ok = false;
+    bool init() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        if (ok && dev == device) return true;
+        if (ok) return false;            // a thread that switches devices falls back to one stream
+        for (int i = 0; i < POTRI_MAX_DEPTH; ++i) {
+            if (cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&forked[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&joined[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        device = dev;
+        ok = true;
+        return true;
+    }
+};
+static thread_local PotriSide g_side;
+static bool g_potri_overlap = true;
+void set_potri_overlap(bool on) { g_potri_overlap = on; }
+
 struct PotriCtx {
     double* A; long lda;
     double* Z; long ldz;
@@ -222,14 +276,18 @@ struct PotriCtx {
     bool keep_L;
     cudaStream_t st;
     cudaError_t err;
+    PotriSide* side;    // nullptr: everything on st
 };
 
-static void gemm_checked(PotriCtx& c, bool a_mn, bool b_mn, const GemmArgs& g) {
+static void gemm_checked(PotriCtx& c, bool a_mn, bool b_mn, const GemmArgs& g, cudaStream_t st) {
     if (c.err != cudaSuccess) return;
-    c.err = launch_dgemm(a_mn, b_mn, g, c.st);
+    c.err = launch_dgemm(a_mn, b_mn, g, st);
+}
+static void cuda_checked(PotriCtx& c, cudaError_t e) {
+    if (c.err == cudaSuccess) c.err = e;
 }
 
-static void potri_rec(PotriCtx& c, int off, int n, bool need_inv) {
+static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
     if (c.err != cudaSuccess) return;
     if (n == TILE) {
         potri_leaf_kernel<<<1, NTHREADS, LEAF_SMEM_BYTES, c.st>>>(
@@ -245,12 +303,21 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv) {
     double* Z21 = c.Z + (long)(off + n1) * c.ldz + off;
     double* Z22 = c.Z + (long)(off + n1) * (c.ldz + 1);
 
-    potri_rec(c, off, n1, true);
+    potri_rec(c, off, n1, true, depth + 1);
     // T = A21 * Z11^T -> Z21 (scratch use of the block that will later hold Z21)
-    gemm_checked(c, false, false, GemmArgs{A21, c.lda, Z11, c.ldz, Z21, c.ldz, n2, n1, n1, 1.0, 0.0, 0, KR_LE_N});
+    gemm_checked(c, false, false, GemmArgs{A21, c.lda, Z11, c.ldz, Z21, c.ldz, n2, n1, n1, 1.0, 0.0, 0, KR_LE_N}, c.st);
+    // U = T * Z11 into A21 (free once T is formed) on the side stream of this depth
+    const bool fork = need_inv && !c.keep_L && c.side && depth < POTRI_MAX_DEPTH && n >= 4 * TILE;
+    if (fork && c.err == cudaSuccess) {
+        cuda_checked(c, cudaEventRecord(c.side->forked[depth], c.st));
+        cuda_checked(c, cudaStreamWaitEvent(c.side->stream[depth], c.side->forked[depth], 0));
+        gemm_checked(c, false, true, GemmArgs{Z21, c.ldz, Z11, c.ldz, A21, c.lda, n2, n1, n1, 1.0, 0.0, 0, KR_GE_N},
+                     c.side->stream[depth]);
+        cuda_checked(c, cudaEventRecord(c.side->joined[depth], c.side->stream[depth]));
+    }
     // A22 -= T * T^T (lower tiles)
-    gemm_checked(c, false, false, GemmArgs{Z21, c.ldz, Z21, c.ldz, A22, c.lda, n2, n2, n1, -1.0, 1.0, 1, KR_FULL});
-    potri_rec(c, off + n1, n2, need_inv);
+    gemm_checked(c, false, false, GemmArgs{Z21, c.ldz, Z21, c.ldz, A22, c.lda, n2, n2, n1, -1.0, 1.0, 1, KR_FULL}, c.st);
+    potri_rec(c, off + n1, n2, need_inv, depth + 1);
     if (c.err != cudaSuccess) return;
     double* U = A21; long ldu = c.lda;
     if (c.keep_L) {
@@ -260,8 +327,9 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv) {
     }
     if (need_inv) {
         // U = T * Z11 ; Z21 = -Z22 * U
-        gemm_checked(c, false, true, GemmArgs{Z21, c.ldz, Z11, c.ldz, U, ldu, n2, n1, n1, 1.0, 0.0, 0, KR_GE_N});
-        gemm_checked(c, false, true, GemmArgs{Z22, c.ldz, U, ldu, Z21, c.ldz, n2, n1, n2, -1.0, 0.0, 0, KR_LE_M});
+        if (fork) cuda_checked(c, cudaStreamWaitEvent(c.st, c.side->joined[depth], 0));
+        else gemm_checked(c, false, true, GemmArgs{Z21, c.ldz, Z11, c.ldz, U, ldu, n2, n1, n1, 1.0, 0.0, 0, KR_GE_N}, c.st);
+        gemm_checked(c, false, true, GemmArgs{Z22, c.ldz, U, ldu, Z21, c.ldz, n2, n1, n2, -1.0, 0.0, 0, KR_LE_M}, c.st);
     }
 }
 
@@ -276,8 +344,9 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
     }
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess};
-    potri_rec(c, 0, n, need_inv);
+    PotriSide* side = (g_potri_overlap && !keep_L && need_inv && n >= 4 * TILE && g_side.init()) ? &g_side : nullptr;
+    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess, side};
+    potri_rec(c, 0, n, need_inv, 0);
     return c.err;
 }
 

@@ -13,6 +13,7 @@ namespace gp2d {
 // log(L_ii); *info the 1-based index of the first non-positive pivot, else 0.
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
                         bool need_inv, bool keep_L, double* W, cudaStream_t st);
+void set_potri_overlap(bool on);      // bring-up switch: side-stream overlap of the inverse GEMMs
 // alpha = Z^T Z y and LML from Z, logdiag.  y_block is the caller's vector: stacked [u;v] of
 // length 2N (ncomp = 2) or N scalar observations (ncomp = 1); everything else is internal
 // (pair-interleaved for ncomp = 2, padded to npad).

@@ -48,7 +48,7 @@ def tile_variant(request):
     """Force the 128x128-tile or the 64x64-tile GEMM kernel for every launch in the test."""
     lib.gp2d_dbg_set_small_tile_threshold(request.param)
     yield request.param
-    lib.gp2d_dbg_set_small_tile_threshold(296)
+    lib.gp2d_dbg_set_small_tile_threshold(-1)
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
@@ -301,6 +301,29 @@ def test_predict_state_ships_to_another_workspace():
     m1, v1 = b.predict(Xs)
     assert torch.equal(m0, m1) and torch.equal(v0, v1)
     assert a.predict_state().numel() < a.ws.numel() // 2
+
+
+def test_side_stream_overlap_changes_nothing():
+    """The inverse-update GEMMs run on side streams beside the Cholesky chain; with the overlap
+    switched off the same kernels run on one stream: identical bits either way."""
+    lib.gp2d_dbg_set_potri_overlap.restype = C.c_int
+    lib.gp2d_dbg_set_potri_overlap.argtypes = [C.c_int]
+    X, y = synthetic.drifter_snapshot(1100, config_id=6)
+    Xs = synthetic.prediction_grid(X, 30, 30)
+    res = []
+    for on in (1, 0, 1):
+        lib.gp2d_dbg_set_potri_overlap(on)
+        m = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+        lml, grad = m.lml_and_grad()
+        al = m.alpha()
+        mean, var = m.predict(Xs)
+        res.append((lml, grad, al, mean, var))
+    lib.gp2d_dbg_set_potri_overlap(1)
+    for r in res[1:]:
+        assert r[0] == res[0][0] and np.array_equal(r[1], res[0][1])
+        assert torch.equal(r[2], res[0][2]) and torch.equal(r[3], res[0][3]) and torch.equal(r[4], res[0][4])
+    f = orc.fit(X, y, 1.3, 3.1, 0.2, 0.05)
+    np.testing.assert_allclose(res[0][2].cpu().numpy(), f["alpha"], rtol=1e-7, atol=1e-9 * np.abs(f["alpha"]).max())
 
 
 def test_not_positive_definite_raises():

@@ -125,6 +125,32 @@ def gemm():
     lib.gp2d_dbg_set_cta_threads(256)
 
 
+def gemm_small():
+    """128-tile warp-specialised kernel vs 64-tile kernel on the small GEMMs of the Cholesky recursion."""
+    lib.gp2d_dbg_gemm.restype = C.c_int
+    lib.gp2d_dbg_gemm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                  C.c_int, C.c_void_p]
+    lib.gp2d_dbg_set_small_tile_threshold.restype = C.c_int
+    lib.gp2d_dbg_set_small_tile_threshold.argtypes = [C.c_int]
+    st = torch.cuda.current_stream().cuda_stream
+    for n in (256, 512, 768, 1024, 1280, 1536, 2048, 3072):
+        A = torch.randn(n, n, dtype=torch.float64, device=dev)
+        B = torch.randn(n, n, dtype=torch.float64, device=dev)
+        Cm = torch.zeros(n, n, dtype=torch.float64, device=dev)
+        res = []
+        for thr in (0, 1 << 30):
+            lib.gp2d_dbg_set_small_tile_threshold(thr)
+            for lower in (0, 1):
+                t = timeit(lambda: lib.gp2d_dbg_gemm(0, 0, A.data_ptr(), n, B.data_ptr(), n, Cm.data_ptr(), n, n, n, n,
+                                                     1.0, 0.0, lower, 0, st), reps=20, warm=3)
+                res.append(t * 1e6)
+        t128 = (n // 128) ** 2
+        print("gemm n=%d (%d tiles / %d lower): ws128 %.1f us (lower %.1f)   tile64 %.1f us (lower %.1f)" % (
+            n, t128, (n // 128) * (n // 128 + 1) // 2, res[0], res[1], res[2], res[3]))
+    lib.gp2d_dbg_set_small_tile_threshold(-1)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["micro", "stages", "potrf"]
     if "micro" in what:
@@ -137,3 +163,5 @@ if __name__ == "__main__":
         potrf_sizes()
     if "gemm" in what:
         gemm()
+    if "gemm_small" in what:
+        gemm_small()
