@@ -390,3 +390,90 @@ def test_config2_full_size_properties():
     # GP identity at the observation sites: K alpha = y - noise * alpha
     pm, _ = m.predict(X)
     torch.testing.assert_close(pm + noise * m.alpha(), m.y, rtol=1e-9, atol=1e-10)
+
+
+# ---- guard bands: no kernel writes outside the buffers the C ABI was given ----------------------
+# (compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are hunted this way)
+GUARD = 8192
+
+
+def _guarded(nbytes):
+    """uint8 tensor of nbytes with GUARD bytes of 0xA5 on both sides; returns (whole, interior view)."""
+    nbytes = (int(nbytes) + 255) // 256 * 256
+    whole = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+    return whole, whole[GUARD:GUARD + nbytes]
+
+
+def _intact(whole):
+    return bool((whole[:GUARD] == 0xA5).all()) and bool((whole[-GUARD:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("N,M", [(1, 1), (63, 65), (200, 129), (321, 1000), (1100, 5000)])
+def test_no_writes_outside_buffers_helmholtz(N, M):
+    from gp2d_b200.engine import _stream
+    X, y = synthetic.drifter_snapshot(N, config_id=11, seed_offset=N)
+    Xs = synthetic.prediction_grid(X, M, 1)
+    Xd, yd, Xsd = dev(X), dev(y), dev(Xs)
+    theta = (1.3, 3.1, 0.2)
+    wsW, ws = _guarded(lib.gp2d_fit_workspace_bytes(N))
+    pwW, pws = _guarded(lib.gp2d_predict_workspace_bytes(N, M))
+    outW, out = _guarded(8 * (4 * M + 2 * N + 8 + 2))
+    o = out.view(torch.float64)
+    mean, var, alpha, scal = o[:2 * M], o[2 * M:4 * M], o[4 * M:4 * M + 2 * N], o[4 * M + 2 * N:4 * M + 2 * N + 8]
+    info = torch.zeros(1, dtype=torch.int32, device=DEV)
+    assert lib.gp2d_lml_grad(Xd.data_ptr(), N, yd.data_ptr(), *theta, 0.05, 1e-8, 0, ws.data_ptr(), ws.numel(),
+                             scal.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_fit(Xd.data_ptr(), N, yd.data_ptr(), *theta, 0.05, 0.0, ws.data_ptr(), ws.numel(), alpha.data_ptr(),
+                        scal.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_predict(ws.data_ptr(), N, *theta, Xsd.data_ptr(), M, M, 0.0, mean.data_ptr(), var.data_ptr(),
+                            pws.data_ptr(), pws.numel(), _stream()) == 0
+    # kernel build into a matrix with a wider leading dimension: the padding columns stay untouched
+    ld = 2 * M + 6
+    KW, Kb = _guarded(8 * 2 * N * ld)
+    assert lib.gp2d_kernel_build(Xd.data_ptr(), N, Xsd.data_ptr(), M, *theta, 0.0, Kb.data_ptr(), ld, _stream()) == 0
+    torch.cuda.synchronize()
+    assert _intact(wsW) and _intact(pwW) and _intact(outW) and _intact(KW)
+    Kv = Kb.view(torch.float64)[:2 * N * ld].view(2 * N, ld)
+    assert bool((Kv[:, 2 * M:].contiguous().view(torch.uint8) == 0xA5).all())
+    f = orc.fit(X, y, *theta, 0.05)
+    mo, vo = orc.predict(X, f, *theta, Xs)
+    np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-9 * max(np.abs(mo).max(), 1e-3))
+    np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,M,D,Q", [(1, 1, 1, 1), (127, 129, 3, 2), (500, 3000, 3, 2), (1025, 700, 4, 4)])
+def test_no_writes_outside_buffers_rbf(N, M, D, Q):
+    from gp2d_b200.engine import _stream
+    rng = np.random.default_rng(N)
+    X, Xs = rng.uniform(0, 12, (N, D)), rng.uniform(0, 12, (M, D))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N)
+    var_h = np.ascontiguousarray(rng.uniform(0.2, 1.5, Q))
+    ls_h = np.ascontiguousarray(rng.uniform(1.0, 5.0, (Q, D)))
+    Xd, yd, Xsd = dev(X), dev(y), dev(Xs)
+    wsW, ws = _guarded(lib.gp2d_rbf_fit_workspace_bytes(N, D))
+    pwW, pws = _guarded(lib.gp2d_rbf_predict_workspace_bytes(N, M))
+    ng = 2 + Q * (1 + D)
+    outW, out = _guarded(8 * (2 * M + N + ng))
+    o = out.view(torch.float64)
+    mean, var, alpha, scal = o[:M], o[M:2 * M], o[2 * M:2 * M + N], o[2 * M + N:2 * M + N + ng]
+    info = torch.zeros(1, dtype=torch.int32, device=DEV)
+    args = (D, )
+    assert lib.gp2d_rbf_lml_grad(Xd.data_ptr(), N, D, yd.data_ptr(), Q, var_h.ctypes.data, ls_h.ctypes.data, 0.01, 1e-8,
+                                 ws.data_ptr(), ws.numel(), scal.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_rbf_fit(Xd.data_ptr(), N, D, yd.data_ptr(), Q, var_h.ctypes.data, ls_h.ctypes.data, 0.01, 1e-8,
+                            ws.data_ptr(), ws.numel(), alpha.data_ptr(), scal.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_rbf_predict(ws.data_ptr(), N, D, Q, var_h.ctypes.data, ls_h.ctypes.data, Xsd.data_ptr(), M, 0.01,
+                                mean.data_ptr(), var.data_ptr(), pws.data_ptr(), pws.numel(), _stream()) == 0
+    ld = M + 3
+    KW, Kb = _guarded(8 * N * ld)
+    assert lib.gp2d_rbf_kernel_build(Xd.data_ptr(), N, Xsd.data_ptr(), M, D, Q, var_h.ctypes.data, ls_h.ctypes.data, 0.0,
+                                     Kb.data_ptr(), ld, _stream()) == 0
+    torch.cuda.synchronize()
+    assert _intact(wsW) and _intact(pwW) and _intact(outW) and _intact(KW)
+    Kv = Kb.view(torch.float64)[:N * ld].view(N, ld)
+    assert bool((Kv[:, M:].contiguous().view(torch.uint8) == 0xA5).all())
+    np.testing.assert_allclose(Kv[:, :M].cpu().numpy(), orc.rbf_sum_K(X, Xs, var_h, ls_h), rtol=1e-12, atol=1e-15)
+    f = orc.rbf_fit(X, y, var_h, ls_h, 0.01, jitter=1e-8)
+    mo, vo = orc.rbf_predict(X, f, var_h, ls_h, Xs, var_add=0.01)
+    np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-8 * max(np.abs(mo).max(), 1e-3))
+    np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
