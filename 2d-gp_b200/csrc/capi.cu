@@ -48,8 +48,10 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
     return L;
 }
 
-FitLayout fit_layout(int N) {
-    return fit_layout_general(2 * (size_t)N, 2 * (size_t)N, 4 * (size_t)lml_grad_partials(round_up(2 * N, TILE)));
+// ldx = 2: points (a, b); ldx = 3: space-time points (t, a, b)
+FitLayout fit_layout(int N, int ldx = 2) {
+    return fit_layout_general(2 * (size_t)N, (size_t)ldx * N,
+                              (HELM_NP + 1) * (size_t)lml_grad_partials(round_up(2 * N, TILE)));
 }
 
 FitLayout rbf_layout(int N, int D) {
@@ -139,7 +141,7 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     double* A = at<double>(ws, L.off_A);
     double* Z = at<double>(ws, L.off_Z);
     cudaError_t e;
-    e = cudaMemcpyAsync(at<double>(ws, L.off_X), X, 2 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyAsync(at<double>(ws, L.off_X), X, (size_t)hp.ldx * N * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
@@ -193,7 +195,7 @@ int gp2d_kdiag(int M, double l_df, double l_cf, double ratio, double* out, void*
 
 size_t gp2d_kernel_grad_workspace_bytes(int N, int M) {
     if (N <= 0 || M <= 0) return 256;
-    return align256(3 * sizeof(double) * (size_t)grad_sums_block_partials(N, M));
+    return align256(HELM_NP * sizeof(double) * ((size_t)grad_sums_block_partials(N, M) + 1));
 }
 
 int gp2d_kernel_grad(const double* X, int N, const double* X2, int M, double l_df, double l_cf,
@@ -208,7 +210,7 @@ int gp2d_kernel_grad(const double* X, int N, const double* X2, int M, double l_d
     if (!ws || ws_bytes < gp2d_kernel_grad_workspace_bytes(N, M)) return -12;
     if (!out3) return -13;
     return cuda_rc(kernel_grad_sums_block(X, N, X2, M, make_helm(l_df, l_cf, ratio), reference_compat != 0,
-                                          dL_dK, (long)ld, (double*)ws, (int)(ws_bytes / (3 * sizeof(double))),
+                                          dL_dK, (long)ld, (double*)ws, (int)(ws_bytes / (HELM_NP * sizeof(double))),
                                           out3, (cudaStream_t)stream));
 }
 
@@ -380,10 +382,151 @@ int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l
     e = launch_dgemm(true, true, GemmArgs{Z, L.npad, Z, L.npad, Kinv, L.npad, L.npad, L.npad, L.npad, 1.0, 0.0, 1, KR_GE_M}, st);
     if (e != cudaSuccess) return cuda_rc(e);
     double* scal = at<double>(ws, L.off_scal);
+    // scal = (LML, d/dl_df, d/dl_cf, d/dratio, d/dtvar, d/dlt, d/dnoise)
     e = lml_grad_reduce(Kinv, L.npad, L.npad, at<double>(ws, L.off_alpha), at<double>(ws, L.off_X), N, hp,
                         reference_compat != 0, at<double>(ws, L.off_partial), scal + 1, st);
     if (e != cudaSuccess) return cuda_rc(e);
-    e = cudaMemcpyAsync(out5, scal, 5 * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyAsync(out5, scal, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemcpyAsync(out5 + 4, scal + 6, sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
+/* ---- space-time product kernel: tvar exp(-dt^2 / 2 lt^2) * Helmholtz(a, b) ------------------------ */
+
+namespace {
+bool st_ok(double tvar, double lt) { return tvar > 0.0 && lt > 0.0 && isfinite(tvar) && isfinite(lt); }
+}
+
+int gp2d_st_kernel_build(const double* X3, int N, const double* X3b, int M, double l_df, double l_cf, double ratio,
+                         double tvar, double lt, double diag_add, double* K, int64_t ldk, void* stream) {
+    if (!X3) return -1;
+    if (N < 0) return -2;
+    if (M < 0 || (X3b == nullptr && M != N)) return -4;
+    if (!theta_ok(l_df, l_cf, ratio)) return -5;
+    if (!st_ok(tvar, lt)) return -8;
+    if (!K && N > 0 && M > 0) return -11;
+    if (ldk < 2 * (int64_t)M) return -12;
+    return cuda_rc(build_block_layout(X3, N, X3b, M, make_helm_st(l_df, l_cf, ratio, tvar, lt), diag_add, K, (long)ldk,
+                                      (cudaStream_t)stream));
+}
+
+int gp2d_st_kernel_grad(const double* X3, int N, const double* X3b, int M, double l_df, double l_cf, double ratio,
+                        double tvar, double lt, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                        double* out5, void* stream) {
+    if (!X3) return -1;
+    if (N <= 0) return -2;
+    if (M <= 0 || (X3b == nullptr && M != N)) return -4;
+    if (!theta_ok(l_df, l_cf, ratio)) return -5;
+    if (!st_ok(tvar, lt)) return -8;
+    if (!dL_dK) return -10;
+    if (ld < 2 * (int64_t)M) return -11;
+    if (!ws || ws_bytes < gp2d_kernel_grad_workspace_bytes(N, M)) return -13;
+    if (!out5) return -14;
+    return cuda_rc(kernel_grad_sums_block(X3, N, X3b, M, make_helm_st(l_df, l_cf, ratio, tvar, lt), false, dL_dK,
+                                          (long)ld, (double*)ws, (int)(ws_bytes / (HELM_NP * sizeof(double))), out5,
+                                          (cudaStream_t)stream));
+}
+
+size_t gp2d_st_fit_workspace_bytes(int N) {
+    if (N <= 0) return 0;
+    return fit_layout(N, 3).total;
+}
+
+int gp2d_st_fit_predict_state(int N, size_t* offset, size_t* bytes) {
+    if (N <= 0) return -1;
+    if (!offset) return -2;
+    if (!bytes) return -3;
+    FitLayout L = fit_layout(N, 3);
+    *offset = L.off_Zt;
+    *bytes = L.total - L.off_Zt;
+    return 0;
+}
+
+int gp2d_st_fit(const double* X3, int N, const double* y, double l_df, double l_cf, double ratio, double tvar,
+                double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
+                double* lml_out, int* info, void* stream) {
+    if (!X3) return -1;
+    if (N <= 0) return -2;
+    if (!y) return -3;
+    if (!theta_ok(l_df, l_cf, ratio)) return -4;
+    if (!st_ok(tvar, lt)) return -7;
+    if (!(noise >= 0.0)) return -9;
+    if (!(jitter >= 0.0)) return -10;
+    FitLayout L = fit_layout(N, 3);
+    if (!ws) return -11;
+    if (ws_bytes < L.total) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = fit_core(X3, N, y, make_helm_st(l_df, l_cf, ratio, tvar, lt), noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (alpha_out) {
+        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (lml_out) {
+        e = cudaMemcpyAsync(lml_out, at<double>(ws, L.off_scal), sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
+int gp2d_st_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, double tvar, double lt,
+                    const double* Xs3, int M, int64_t out_stride, double var_add, double* mean, double* var,
+                    void* ws, size_t ws_bytes, void* stream) {
+    if (!fit_ws) return -1;
+    if (N <= 0) return -2;
+    if (!theta_ok(l_df, l_cf, ratio)) return -3;
+    if (!st_ok(tvar, lt)) return -6;
+    if (M < 0) return -9;
+    if (M == 0) return 0;
+    if (!Xs3) return -8;
+    if (out_stride < M) return -10;
+    if (!mean) return -12;
+    if (!var) return -13;
+    FitLayout L = fit_layout(N, 3);
+    if (!ws) return -14;
+    if (ws_bytes < predict_panel_bytes(L.npad)) return -15;
+    return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
+                                 at<double>(fit_ws, L.off_X), N, make_helm_st(l_df, l_cf, ratio, tvar, lt), Xs3, M,
+                                 (long)out_stride, var_add, mean, var, (double*)ws, ws_bytes, (cudaStream_t)stream));
+}
+
+int gp2d_st_lml_grad(const double* X3, int N, const double* y, double l_df, double l_cf, double ratio, double tvar,
+                     double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* out7, int* info,
+                     void* stream) {
+    if (!X3) return -1;
+    if (N <= 0) return -2;
+    if (!y) return -3;
+    if (!theta_ok(l_df, l_cf, ratio)) return -4;
+    if (!st_ok(tvar, lt)) return -7;
+    if (!(noise >= 0.0)) return -9;
+    if (!(jitter >= 0.0)) return -10;
+    FitLayout L = fit_layout(N, 3);
+    if (!ws) return -11;
+    if (ws_bytes < L.total) return -12;
+    if (!out7) return -13;
+    cudaStream_t st = (cudaStream_t)stream;
+    HelmParams hp = make_helm_st(l_df, l_cf, ratio, tvar, lt);
+    cudaError_t e = fit_core(X3, N, y, hp, noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* Z = at<double>(ws, L.off_Z);
+    double* Kinv = at<double>(ws, L.off_A);
+    e = launch_dgemm(true, true, GemmArgs{Z, L.npad, Z, L.npad, Kinv, L.npad, L.npad, L.npad, L.npad, 1.0, 0.0, 1, KR_GE_M}, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* scal = at<double>(ws, L.off_scal);
+    e = lml_grad_reduce(Kinv, L.npad, L.npad, at<double>(ws, L.off_alpha), at<double>(ws, L.off_X), N, hp, false,
+                        at<double>(ws, L.off_partial), scal + 1, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemcpyAsync(out7, scal, 7 * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (info) {
         e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);

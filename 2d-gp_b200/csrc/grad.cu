@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
                 const double* __restrict__ X, int N, HelmParams hp, int compat,
                 double* __restrict__ partial) {
-    __shared__ double sh[4 * 32];
+    __shared__ double sh[(HELM_NP + 1) * 32];
     int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
@@ -23,9 +23,9 @@ lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restri
     const int J = t - I * (I + 1) / 2;
     const int jj = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = J * 64 + jj;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[HELM_NP + 1] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (j < N) {
-        const double bx = X[2 * (long)j], by = X[2 * (long)j + 1];
+        const HelmPoint qb = helm_point(hp, X, j);
         const double b0 = alpha[2 * j], b1 = alpha[2 * j + 1];
         for (int ii = ty; ii < 64; ii += 4) {
             const int i = I * 64 + ii;
@@ -36,20 +36,22 @@ lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restri
             const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
             const double W11 = 0.5 * (a0 * b0 - q0.x), W12 = 0.5 * (a0 * b1 - q0.y);
             const double W21 = 0.5 * (a1 * b0 - q1.x), W22 = 0.5 * (a1 * b1 - q1.y);
-            double g[3][3];
-            helm_block_grad(hp, compat, X[2 * (long)i] - bx, X[2 * (long)i + 1] - by, g);
+            double g[HELM_NP][3];
+            const HelmPoint pa = helm_point(hp, X, i);
+            helm_block_grad(hp, compat, pa.a - qb.a, pa.b - qb.b, pa.t - qb.t, g);
             const double wgt = (i == j) ? 1.0 : 2.0;
             const double Ws = W12 + W21;
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < HELM_NP; ++p)
                 acc[p] += wgt * (g[p][0] * W11 + g[p][1] * Ws + g[p][2] * W22);
-            if (i == j) acc[3] += W11 + W22;
+            if (i == j) acc[HELM_NP] += W11 + W22;
         }
     }
-    block_reduce<4>(acc, sh);
+    block_reduce<HELM_NP + 1>(acc, sh);
     if (threadIdx.x == 0) {
-        double* o = partial + 4 * (long)blockIdx.x;
-        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+        double* o = partial + (HELM_NP + 1) * (long)blockIdx.x;
+#pragma unroll
+        for (int p = 0; p <= HELM_NP; ++p) o[p] = acc[p];
     }
 }
 
@@ -58,12 +60,13 @@ int lml_grad_partials(int npad) {
     return T * (T + 1) / 2;
 }
 
+// out6 = d LML / d(l_df, l_cf, ratio, tvar, lt, noise); partial holds (HELM_NP + 1) * lml_grad_partials doubles
 cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha_int,
                             const double* X, int N, const HelmParams& hp, int compat,
-                            double* partial, double* out4, cudaStream_t st) {
+                            double* partial, double* out6, cudaStream_t st) {
     int count = lml_grad_partials(npad);
     lml_grad_kernel<<<count, 256, 0, st>>>(Kinv, ld, alpha_int, X, N, hp, compat, partial);
-    final_reduce_kernel<4><<<1, 1024, 0, st>>>(partial, count, out4);
+    final_reduce_kernel<HELM_NP + 1><<<1, 1024, 0, st>>>(partial, count, out6);
     return cudaGetLastError();
 }
 

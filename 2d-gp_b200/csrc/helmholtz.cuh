@@ -10,11 +10,17 @@
 
 namespace gp2d {
 
+// Optional time factor (space-time product kernel, scratch.py:506-508: Kt(t) * nonDivK(y, x) with
+// Kt = var exp(-dt^2 / 2 l_t^2) tiled over the 2x2 blocks, myKernel.py:350-360): points then have
+// three columns (t, a, b) and every 2x2 block is multiplied by tau(dt) = tvar exp(-dt^2 / 2 lt^2).
 struct HelmParams {
     double s_df, s_cf;   // 1/l_df^2, 1/l_cf^2
     double w_df, w_cf;   // ratio/l_df^2, (1-ratio)/l_cf^2
     double l_df, l_cf, ratio;
     int same_len;        // l_df == l_cf: one exp per pair
+    int has_t;           // time factor on
+    int ldx, xo;         // row stride of the point arrays and column of the first spatial coordinate
+    double tvar, lt, thalf;   // thalf = 1 / (2 lt^2)
 };
 
 inline HelmParams make_helm(double l_df, double l_cf, double ratio) {
@@ -25,6 +31,15 @@ inline HelmParams make_helm(double l_df, double l_cf, double ratio) {
     p.w_df = ratio * p.s_df;
     p.w_cf = (1.0 - ratio) * p.s_cf;
     p.same_len = (l_df == l_cf);
+    p.has_t = 0; p.ldx = 2; p.xo = 0;
+    p.tvar = 1.0; p.lt = 1.0; p.thalf = 0.0;
+    return p;
+}
+
+inline HelmParams make_helm_st(double l_df, double l_cf, double ratio, double tvar, double lt) {
+    HelmParams p = make_helm(l_df, l_cf, ratio);
+    p.has_t = 1; p.ldx = 3; p.xo = 1;
+    p.tvar = tvar; p.lt = lt; p.thalf = 0.5 / (lt * lt);
     return p;
 }
 
@@ -86,6 +101,29 @@ __device__ __forceinline__ void helm_block(const HelmParams& p, double d1, doubl
     k12 = c * (es - fs);
 }
 
+// A point of either layout: [N,2] rows (a, b) or [N,3] rows (t, a, b).
+struct HelmPoint { double a, b, t; };
+__device__ __forceinline__ HelmPoint helm_point(const HelmParams& p, const double* __restrict__ X, long i) {
+    const double* r = X + p.ldx * i;
+    HelmPoint q;
+    q.a = r[p.xo];
+    q.b = r[p.xo + 1];
+    q.t = p.has_t ? r[0] : 0.0;
+    return q;
+}
+__device__ __forceinline__ double helm_tau(const HelmParams& p, double dt) {
+    return p.tvar * exp_neg(-p.thalf * dt * dt);
+}
+// 2x2 block between two points, time factor included when it is on.
+__device__ __forceinline__ void helm_block_pts(const HelmParams& p, const HelmPoint& x, const HelmPoint& y,
+                                               double& k11, double& k12, double& k22) {
+    helm_block(p, x.a - y.a, x.b - y.b, k11, k12, k22);
+    if (p.has_t) {
+        const double tau = helm_tau(p, x.t - y.t);
+        k11 *= tau; k12 *= tau; k22 *= tau;
+    }
+}
+
 // Derivatives of the block w.r.t. (l_df, l_cf, ratio).
 //   compat == 0: analytic derivative
 //       dK_df/dl = ratio e^{-C/2} [ (C-2)/l^3 A_df + (2/l^5)(r^2 I - B) ]
@@ -94,8 +132,11 @@ __device__ __forceinline__ void helm_block(const HelmParams& p, double d1, doubl
 //       (myKernel.py:77-81, 91-96): (2/l^3) G + A (2-C)/l^3
 //   d/dratio = K_df - K_cf (myKernel.py:99-102) in both modes.
 // g[p][0..2] = (11, 12, 22) entries for parameter p.
+// g[3], g[4]: derivatives w.r.t. (tvar, lt) of the time factor (zero when it is off); with the
+// factor on, g[0..2] carry tau as well.
+constexpr int HELM_NP = 5;
 __device__ __forceinline__ void helm_block_grad(const HelmParams& p, int compat, double d1,
-                                                double d2, double (&g)[3][3]) {
+                                                double d2, double dt, double (&g)[HELM_NP][3]) {
     double a = d1 * d1, b = d2 * d2, c = d1 * d2, r2 = a + b;
     {   // divergence-free part
         double l = p.l_df, s = p.s_df, l3 = l * l * l;
@@ -123,6 +164,21 @@ __device__ __forceinline__ void helm_block_grad(const HelmParams& p, int compat,
         g[1][1] = w * (ca * A12 + cg * c);
         g[1][2] = w * (ca * A22 + cg * b);
         g[2][0] -= s * E * A11; g[2][1] -= s * E * A12; g[2][2] -= s * E * A22;
+    }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) g[3][e] = g[4][e] = 0.0;
+    if (p.has_t) {
+        // spatial block K_sp = ratio K_df + (1-ratio) K_cf; K = tau K_sp
+        double k11, k12, k22;
+        helm_block(p, d1, d2, k11, k12, k22);
+        const double et = exp_neg(-p.thalf * dt * dt), tau = p.tvar * et;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) g[q][e] *= tau;
+        const double cl = tau * dt * dt / (p.lt * p.lt * p.lt);      // dtau/dlt = tau dt^2 / lt^3
+        g[3][0] = et * k11; g[3][1] = et * k12; g[3][2] = et * k22;
+        g[4][0] = cl * k11; g[4][1] = cl * k12; g[4][2] = cl * k22;
     }
 }
 

@@ -28,16 +28,16 @@ build_block_kernel(const double* __restrict__ X, int N, const double* __restrict
     const int i0 = blockIdx.y * BB_I + ty * 8;
     if (j0 >= M) return;
     const bool has1 = (j0 + 1 < M);
-    const double bx0 = X2[2 * (long)j0], by0 = X2[2 * (long)j0 + 1];
-    const double bx1 = has1 ? X2[2 * (long)j0 + 2] : bx0, by1 = has1 ? X2[2 * (long)j0 + 3] : by0;
+    const HelmPoint q0 = helm_point(hp, X2, j0);
+    const HelmPoint q1 = has1 ? helm_point(hp, X2, j0 + 1) : q0;
 #pragma unroll 2
     for (int r = 0; r < 8; ++r) {
         const int i = i0 + r;
         if (i >= N) break;
-        const double ax = X[2 * (long)i], ay = X[2 * (long)i + 1];
+        const HelmPoint pa = helm_point(hp, X, i);
         double a11, a12, a22, b11, b12, b22;
-        helm_block(hp, ax - bx0, ay - by0, a11, a12, a22);
-        helm_block(hp, ax - bx1, ay - by1, b11, b12, b22);
+        helm_block_pts(hp, pa, q0, a11, a12, a22);
+        helm_block_pts(hp, pa, q1, b11, b12, b22);
         if (symmetric) {
             if (i == j0) { a11 += diag_add; a22 += diag_add; }
             if (i == j0 + 1) { b11 += diag_add; b22 += diag_add; }
@@ -83,13 +83,13 @@ build_interleaved_kernel(const double* __restrict__ X, int N, HelmParams hp, dou
     const int jj = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = J * 64 + jj;
     const bool jv = j < N;
-    const double bx = jv ? X[2 * (long)j] : 0.0, by = jv ? X[2 * (long)j + 1] : 0.0;
+    const HelmPoint qb = helm_point(hp, X, jv ? j : 0);
 #pragma unroll 4
     for (int ii = ty; ii < 64; ii += 4) {
         const int i = I * 64 + ii;
         double k11, k12, k22;
         if (jv && i < N) {
-            helm_block(hp, X[2 * (long)i] - bx, X[2 * (long)i + 1] - by, k11, k12, k22);
+            helm_block_pts(hp, helm_point(hp, X, i), qb, k11, k12, k22);
             if (i == j) { k11 += diag_add; k22 += diag_add; }
         } else {
             k12 = 0.0;
@@ -243,28 +243,30 @@ __global__ void __launch_bounds__(256)
 grad_sums_block_kernel(const double* __restrict__ X, int N, const double* __restrict__ X2, int M,
                        HelmParams hp, int compat, const double* __restrict__ W, long ld,
                        double* __restrict__ partial) {
-    __shared__ double sh[3 * 32];
+    __shared__ double sh[HELM_NP * 32];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = blockIdx.x * GS_J + tx;
-    double acc[3] = {0.0, 0.0, 0.0};
+    double acc[HELM_NP] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (j < M) {
-        const double bx = X2[2 * (long)j], by = X2[2 * (long)j + 1];
+        const HelmPoint qb = helm_point(hp, X2, j);
         for (int r = 0; r < 8; ++r) {
             const int i = blockIdx.y * GS_I + ty * 8 + r;
             if (i >= N) break;
-            double g[3][3];
-            helm_block_grad(hp, compat, X[2 * (long)i] - bx, X[2 * (long)i + 1] - by, g);
+            double g[HELM_NP][3];
+            const HelmPoint pa = helm_point(hp, X, i);
+            helm_block_grad(hp, compat, pa.a - qb.a, pa.b - qb.b, pa.t - qb.t, g);
             const double* w0 = W + (long)i * ld + j;
             const double* w1 = W + ((long)N + i) * ld + j;
             const double w11 = w0[0], w12 = w0[M] + w1[0], w22 = w1[M];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) acc[p] += g[p][0] * w11 + g[p][1] * w12 + g[p][2] * w22;
+            for (int p = 0; p < HELM_NP; ++p) acc[p] += g[p][0] * w11 + g[p][1] * w12 + g[p][2] * w22;
         }
     }
-    block_reduce<3>(acc, sh);
+    block_reduce<HELM_NP>(acc, sh);
     if (threadIdx.x == 0) {
-        double* o = partial + 3 * ((long)blockIdx.y * gridDim.x + blockIdx.x);
-        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+        double* o = partial + HELM_NP * ((long)blockIdx.y * gridDim.x + blockIdx.x);
+#pragma unroll
+        for (int p = 0; p < HELM_NP; ++p) o[p] = acc[p];
     }
 }
 
@@ -272,16 +274,21 @@ int grad_sums_block_partials(int N, int M) {
     return ((M + GS_J - 1) / GS_J) * ((N + GS_I - 1) / GS_I);
 }
 
+// out receives 3 sums (l_df, l_cf, ratio), or 5 (+ tvar, lt) when the time factor is on; partial
+// holds HELM_NP * (grad_sums_block_partials + 1) doubles.
 cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int M, const HelmParams& hp,
                                    int compat, const double* dL_dK, long ld, double* partial,
-                                   int partial_cap, double* out3, cudaStream_t st) {
+                                   int partial_cap, double* out, cudaStream_t st) {
     if (X2 == nullptr) X2 = X;
     dim3 grid((M + GS_J - 1) / GS_J, (N + GS_I - 1) / GS_I);
     int count = grid.x * grid.y;
-    if (count > partial_cap) return cudaErrorInvalidValue;
+    if (count + 1 > partial_cap) return cudaErrorInvalidValue;
+    double* full = partial + (size_t)HELM_NP * count;
     grad_sums_block_kernel<<<grid, 256, 0, st>>>(X, N, X2, M, hp, compat, dL_dK, ld, partial);
-    final_reduce_kernel<3><<<1, 1024, 0, st>>>(partial, count, out3);
-    return cudaGetLastError();
+    final_reduce_kernel<HELM_NP><<<1, 1024, 0, st>>>(partial, count, full);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(out, full, (hp.has_t ? 5 : 3) * sizeof(double), cudaMemcpyDeviceToDevice, st);
 }
 
 }  // namespace gp2d

@@ -38,7 +38,7 @@ cudaError_t build_interleaved_lower(const double* X, int N, const HelmParams& hp
 // sum(dK/dtheta * dL_dK) for theta = (l_df, l_cf, ratio); dL_dK in block layout [2N,2M].
 cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int M, const HelmParams& hp,
                                    int compat, const double* dL_dK, long ld, double* partial,
-                                   int partial_cap, double* out3, cudaStream_t st);
+                                   int partial_cap, double* out, cudaStream_t st);
 int grad_sums_block_partials(int N, int M);
 
 // scalar ARD-RBF sum (rbf.cuh): K[N,M] row-major; internal padded lower tiles; sum(dK/dtheta * dL_dK)
@@ -68,10 +68,10 @@ cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, c
 int predict_max_ctas();
 
 // grad.cu ---------------------------------------------------------------------------------
-// From Kinv (lower, interleaved, padded) and alpha_int: out4 = d LML / d(l_df, l_cf, ratio, noise).
+// From Kinv (lower, interleaved, padded) and alpha_int: out6 = d LML / d(l_df, l_cf, ratio, tvar, lt, noise).
 cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha_int,
                             const double* X, int N, const HelmParams& hp, int compat,
-                            double* partial, double* out4, cudaStream_t st);
+                            double* partial, double* out6, cudaStream_t st);
 int lml_grad_partials(int npad);
 // scalar ARD-RBF sum: out[Q (1 + D) + 1] = d LML / d(var_q, l_{q,0..D-1})_q, then d LML / d noise
 int rbf_lml_grad_partial_doubles(int npad);

@@ -121,14 +121,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
         if (!producer && FAM == FAM_HELM) {
             const int gj = gp0 + gjl;
             const bool gvalid = gj < p.M;
-            const double gx = gvalid ? p.Xs[2 * (long)gj] : 0.0;
-            const double gy = gvalid ? p.Xs[2 * (long)gj + 1] : 0.0;
+            const HelmPoint gpt = helm_point(p.hp, p.Xs, gvalid ? gj : 0);
             const int nobs_pad = p.npad >> 1;
-#pragma unroll 4
+#pragma unroll 2
             for (int o = os; o < nobs_pad; o += OS) {
                 double k11 = 0.0, k12 = 0.0, k22 = 0.0;
                 if (gvalid && o < p.N) {
-                    helm_block(p.hp, p.X[2 * (long)o] - gx, p.X[2 * (long)o + 1] - gy, k11, k12, k22);
+                    helm_block_pts(p.hp, helm_point(p.hp, p.X, o), gpt, k11, k12, k22);
                     const double a0 = p.alpha[2 * o], a1 = p.alpha[2 * o + 1];
                     mu0 = fma(k11, a0, fma(k12, a1, mu0));
                     mu1 = fma(k12, a0, fma(k22, a1, mu1));
@@ -360,7 +359,7 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
     PredictArgs a{};
     a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
-    a.kss = hp.w_df + hp.w_cf;           // ratio/l_df^2 + (1-ratio)/l_cf^2   (myKernel.py:55-57)
+    a.kss = hp.tvar * (hp.w_df + hp.w_cf);   // ratio/l_df^2 + (1-ratio)/l_cf^2 (myKernel.py:55-57), times the time variance
     a.var_add = var_add; a.mean = mean; a.var = var;
     return predict_launch<FAM_HELM>(a, scratch, scratch_bytes, st);
 }

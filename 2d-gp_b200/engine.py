@@ -12,7 +12,8 @@ import torch
 from ._lib import lib, check, Gp2dError
 
 __all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
-           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host", "rbf_K", "rbf_grad_sums", "ScalarGP"]
+           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host", "rbf_K", "rbf_grad_sums", "ScalarGP",
+           "st_K", "st_grad_sums", "SpaceTimeGP"]
 
 
 class LinAlgError(np.linalg.LinAlgError):
@@ -253,6 +254,133 @@ class HelmholtzGP:
             raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         self.lml = float(host[0])
         return self.lml, host[1:5].copy()
+
+
+# ------------------------------------------------------------------------------------------
+# space-time product kernel Kt(t) * Helmholtz(a, b)  (scratch.py:506-508; myKernel.py:337-363)
+# ------------------------------------------------------------------------------------------
+def _points3(X, device=None) -> torch.Tensor:
+    t = as_dev(X, device)
+    if t.dim() != 2 or t.shape[1] != 3:
+        raise ValueError("space-time points must be [N,3] rows (t, a, b)")
+    return t
+
+
+def st_K(X3, X3b, l_df, l_cf, ratio, tvar, lt, diag_add=0.0) -> torch.Tensor:
+    """[2N,2M] tvar exp(-dt^2/2lt^2) * Helmholtz block matrix (device tensor)."""
+    Xd = _points3(X3)
+    X2d = None if X3b is None else _points3(X3b, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    out = torch.empty((2 * N, 2 * M), dtype=torch.float64, device=Xd.device)
+    if N and M:
+        with torch.cuda.device(Xd.device):
+            check(lib.gp2d_st_kernel_build(_ptr(Xd), N, _ptr(X2d), M, l_df, l_cf, ratio, tvar, lt, diag_add, _ptr(out),
+                                           out.stride(0), _stream()), "gp2d_st_kernel_build")
+    return out
+
+
+def st_grad_sums(dL_dK, X3, X3b, l_df, l_cf, ratio, tvar, lt) -> torch.Tensor:
+    """sum(dK/dtheta * dL_dK) for theta = (l_df, l_cf, ratio, tvar, lt) -> device tensor[5]."""
+    Xd = _points3(X3)
+    X2d = None if X3b is None else _points3(X3b, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    W = as_dev(dL_dK, Xd.device)
+    if tuple(W.shape) != (2 * N, 2 * M):
+        raise ValueError("dL_dK must be [2N,2M]")
+    nb = lib.gp2d_kernel_grad_workspace_bytes(N, M)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    out = torch.empty(5, dtype=torch.float64, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        check(lib.gp2d_st_kernel_grad(_ptr(Xd), N, _ptr(X2d), M, l_df, l_cf, ratio, tvar, lt, _ptr(W), W.stride(0),
+                                      _ptr(ws), nb, _ptr(out), _stream()), "gp2d_st_kernel_grad")
+    return out
+
+
+class SpaceTimeGP:
+    """HelmholtzGP with the time factor: points [N,3] rows (t, a, b), y the stacked components."""
+
+    def __init__(self, X3, y, l_df, l_cf, ratio, tvar, lt, noise, jitter=0.0, device=None):
+        self.X = _points3(X3, device)
+        self.N = int(self.X.shape[0])
+        self.y = as_dev(y, self.X.device).reshape(-1)
+        if self.y.numel() != 2 * self.N:
+            raise ValueError("y must stack both components: length 2N")
+        self.set_params(l_df, l_cf, ratio, tvar, lt, noise)
+        self.jitter = float(jitter)
+        self.ws_bytes = lib.gp2d_st_fit_workspace_bytes(self.N)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.X.device)
+        self._scal = torch.zeros(8, dtype=torch.float64, device=self.X.device)
+        self._info = torch.zeros(1, dtype=torch.int32, device=self.X.device)
+        self._pws = None
+        self.lml = None
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def set_params(self, l_df, l_cf, ratio, tvar, lt, noise):
+        self.theta = tuple(float(v) for v in (l_df, l_cf, ratio, tvar, lt))
+        self.noise = float(noise)
+        self.fitted = False
+
+    def fit_async(self, alpha_out=None):
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_st_fit(_ptr(self.X), self.N, _ptr(self.y), *self.theta, self.noise, self.jitter, _ptr(self.ws),
+                                  self.ws_bytes, _ptr(alpha_out), _ptr(self._scal), _ptr(self._info), _stream()),
+                  "gp2d_st_fit")
+        self.fitted = True
+
+    def fit(self):
+        self.fit_async()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(self._scal[0].item())
+        return self.lml
+
+    def alpha(self) -> torch.Tensor:
+        out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
+        self.fit_async(alpha_out=out)
+        return out
+
+    def predict_state(self) -> torch.Tensor:
+        import ctypes as C
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(lib.gp2d_st_fit_predict_state(self.N, C.byref(off), C.byref(nb)), "gp2d_st_fit_predict_state")
+        return self.ws[off.value:off.value + nb.value]
+
+    def predict(self, Xs3, include_noise=False, out_mean=None, out_var=None):
+        if not self.fitted:
+            self.fit()
+        Xsd = _points3(Xs3, self.device)
+        M = int(Xsd.shape[0])
+        mean = out_mean if out_mean is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        var = out_var if out_var is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        if M:
+            with torch.cuda.device(self.device):
+                nb = lib.gp2d_predict_workspace_bytes(self.N, M)
+                if self._pws is None or self._pws.numel() < nb:
+                    self._pws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+                check(lib.gp2d_st_predict(_ptr(self.ws), self.N, *self.theta, _ptr(Xsd), M, M,
+                                          self.noise if include_noise else 0.0, _ptr(mean), _ptr(var), _ptr(self._pws),
+                                          self._pws.numel(), _stream()), "gp2d_st_predict")
+        return mean, var
+
+    def lml_and_grad(self):
+        """(LML, grad[6]) over (l_df, l_cf, ratio, tvar, lt, noise)."""
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_st_lml_grad(_ptr(self.X), self.N, _ptr(self.y), *self.theta, self.noise, self.jitter,
+                                       _ptr(self.ws), self.ws_bytes, _ptr(self._scal), _ptr(self._info), _stream()),
+                  "gp2d_st_lml_grad")
+        self.fitted = True
+        host = self._scal[:7].cpu().numpy()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(host[0])
+        return self.lml, host[1:7].copy()
 
 
 # ------------------------------------------------------------------------------------------

@@ -18,9 +18,9 @@ import pickle
 import numpy as np
 import scipy.optimize as sopt
 
-from .engine import HelmholtzGP, LinAlgError, ScalarGP
+from .engine import HelmholtzGP, LinAlgError, ScalarGP, SpaceTimeGP
 from .kern import RBF, Add, _ScalarKern
-from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase
+from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase, Kt, SpaceTimeKern
 from .params import Param
 
 GPY_JITTER = 1e-8       # GPy adds 1e-8 to the diagonal before factorising
@@ -39,10 +39,11 @@ class GPRegression:
         Y = np.asarray(Y, dtype=np.float64)
         if kernel is None:
             kernel = myKernel(2, [0, 1], 1.0, 1.0, 0.5)
-        if not isinstance(kernel, (_HelmholtzBase, _ScalarKern)):
-            raise TypeError("kernel must be myKernel / nonDivK / nonRotK or an RBF (sum)")
+        if not isinstance(kernel, (_HelmholtzBase, _ScalarKern, SpaceTimeKern)):
+            raise TypeError("kernel must be myKernel / nonDivK / nonRotK, Kt * one of them, or an RBF (sum)")
         self.kern = kernel
         self.scalar = isinstance(kernel, _ScalarKern)
+        self.spacetime = isinstance(kernel, SpaceTimeKern)
         self.Y = Y.reshape(-1, 1)
         self.Gaussian_noise = Param("Gaussian_noise.variance", noise_var).constrain_positive()
         self.likelihood = self
@@ -56,6 +57,13 @@ class GPRegression:
                 raise ValueError("Y must hold one observation per row of X: shape [N,1]")
             self._gp = ScalarGP(self.X, self.Y.reshape(-1), *self.kern.rbf_params(), float(self.Gaussian_noise),
                                 jitter=self.jitter, device=device)
+        elif self.spacetime:
+            # Kt(t) * Helmholtz(y, x): points (t, a, b), stacked components (scratch.py:495-510)
+            self.X = self.kern.points3(X)
+            if self.Y.shape[0] != 2 * self.X.shape[0]:
+                raise ValueError("Y must stack both velocity components: shape [2N,1]")
+            self._gp = SpaceTimeGP(self.X, self.Y.reshape(-1), *self.kern.theta5(), float(self.Gaussian_noise),
+                                   jitter=self.jitter, device=device)
         else:
             if reference_compat is not None:
                 self.kern.reference_compat = bool(reference_compat)
@@ -77,7 +85,7 @@ class GPRegression:
         return np.array([float(p) for p in self.parameters])
 
     def parameter_names(self):
-        if self.scalar:
+        if self.scalar or self.spacetime:
             return self.kern.parameter_names() + ["Gaussian_noise.variance"]
         return ["%s.%s" % (self.kern.name, p.name) for p in self.kern.parameters] + ["Gaussian_noise.variance"]
 
@@ -87,6 +95,8 @@ class GPRegression:
     def _sync(self):
         if self.scalar:
             self._gp.set_params(*self.kern.rbf_params(), float(self.Gaussian_noise))
+        elif self.spacetime:
+            self._gp.set_params(*self.kern.theta5(), float(self.Gaussian_noise))
         else:
             self._gp.set_params(*self.kern._theta(), float(self.Gaussian_noise))
 
@@ -109,6 +119,16 @@ class GPRegression:
                 self._ll, g = self._gp.lml_and_grad()
                 self.kern._scatter_gradient(g[:-1])
                 self.Gaussian_noise.gradient = float(g[-1])
+            except LinAlgError:
+                self._ll = -np.inf
+                for p in self.parameters:
+                    p.gradient = 0.0
+            return self._ll
+        if self.spacetime:
+            try:
+                self._ll, g = self._gp.lml_and_grad()
+                self.kern.scatter_gradient(g[:5])
+                self.Gaussian_noise.gradient = float(g[5])
             except LinAlgError:
                 self._ll = -np.inf
                 for p in self.parameters:
@@ -253,6 +273,8 @@ class GPRegression:
         Xnew = np.asarray(Xnew, dtype=np.float64)
         if self.scalar:
             Xnew = self.kern._slice(Xnew)
+        elif self.spacetime:
+            Xnew = self.kern.points3(Xnew)
         elif Xnew.shape[1] != 2:
             Xnew = Xnew[:, self.kern.active_dims]
         if not self._gp.fitted:
@@ -264,13 +286,16 @@ class GPRegression:
     # ---- persistence (krig.py:412,438,452) -----------------------------------------------------
     def _state(self):
         k = self.kern
-        st = {"kernel": type(k).__name__, "active_dims": k.active_dims, "params": self.param_array,
+        st = {"kernel": type(k).__name__, "active_dims": getattr(k, "active_dims", None), "params": self.param_array,
               "constraints": [p.constraint for p in self.parameters],
               "X": self.X, "Y": self.Y, "jitter": self.jitter,
               "runs": [r.__dict__ for r in self.optimization_runs]}
         if self.scalar:
             st["parts"] = [{"input_dim": p.input_dim, "ARD": p.ARD, "name": p.name} for p in k.parts_list()]
             st["active_dims"] = list(range(self.X.shape[1]))      # X is stored already sliced
+        elif self.spacetime:
+            st["space"] = type(k.kxy).__name__                    # X is stored as (t, a, b)
+            st["active_dims"] = [0, 1, 2]
         else:
             st["reference_compat"] = k.reference_compat
         return st
@@ -290,6 +315,18 @@ def load(path, device=None):
         st = pickle.load(f)
     p = st["params"]
     name = st["kernel"]
+    if "space" in st:
+        kxy = {"myKernel": lambda: myKernel(2, [1, 2], p[2], p[3], p[4]), "nonDivK": lambda: nonDivK(2, [1, 2], p[2]),
+               "nonRotK": lambda: nonRotK(2, [1, 2], p[2])}[st["space"]]()
+        k = Kt(1, [0], p[0], p[1]) * kxy
+        m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
+        for prm, c in zip(m.parameters, st["constraints"]):
+            prm.constraint = c
+        for d in st["runs"]:
+            r = _Run(None, None, None, None)
+            r.__dict__.update(d)
+            m.optimization_runs.append(r)
+        return m
     if "parts" in st:
         parts, o = [], 0
         for d in st["parts"]:

@@ -78,6 +78,11 @@ class _HelmholtzBase:
         import copy
         return copy.deepcopy(self)
 
+    def __mul__(self, other):
+        if isinstance(other, Kt):
+            return SpaceTimeKern(other, self)
+        return NotImplemented
+
 
 class myKernel(_HelmholtzBase):
     """myKernel.myKernel (myKernel.py:12-146)."""
@@ -129,3 +134,109 @@ class nonRotK(_HelmholtzBase):
 
     def update_gradients_full(self, dL_dK, X, X2=None):
         self.length.gradient = float(self._grad_sums(dL_dK, X, X2)[1])
+
+
+class Kt:
+    """Time kernel of myKernel.Kt (myKernel.py:337-391): var * exp(-dt^2 / 2 lengthscale^2) tiled
+    over the 2x2 velocity blocks.  Used as ``Kt(...) * nonDivK(...)`` (scratch.py:506-508).  The
+    reference's gradient method is a stub (myKernel.py:365-372); here it is the derivative."""
+
+    def __init__(self, input_dim=1, active_dims=[0], var=1, lengthscale=1.):
+        assert input_dim == 1, "For this kernel we assume input_dim=1"          # myKernel.py:340
+        self.input_dim, self.active_dims, self.name = 1, list(active_dims), "Kt"
+        self.var = Param("var", var).constrain_positive()
+        self.lengthscale = Param("lengthscale", lengthscale).constrain_positive()
+        self.parameters = [self.var, self.lengthscale]
+
+    def parameters_changed(self):
+        pass
+
+    def _t(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        return X[:, self.active_dims] if X.shape[1] != 1 else X
+
+    def K(self, X, X2=None):
+        C = engine.rbf_K(self._t(X), None if X2 is None else self._t(X2), [float(self.var)], [[float(self.lengthscale)]])
+        return C.repeat(2, 2).cpu().numpy()                                   # [[C, C], [C, C]]  (myKernel.py:357-358)
+
+    def Kdiag(self, X):
+        return np.ones(np.shape(X)[0] * np.shape(X)[1] * 2) * float(self.var)     # myKernel.py:362-363
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        W = np.asarray(dL_dK, dtype=np.float64)
+        n, m = W.shape[0] // 2, W.shape[1] // 2
+        Wf = W[:n, :m] + W[:n, m:] + W[n:, :m] + W[n:, m:]
+        g = engine.rbf_grad_sums(Wf, self._t(X), None if X2 is None else self._t(X2), [float(self.var)],
+                                 [[float(self.lengthscale)]]).cpu().numpy()
+        self.var.gradient, self.lengthscale.gradient = float(g[0]), float(g[1])
+
+    def update_gradients_diag(self, dL_dKdiag, X):
+        pass
+
+    def gradients_X_diag(self, dL_dKdiag, X):
+        pass
+
+    def copy(self):
+        import copy
+        return copy.deepcopy(self)
+
+    def __mul__(self, other):
+        if isinstance(other, _HelmholtzBase):
+            return SpaceTimeKern(self, other)
+        return NotImplemented
+
+
+class SpaceTimeKern:
+    """``Kt(t) * <Helmholtz kernel>(a, b)``: GPy's product of kernels acting on different columns
+    (scratch.py:506-508).  Parameters in GPy's order: the time part first, then the space part."""
+
+    family = "spacetime"
+
+    def __init__(self, kt, kxy):
+        self.kt, self.kxy = kt.copy(), kxy.copy()
+        self.name = "mul"
+
+    @property
+    def parameters(self):
+        return list(self.kt.parameters) + list(self.kxy.parameters)
+
+    @property
+    def param_array(self):
+        return np.array([float(p) for p in self.parameters])
+
+    def parameter_names(self):
+        return ["mul.Kt." + p.name for p in self.kt.parameters] + \
+               ["mul.%s.%s" % (self.kxy.name, p.name) for p in self.kxy.parameters]
+
+    def theta5(self):
+        """(l_df, l_cf, ratio, tvar, lt)."""
+        return tuple(self.kxy._theta()) + (float(self.kt.var), float(self.kt.lengthscale))
+
+    def points3(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        return np.ascontiguousarray(X[:, list(self.kt.active_dims) + list(self.kxy.active_dims)])
+
+    def K(self, X, X2=None):
+        return engine.st_K(self.points3(X), None if X2 is None else self.points3(X2), *self.theta5()).cpu().numpy()
+
+    def Kdiag(self, X):
+        l_df, l_cf, ratio, tvar, _ = self.theta5()
+        return np.full(2 * np.shape(X)[0], tvar * (ratio / l_df ** 2 + (1 - ratio) / l_cf ** 2))
+
+    def scatter_gradient(self, g5):
+        """g5 ordered (l_df, l_cf, ratio, tvar, lt), the engine's order."""
+        self.kt.var.gradient, self.kt.lengthscale.gradient = float(g5[3]), float(g5[4])
+        if isinstance(self.kxy, myKernel):
+            self.kxy.length_df.gradient, self.kxy.length_cf.gradient, self.kxy.ratio.gradient = map(float, g5[:3])
+        elif isinstance(self.kxy, nonDivK):
+            self.kxy.length.gradient = float(g5[0])
+        else:
+            self.kxy.length.gradient = float(g5[1])
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        g = engine.st_grad_sums(dL_dK, self.points3(X), None if X2 is None else self.points3(X2), *self.theta5())
+        self.scatter_gradient(g.cpu().numpy())
+
+    def copy(self):
+        import copy
+        return copy.deepcopy(self)

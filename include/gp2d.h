@@ -125,6 +125,31 @@ int gp2d_lml_grad(const double* X, int N, const double* y,
                   int reference_compat, void* ws, size_t ws_bytes, double* out5, int* info,
                   void* stream);
 
+/* ---- space-time product kernel ---------------------------------------------------------------
+ * K = tvar * exp(-dt^2 / (2 lt^2)) * Helmholtz(l_df, l_cf, ratio)(a - a', b - b'): the product
+ * Kt(t) * nonDivK(y, x) of scratch.py:506-508 with Kt of myKernel.py:337-363 (an RBF in time tiled
+ * over the 2x2 blocks), generalised to the combined Helmholtz kernel.  Points are [N,3] row-major
+ * (t, a, b); everything else (block layout, stacked observations, workspaces, return codes) is as
+ * in the functions above.  gp2d_st_kernel_grad: out5 = sums for (l_df, l_cf, ratio, tvar, lt).
+ * gp2d_st_lml_grad: out7 = (LML, d/dl_df, d/dl_cf, d/dratio, d/dtvar, d/dlt, d/dnoise).
+ * gp2d_kernel_grad_workspace_bytes and gp2d_predict_workspace_bytes size the scratch here too. */
+int gp2d_st_kernel_build(const double* X3, int N, const double* X3b, int M, double l_df, double l_cf, double ratio,
+                         double tvar, double lt, double diag_add, double* K, int64_t ldk, void* stream);
+int gp2d_st_kernel_grad(const double* X3, int N, const double* X3b, int M, double l_df, double l_cf, double ratio,
+                        double tvar, double lt, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                        double* out5, void* stream);
+size_t gp2d_st_fit_workspace_bytes(int N);
+int gp2d_st_fit_predict_state(int N, size_t* offset, size_t* bytes);
+int gp2d_st_fit(const double* X3, int N, const double* y, double l_df, double l_cf, double ratio, double tvar,
+                double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
+                double* lml_out, int* info, void* stream);
+int gp2d_st_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, double tvar, double lt,
+                    const double* Xs3, int M, int64_t out_stride, double var_add, double* mean, double* var,
+                    void* ws, size_t ws_bytes, void* stream);
+int gp2d_st_lml_grad(const double* X3, int N, const double* y, double l_df, double l_cf, double ratio, double tvar,
+                     double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* out7, int* info,
+                     void* stream);
+
 /* ---- scalar ARD-RBF sum family --------------------------------------------------------------
  * k(x,x') = sum_{q<Q} var[q] exp(-1/2 sum_{d<D} ((x_d - x'_d) / ls[q*D+d])^2), D <= 4, Q <= 4,
  * scalar observations y[N].  var[Q] and ls[Q*D] are HOST arrays (read before the call returns);

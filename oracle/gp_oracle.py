@@ -23,6 +23,7 @@ __all__ = [
     "helmholtz_K", "helmholtz_Kdiag", "helmholtz_dK", "kernel_grad_sums",
     "fit", "predict", "lml", "lml_and_grad", "fit_predict_inverse_form",
     "haversine_km", "simlaser_inputs", "rbf_ard_K", "LOG_2PI",
+    "kt_K", "st_K", "st_dK", "st_fit", "st_predict", "st_lml_and_grad",
     "rbf_sum_K", "rbf_sum_dK", "rbf_kernel_grad_sums", "rbf_fit", "rbf_predict", "rbf_lml_and_grad",
 ]
 
@@ -228,6 +229,69 @@ def fit_predict_inverse_form(X, y, l_df, l_cf, ratio, noise, Xs, ks_cf_weight=No
     kss = helmholtz_Kdiag(1, l_df, l_cf, ratio)[0]
     var = kss - np.einsum("ij,ij->i", Ks @ Ki, Ks)
     return mean, var
+
+
+# --------------------------------------------------------------------------------------
+# space-time product kernel.  Kt.K (myKernel.py:350-360) is a time RBF
+# var*exp(-dt^2/2l^2) tiled over the 2x2 blocks; scratch.coKriging multiplies it with the
+# divergence-free kernel of (y, x) (scratch.py:506-508: k = kt * kxy, GPy's Prod = elementwise
+# product).  The reference code path is dead upstream (ctor keyword mismatch), so this part of the
+# oracle restates the formulas only: "parity unpinned".
+# --------------------------------------------------------------------------------------
+def kt_K(t, t2, var, lengthscale):
+    """Kt.K: [[C, C], [C, C]] with C the 1-D RBF of the times (myKernel.py:350-360)."""
+    t = np.asarray(t, dtype=np.float64).reshape(-1, 1)
+    t2 = t if t2 is None else np.asarray(t2, dtype=np.float64).reshape(-1, 1)
+    C = rbf_ard_K(t, t2, var, [lengthscale])
+    return _blk(C, C, C, C)
+
+
+def st_K(X3, X3b, l_df, l_cf, ratio, tvar, lt):
+    """Kt(t) * Helmholtz(a, b) for points [N,3] rows (t, a, b), block layout [2N,2M]."""
+    X3 = np.asarray(X3, dtype=np.float64)
+    X3b = X3 if X3b is None else np.asarray(X3b, dtype=np.float64)
+    return kt_K(X3[:, 0], X3b[:, 0], tvar, lt) * helmholtz_K(X3[:, 1:3], X3b[:, 1:3], l_df, l_cf, ratio)
+
+
+def st_dK(X3, X3b, l_df, l_cf, ratio, tvar, lt):
+    """dK/d(l_df, l_cf, ratio, tvar, lt) by the product rule (analytic spatial derivatives)."""
+    X3 = np.asarray(X3, dtype=np.float64)
+    X3b = X3 if X3b is None else np.asarray(X3b, dtype=np.float64)
+    T = kt_K(X3[:, 0], X3b[:, 0], tvar, lt)
+    H = helmholtz_K(X3[:, 1:3], X3b[:, 1:3], l_df, l_cf, ratio)
+    dH = helmholtz_dK(X3[:, 1:3], X3b[:, 1:3], l_df, l_cf, ratio)
+    dt = X3[:, 0][:, None] - X3b[:, 0][None, :]
+    dt2 = _blk(dt * dt, dt * dt, dt * dt, dt * dt)
+    return [T * dH[0], T * dH[1], T * dH[2], T * H / tvar, T * H * dt2 / lt ** 3]
+
+
+def st_fit(X3, y, l_df, l_cf, ratio, tvar, lt, noise, jitter=0.0):
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = st_K(X3, None, l_df, l_cf, ratio, tvar, lt)
+    n = K.shape[0]
+    K[np.diag_indices(n)] += noise + jitter
+    L = sla.cholesky(K, lower=True, check_finite=False)
+    alpha = sla.cho_solve((L, True), y, check_finite=False)
+    val = -0.5 * float(y @ alpha) - float(np.sum(np.log(np.diag(L)))) - 0.5 * n * LOG_2PI
+    return {"L": L, "alpha": alpha, "lml": val}
+
+
+def st_predict(X3, fitres, l_df, l_cf, ratio, tvar, lt, Xs3, var_add=0.0):
+    Xs3 = np.asarray(Xs3, dtype=np.float64)
+    Ks = st_K(Xs3, X3, l_df, l_cf, ratio, tvar, lt)
+    mean = Ks @ fitres["alpha"]
+    V = sla.solve_triangular(fitres["L"], Ks.T, lower=True, check_finite=False)
+    var = tvar * helmholtz_Kdiag(1, l_df, l_cf, ratio)[0] - np.einsum("ij,ij->j", V, V)
+    return mean, np.where(var < 0.0, 0.0, var) + var_add
+
+
+def st_lml_and_grad(X3, y, l_df, l_cf, ratio, tvar, lt, noise, jitter=0.0):
+    f = st_fit(X3, y, l_df, l_cf, ratio, tvar, lt, noise, jitter)
+    n = f["L"].shape[0]
+    Kinv = sla.cho_solve((f["L"], True), np.eye(n), check_finite=False)
+    W = 0.5 * (np.outer(f["alpha"], f["alpha"]) - Kinv)
+    g = [np.sum(d * W) for d in st_dK(X3, None, l_df, l_cf, ratio, tvar, lt)]
+    return f["lml"], np.array(g + [np.trace(W)])
 
 
 # --------------------------------------------------------------------------------------

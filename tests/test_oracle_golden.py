@@ -197,3 +197,31 @@ def test_rbf_kernel_gradient_matches_central_differences(golden_dir):
         return np.sum(orc.rbf_sum_K(X, X2, [th[0], th[4]], [th[1:4], th[5:8]]) * W)
     fd = np.array([(f(theta + 1e-6 * e) - f(theta - 1e-6 * e)) / 2e-6 for e in np.eye(8)])
     np.testing.assert_allclose(got, fd, rtol=1e-6, atol=1e-8)
+
+
+# ---- space-time product kernel (formula restatement; the upstream path is dead code) --------------
+def test_spacetime_oracle_consistency():
+    rng = np.random.default_rng(5)
+    X3 = np.stack([rng.uniform(0, 6, 12), rng.uniform(0, 10, 12), rng.uniform(0, 10, 12)], axis=1)
+    Xs3 = np.stack([rng.uniform(0, 6, 7), rng.uniform(0, 10, 7), rng.uniform(0, 10, 7)], axis=1)
+    W = rng.normal(size=(24, 14))
+    theta = np.array([1.3, 3.1, 0.2, 0.7, 2.5])
+    go = np.array([np.sum(d * W) for d in orc.st_dK(X3, Xs3, *theta)])
+    f = lambda th: np.sum(orc.st_K(X3, Xs3, *th) * W)
+    fd = np.array([(f(theta + 1e-6 * e) - f(theta - 1e-6 * e)) / 2e-6 for e in np.eye(5)])
+    np.testing.assert_allclose(go, fd, rtol=1e-7, atol=1e-8)
+    # Kt.K is the time RBF tiled 2x2 (myKernel.py:357-358); the product is elementwise (GPy Prod)
+    C = orc.rbf_ard_K(X3[:, :1], Xs3[:, :1], 0.7, [2.5])
+    np.testing.assert_array_equal(orc.kt_K(X3[:, 0], Xs3[:, 0], 0.7, 2.5), np.tile(C, (2, 2)))
+    np.testing.assert_array_equal(orc.st_K(X3, Xs3, *theta), np.tile(C, (2, 2)) * orc.helmholtz_K(X3[:, 1:], Xs3[:, 1:], 1.3, 3.1, 0.2))
+    # equal times, unit variance: exactly the pinned Helmholtz kernel
+    X0 = X3.copy()
+    X0[:, 0] = 1.0
+    np.testing.assert_array_equal(orc.st_K(X0, None, 1.3, 3.1, 0.2, 1.0, 9.0), orc.helmholtz_K(X0[:, 1:], None, 1.3, 3.1, 0.2))
+    y = rng.normal(size=24)
+    lo, g = orc.st_lml_and_grad(X3, y, *theta, 0.1)
+    h = 1e-6
+    for i in range(5):
+        e = np.zeros(5); e[i] = h
+        fdl = (orc.st_fit(X3, y, *(theta + e), 0.1)["lml"] - orc.st_fit(X3, y, *(theta - e), 0.1)["lml"]) / (2 * h)
+        assert abs(g[i] - fdl) <= 1e-5 * max(1.0, abs(fdl))
