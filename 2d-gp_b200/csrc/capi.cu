@@ -63,6 +63,11 @@ inline T* at(void* base, size_t off) { return reinterpret_cast<T*>(reinterpret_c
 template <class T>
 inline const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + off); }
 
+// the predictive kernel lists at most 1024 row blocks of 128 (and two n x n fp64 matrices of that
+// size are already beyond one GPU's memory)
+constexpr int MAX_NPAD = 131072;
+bool size_ok(long n_scalar) { return n_scalar > 0 && n_scalar <= MAX_NPAD; }
+
 bool theta_ok(double l_df, double l_cf, double ratio) {
     return l_df > 0.0 && l_cf > 0.0 && ratio >= 0.0 && ratio <= 1.0 && isfinite(l_df) && isfinite(l_cf);
 }
@@ -289,7 +294,7 @@ int gp2d_dgemm(int transa, int transb, int M, int N, int K, double alpha, const 
 }
 
 size_t gp2d_fit_workspace_bytes(int N) {
-    if (N <= 0) return 0;
+    if (!size_ok(2L * N)) return 0;
     return fit_layout(N).total;
 }
 
@@ -307,7 +312,7 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
              double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
              double* lml_out, int* info, void* stream) {
     if (!X) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!y) return -3;
     if (!theta_ok(l_df, l_cf, ratio)) return -4;
     if (!(noise >= 0.0)) return -7;
@@ -342,7 +347,7 @@ int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double rat
                  int M, int64_t out_stride, double var_add, double* mean, double* var, void* ws,
                  size_t ws_bytes, void* stream) {
     if (!fit_ws) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!theta_ok(l_df, l_cf, ratio)) return -3;
     if (M < 0) return -7;
     if (M == 0) return 0;
@@ -363,7 +368,7 @@ int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l
                   double noise, double jitter, int reference_compat, void* ws, size_t ws_bytes,
                   double* out5, int* info, void* stream) {
     if (!X) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!y) return -3;
     if (!theta_ok(l_df, l_cf, ratio)) return -4;
     if (!(noise >= 0.0)) return -7;
@@ -434,7 +439,7 @@ int gp2d_st_kernel_grad(const double* X3, int N, const double* X3b, int M, doubl
 }
 
 size_t gp2d_st_fit_workspace_bytes(int N) {
-    if (N <= 0) return 0;
+    if (!size_ok(2L * N)) return 0;
     return fit_layout(N, 3).total;
 }
 
@@ -452,7 +457,7 @@ int gp2d_st_fit(const double* X3, int N, const double* y, double l_df, double l_
                 double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
                 double* lml_out, int* info, void* stream) {
     if (!X3) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!y) return -3;
     if (!theta_ok(l_df, l_cf, ratio)) return -4;
     if (!st_ok(tvar, lt)) return -7;
@@ -483,7 +488,7 @@ int gp2d_st_predict(const void* fit_ws, int N, double l_df, double l_cf, double 
                     const double* Xs3, int M, int64_t out_stride, double var_add, double* mean, double* var,
                     void* ws, size_t ws_bytes, void* stream) {
     if (!fit_ws) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!theta_ok(l_df, l_cf, ratio)) return -3;
     if (!st_ok(tvar, lt)) return -6;
     if (M < 0) return -9;
@@ -504,7 +509,7 @@ int gp2d_st_lml_grad(const double* X3, int N, const double* y, double l_df, doub
                      double lt, double noise, double jitter, void* ws, size_t ws_bytes, double* out7, int* info,
                      void* stream) {
     if (!X3) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!y) return -3;
     if (!theta_ok(l_df, l_cf, ratio)) return -4;
     if (!st_ok(tvar, lt)) return -7;
@@ -592,7 +597,7 @@ int gp2d_rbf_kernel_grad(const double* X, int N, const double* X2, int M, int D,
 }
 
 size_t gp2d_rbf_fit_workspace_bytes(int N, int D) {
-    if (N <= 0 || D < 1 || D > RBF_MAXD) return 0;
+    if (!size_ok(N) || D < 1 || D > RBF_MAXD) return 0;
     return rbf_layout(N, D).total;
 }
 
@@ -611,7 +616,7 @@ int gp2d_rbf_fit(const double* X, int N, int D, const double* y, int Q, const do
                  double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out, double* lml_out,
                  int* info, void* stream) {
     if (!X) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(N)) return -2;
     if (!y) return -4;
     RbfParams rp;
     if (!make_rbf(D, Q, var, ls, &rp)) return -5;
@@ -647,7 +652,7 @@ int gp2d_rbf_predict(const void* fit_ws, int N, int D, int Q, const double* var,
                      const double* Xs, int M, double var_add, double* mean, double* variance, void* ws,
                      size_t ws_bytes, void* stream) {
     if (!fit_ws) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(N)) return -2;
     RbfParams rp;
     if (!make_rbf(D, Q, var, ls, &rp)) return -3;
     if (M < 0) return -8;
@@ -666,7 +671,7 @@ int gp2d_rbf_predict(const void* fit_ws, int N, int D, int Q, const double* var,
 int gp2d_rbf_lml_grad(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
                       double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream) {
     if (!X) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(N)) return -2;
     if (!y) return -4;
     RbfParams rp;
     if (!make_rbf(D, Q, var, ls, &rp)) return -5;
@@ -700,7 +705,7 @@ int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, 
                           double ratio, double noise, double jitter, const double* Xs, int M,
                           int include_noise, double* mean, double* var, double* lml) {
     if (!X) return -1;
-    if (N <= 0) return -2;
+    if (!size_ok(2L * N)) return -2;
     if (!y) return -3;
     if (!theta_ok(l_df, l_cf, ratio)) return -4;
     if (M < 0) return -10;

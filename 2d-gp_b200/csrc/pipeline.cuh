@@ -151,6 +151,29 @@ __device__ __forceinline__ void ws_mma_kgroup(const double* As, const double* Bs
         for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
 }
 
+// same, but only the first 4 row blocks (32 rows) of the warp tile: the ragged last row block
+template <bool A_MN, bool B_MN, int Q>
+__device__ __forceinline__ void ws_mma_kgroup_half(const double* As, const double* Bs, const FragLane<A_MN, 64>& fa,
+                                                   const FragLane<B_MN, 32>& fb, double (&acc)[8][4][2]) {
+    double a[4], b[4];
+    a[0] = fa.template ld<Q, 0>(As); a[1] = fa.template ld<Q, 1>(As);
+    a[2] = fa.template ld<Q, 2>(As); a[3] = fa.template ld<Q, 3>(As);
+    b[0] = fb.template ld<Q, 0>(Bs); b[1] = fb.template ld<Q, 1>(Bs);
+    b[2] = fb.template ld<Q, 2>(Bs); b[3] = fb.template ld<Q, 3>(Bs);
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+}
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void ws_mma_stage_half(const double* As, const double* Bs, const FragLane<A_MN, 64>& fa,
+                                                  const FragLane<B_MN, 32>& fb, double (&acc)[8][4][2]) {
+    ws_mma_kgroup_half<A_MN, B_MN, 0>(As, Bs, fa, fb, acc);
+    ws_mma_kgroup_half<A_MN, B_MN, 1>(As, Bs, fa, fb, acc);
+    ws_mma_kgroup_half<A_MN, B_MN, 2>(As, Bs, fa, fb, acc);
+    ws_mma_kgroup_half<A_MN, B_MN, 3>(As, Bs, fa, fb, acc);
+}
+
 // one 128 x 128 x 16 stage: 128 DMMAs per warp
 template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void ws_mma_stage(const double* As, const double* Bs, const FragLane<A_MN, 64>& fa,

@@ -53,11 +53,43 @@ constexpr int PRED_MAX_ROWBLOCKS = 1024;          // npad <= 131072
 constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_ROWBLOCKS / 2;
 constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
+// Phase 1 of the scalar family, out of line: its register needs (two grid points x RBF_MAXD
+// coordinates, the component loop) must not push the accumulator loop into spilling.
+// Thread (gjl, os): grid points gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel row),
+// observations os, os + 4, ...
+__device__ __noinline__ void rbf_phase1(const PredictArgs& p, double* __restrict__ panel, int gp0, int gjl, int os,
+                                        double& mu0, double& mu1) {
+    constexpr int OS = WS_CONSUMERS / 64;
+    const int gj = gp0 + 2 * gjl;
+    const bool v0 = gj < p.M, v1 = gj + 1 < p.M;
+    double b0[RBF_MAXD], b1[RBF_MAXD];
+    rbf_load_point(p.Xs, v0 ? gj : 0, p.rp.D, b0);
+    rbf_load_point(p.Xs, v1 ? gj + 1 : 0, p.rp.D, b1);
+    double m0 = 0.0, m1 = 0.0;
+#pragma unroll 4
+    for (int o = os; o < p.npad; o += OS) {
+        double k0 = 0.0, k1 = 0.0;
+        if (o < p.N) {
+            double a[RBF_MAXD];
+            rbf_load_point(p.X, o, p.rp.D, a);
+            if (v0) k0 = rbf_eval(p.rp, a, b0);
+            if (v1) k1 = rbf_eval(p.rp, a, b1);
+            const double al = p.alpha[o];
+            m0 = fma(k0, al, m0);
+            m1 = fma(k1, al, m1);
+        }
+        *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
+    }
+    fence_proxy_async();
+    mu0 = m0;
+    mu1 = m1;
+}
+
 // 8 consumer warps (phase 1 + DMMA) and one producer warp (bulk-copy ring), see pipeline.cuh.
 // FAM selects the covariance family of phase 1: the matrix-valued Helmholtz kernel (a column tile
 // is 64 grid points x 2 components) or the scalar ARD-RBF sum (a column tile is 128 grid points).
 template <int FAM>
-__global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
+__global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_constant__ PredictArgs p) {
     constexpr int PTS = FAM == FAM_HELM ? 64 : 128;      // grid points per column tile
     constexpr int WM = 2, OS = WS_CONSUMERS / 64;
     extern __shared__ __align__(16) double smem[];
@@ -94,30 +126,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
         const int gp0 = ct * PTS;
         // ---------------- phase 1 (consumer warps): K* panel + mean ------------------------
         double mu0 = 0.0, mu1 = 0.0;
-        if (!producer && FAM == FAM_RBF) {
-            // thread (gjl, os): grid points gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel
-            // row), observations os, os + 4, ...
-            const int gj = gp0 + 2 * gjl;
-            const bool v0 = gj < p.M, v1 = gj + 1 < p.M;
-            double b0[RBF_MAXD], b1[RBF_MAXD];
-            rbf_load_point(p.Xs, v0 ? gj : 0, p.rp.D, b0);
-            rbf_load_point(p.Xs, v1 ? gj + 1 : 0, p.rp.D, b1);
-#pragma unroll 2
-            for (int o = os; o < p.npad; o += OS) {
-                double k0 = 0.0, k1 = 0.0;
-                if (o < p.N) {
-                    double a[RBF_MAXD];
-                    rbf_load_point(p.X, o, p.rp.D, a);
-                    if (v0) k0 = rbf_eval(p.rp, a, b0);
-                    if (v1) k1 = rbf_eval(p.rp, a, b1);
-                    const double al = p.alpha[o];
-                    mu0 = fma(k0, al, mu0);
-                    mu1 = fma(k1, al, mu1);
-                }
-                *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
-            }
-            fence_proxy_async();
-        }
+        if (!producer && FAM == FAM_RBF) rbf_phase1(p, panel, gp0, gjl, os, mu0, mu1);
         if (!producer && FAM == FAM_HELM) {
             const int gj = gp0 + gjl;
             const bool gvalid = gj < p.M;
@@ -201,6 +210,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
                         const int li = sh_rb[q] & 0xffff, g = sh_rb[q] >> 16;
                         const int nkt = 8 * (li + 1);
                         const int row0 = li * TILE + wm * 64;
+                        // rows 32..63 of this warp tile are padding (Helmholtz instantiation only: the RBF one
+                        // has no registers to spare for the second code path)
+                        const bool half = FAM == FAM_HELM && nvalid - row0 <= 32;
                         for (int ckt = 0; ckt < nkt; ++ckt) {
                             mbar_wait(wb.full + rs, rph);
                             const double* st = smem + rs * WS_STAGE_DOUBLES;
@@ -208,7 +220,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(PredictArgs p) {
                             // right of the diagonal (upper half of a diagonal block) and contribute nothing
                             // when they are identity padding (the matching panel rows are zero)
                             const bool skip = (ckt * BK > row0 + 63) || (row0 >= nvalid);
-                            if (!skip) ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                            if (!skip) {
+                                if (half) ws_mma_stage_half<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                                else ws_mma_stage<false, true>(st, st + TILE_DOUBLES, fa, fb, acc);
+                            }
                             __syncwarp();
                             if (lane == 0) mbar_arrive(wb.empty + rs);
                             if (++rs == WS_STAGES) { rs = 0; rph ^= 1u; }
@@ -293,15 +308,20 @@ int predict_max_ctas() {
     return sms;
 }
 
-// Split of the row blocks of one column tile over CTAs: the smallest nsplit in {1,2,4,8} whose
-// number of rounds ceil(ntiles nsplit / SMs) / nsplit is within 3 % of the best.
-int predict_choose_split(long ntiles) {
+// Split of the row blocks of one column tile over CTAs.  An item costs its share of the DMMA work
+// plus a full phase 1 (every CTA of a split tile generates the whole panel), so the time is
+// ~ ceil(ntiles nsplit / SMs) * (1 / nsplit + phi) with phi = phase 1 / DMMA time of a whole tile
+// (measured: ~3 % at npad = 4096 for the Helmholtz block generator, ~4x that for the scalar
+// family, which needs one exponential per entry; both scale as 1 / npad).  The smallest nsplit in
+// {1,2,4,8} within 3 % of the best estimate is taken.
+int predict_choose_split(long ntiles, int npad, int fam) {
     const long sms = predict_max_ctas();
+    const double phi = (fam == FAM_HELM ? 123.0 : 500.0) / (double)npad;
     double best = 1e300;
     double r[4];
     for (int i = 0; i < 4; ++i) {
         const long s = 1L << i;
-        r[i] = (double)((ntiles * s + sms - 1) / sms) / (double)s;
+        r[i] = (double)((ntiles * s + sms - 1) / sms) * (1.0 / (double)s + phi);
         if (r[i] < best) best = r[i];
     }
     for (int i = 0; i < 4; ++i)
@@ -313,7 +333,7 @@ size_t predict_partial_bytes(long ntiles) { return (size_t)ntiles * PRED_GROUPS 
 
 size_t predict_scratch_bytes(int npad, int M, int pts_per_tile) {
     const long ntiles = ((long)M + pts_per_tile - 1) / pts_per_tile;
-    const int ns = predict_choose_split(ntiles);
+    const int ns = predict_choose_split(ntiles, npad, pts_per_tile == 64 ? FAM_HELM : FAM_RBF);
     long ctas = predict_max_ctas();
     if (ntiles * ns < ctas) ctas = ntiles * ns;
     return (size_t)ctas * predict_panel_bytes(npad) + (ns > 1 ? predict_partial_bytes(ntiles) : 0);
@@ -331,7 +351,7 @@ static cudaError_t predict_launch(PredictArgs& a, double* scratch, size_t scratc
     a.ntiles = (a.M + PTS - 1) / PTS;
     // scratch = [partial sums (nsplit > 1)] [one K* panel per CTA]; a buffer too small for the
     // partials falls back to nsplit = 1, fewer panels only shrink the grid
-    a.nsplit = predict_choose_split(a.ntiles);
+    a.nsplit = predict_choose_split(a.ntiles, a.npad, FAM);
     size_t pb = predict_partial_bytes(a.ntiles);
     if (a.nsplit > 1 && scratch_bytes < pb + predict_panel_bytes(a.npad)) a.nsplit = 1;
     if (a.nsplit == 1) pb = 0;

@@ -351,6 +351,12 @@ def test_bad_arguments():
     assert lib.gp2d_kernel_build(X.data_ptr(), 4, None, 4, 1.0, 1.0, 0.5, 0.0, out.data_ptr(), 7, None) == -10
     assert lib.gp2d_fit(X.data_ptr(), 4, out.data_ptr(), 1.0, 1.0, 0.5, 0.1, 0.0, out.data_ptr(), 16, None, None,
                         None, None) == -10
+    # sizes beyond what one GPU can factorise are refused, not attempted
+    assert lib.gp2d_fit_workspace_bytes(70000) == 0
+    assert lib.gp2d_fit(X.data_ptr(), 70000, out.data_ptr(), 1.0, 1.0, 0.5, 0.1, 0.0, out.data_ptr(), 16, None, None,
+                        None, None) == -2
+    assert lib.gp2d_error_string(-2).decode() == "invalid argument 2"
+    assert b"CUDA error" in lib.gp2d_error_string(-1001)
 
 
 # ---- full-size configuration: size-independent properties + sampled oracle -------------------

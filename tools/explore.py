@@ -125,6 +125,23 @@ def gemm():
     lib.gp2d_dbg_set_cta_threads(256)
 
 
+def rbf():
+    """Scalar ARD-RBF path (krig.scikit_prior shape: (t, y, x) inputs, two components)."""
+    rng = np.random.default_rng(1)
+    for N, M in ((4000, 102400), (16384, 20000)):
+        X = np.stack([rng.uniform(0, 24, N), rng.uniform(0, 40, N), rng.uniform(0, 40, N)], axis=1)
+        y = np.sin(X[:, 1] / 5) + 0.05 * rng.normal(size=N)
+        Xs = np.stack([np.full(M, 12.0), rng.uniform(0, 40, M), rng.uniform(0, 40, M)], axis=1)
+        g = gp.ScalarGP(X, y, [0.05, 0.02], [[20.0, 6.0, 7.0], [3.0, 1.5, 2.0]], 0.0009, jitter=1e-10)
+        Xsd = gp.as_dev(Xs)
+        t_fit = timeit(lambda: g.fit_async())
+        t_pred = timeit(lambda: g.predict(Xsd, include_noise=True))
+        t_grad = timeit(lambda: g.lml_and_grad())
+        fl = float(N) * N * M + 2.0 * N * M
+        print("rbf N=%d M=%d: fit %.3f ms  predict %.3f ms (%.2f TF/s)  lml+grad %.3f ms" % (
+            N, M, t_fit * 1e3, t_pred * 1e3, fl / t_pred / 1e12, t_grad * 1e3))
+
+
 def gemm_small():
     """128-tile warp-specialised kernel vs 64-tile kernel on the small GEMMs of the Cholesky recursion."""
     lib.gp2d_dbg_gemm.restype = C.c_int
@@ -163,5 +180,7 @@ if __name__ == "__main__":
         potrf_sizes()
     if "gemm" in what:
         gemm()
+    if "rbf" in what:
+        rbf()
     if "gemm_small" in what:
         gemm_small()
