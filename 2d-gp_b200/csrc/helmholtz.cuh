@@ -69,7 +69,10 @@ __device__ const double EXP2_TAB[64] = {
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
 };
 
-__device__ __forceinline__ double exp_neg(double x) {
+// tab: the 64-entry table above, or a copy of it in shared memory (the fused predictive kernel
+// leaves the L1 only ~30 KB next to its 221 KB of shared memory, and its streaming panel stores
+// evict the table: every lookup then pays an L2 round trip on the critical path)
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab = EXP2_TAB) {
     x = fmax(x, -708.0);
     const double INV = 0x1.71547652b82fep+6;      // 64 / ln 2
     const double C_HI = 0x1.62e42fef80000p-7;    // ln2/64, low 18 bits zero: n * C_HI exact
@@ -83,17 +86,18 @@ __device__ __forceinline__ double exp_neg(double x) {
     const double b = fma(r, 1.0 / 120.0, 1.0 / 24.0);   // 1/24 + r/120
     double p = fma(r2, fma(r2, b, a), r) + 1.0;         // 1 + r + r^2 a + r^4 b
     // 2^(j/64) with k added to its exponent field (k >= -1022: stays normal)
-    const long long tb = __double_as_longlong(EXP2_TAB[ni & 63]) + ((long long)(ni >> 6) << 52);
+    const long long tb = __double_as_longlong(tab[ni & 63]) + ((long long)(ni >> 6) << 52);
     return p * __longlong_as_double(tb);
 }
 
 // 2x2 block for separation (d1, d2).
 __device__ __forceinline__ void helm_block(const HelmParams& p, double d1, double d2,
-                                           double& k11, double& k12, double& k22) {
+                                           double& k11, double& k12, double& k22,
+                                           const double* __restrict__ tab = EXP2_TAB) {
     double a = d1 * d1, b = d2 * d2, c = d1 * d2;
     double r2 = a + b;
-    double E = exp_neg(-0.5 * p.s_df * r2);
-    double F = p.same_len ? E : exp_neg(-0.5 * p.s_cf * r2);
+    double E = exp_neg(-0.5 * p.s_df * r2, tab);
+    double F = p.same_len ? E : exp_neg(-0.5 * p.s_cf * r2, tab);
     double e = p.w_df * E, f = p.w_cf * F;
     double es = e * p.s_df, fs = f * p.s_cf;
     k11 = fma(-b, es, e) + fma(-a, fs, f);
@@ -104,22 +108,25 @@ __device__ __forceinline__ void helm_block(const HelmParams& p, double d1, doubl
 // A point of either layout: [N,2] rows (a, b) or [N,3] rows (t, a, b).
 struct HelmPoint { double a, b, t; };
 __device__ __forceinline__ HelmPoint helm_point(const HelmParams& p, const double* __restrict__ X, long i) {
+    // read-only path (ld.global.nc): point arrays are never written by the kernels that read them,
+    // and the compiler may then hoist these loads over unrelated stores (unrolled panel generation)
     const double* r = X + p.ldx * i;
     HelmPoint q;
-    q.a = r[p.xo];
-    q.b = r[p.xo + 1];
-    q.t = p.has_t ? r[0] : 0.0;
+    q.a = __ldg(r + p.xo);
+    q.b = __ldg(r + p.xo + 1);
+    q.t = p.has_t ? __ldg(r) : 0.0;
     return q;
 }
-__device__ __forceinline__ double helm_tau(const HelmParams& p, double dt) {
-    return p.tvar * exp_neg(-p.thalf * dt * dt);
+__device__ __forceinline__ double helm_tau(const HelmParams& p, double dt, const double* __restrict__ tab = EXP2_TAB) {
+    return p.tvar * exp_neg(-p.thalf * dt * dt, tab);
 }
 // 2x2 block between two points, time factor included when it is on.
 __device__ __forceinline__ void helm_block_pts(const HelmParams& p, const HelmPoint& x, const HelmPoint& y,
-                                               double& k11, double& k12, double& k22) {
-    helm_block(p, x.a - y.a, x.b - y.b, k11, k12, k22);
+                                               double& k11, double& k12, double& k22,
+                                               const double* __restrict__ tab = EXP2_TAB) {
+    helm_block(p, x.a - y.a, x.b - y.b, k11, k12, k22, tab);
     if (p.has_t) {
-        const double tau = helm_tau(p, x.t - y.t);
+        const double tau = helm_tau(p, x.t - y.t, tab);
         k11 *= tau; k12 *= tau; k22 *= tau;
     }
 }

@@ -74,7 +74,7 @@ __device__ __noinline__ void rbf_phase1(const PredictArgs& p, double* __restrict
             rbf_load_point(p.X, o, p.rp.D, a);
             if (v0) k0 = rbf_eval(p.rp, a, b0);
             if (v1) k1 = rbf_eval(p.rp, a, b1);
-            const double al = p.alpha[o];
+            const double al = __ldg(p.alpha + o);
             m0 = fma(k0, al, m0);
             m1 = fma(k1, al, m1);
         }
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
                 double k11 = 0.0, k12 = 0.0, k22 = 0.0;
                 if (gvalid && o < p.N) {
                     helm_block_pts(p.hp, helm_point(p.hp, p.X, o), gpt, k11, k12, k22);
-                    const double a0 = p.alpha[2 * o], a1 = p.alpha[2 * o + 1];
+                    const double a0 = __ldg(p.alpha + 2 * o), a1 = __ldg(p.alpha + 2 * o + 1);
                     mu0 = fma(k11, a0, fma(k12, a1, mu0));
                     mu1 = fma(k12, a0, fma(k22, a1, mu1));
                 }

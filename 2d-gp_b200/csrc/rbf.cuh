@@ -40,7 +40,8 @@ inline bool make_rbf(int D, int Q, const double* var, const double* ls, RbfParam
 }
 
 // a, b: coordinates padded with zeros to RBF_MAXD
-__device__ __forceinline__ double rbf_eval(const RbfParams& p, const double (&a)[RBF_MAXD], const double (&b)[RBF_MAXD]) {
+__device__ __forceinline__ double rbf_eval(const RbfParams& p, const double (&a)[RBF_MAXD], const double (&b)[RBF_MAXD],
+                                           const double* __restrict__ tab = EXP2_TAB) {
     double k = 0.0;
 #pragma unroll
     for (int q = 0; q < RBF_MAXQ; ++q) {
@@ -51,7 +52,7 @@ __device__ __forceinline__ double rbf_eval(const RbfParams& p, const double (&a)
                 const double t = (a[d] - b[d]) * p.inv[q][d];
                 s = fma(t, t, s);
             }
-            k = fma(p.var[q], exp_neg(-0.5 * s), k);
+            k = fma(p.var[q], exp_neg(-0.5 * s, tab), k);
         }
     }
     return k;
@@ -59,7 +60,7 @@ __device__ __forceinline__ double rbf_eval(const RbfParams& p, const double (&a)
 
 __device__ __forceinline__ void rbf_load_point(const double* __restrict__ X, long i, int D, double (&x)[RBF_MAXD]) {
 #pragma unroll
-    for (int d = 0; d < RBF_MAXD; ++d) x[d] = d < D ? X[i * D + d] : 0.0;
+    for (int d = 0; d < RBF_MAXD; ++d) x[d] = d < D ? __ldg(X + i * D + d) : 0.0;      // read-only path, see helm_point
 }
 
 // gradient accumulators: per component q, slot q (1 + RBF_MAXD) is d/dvar_q and the next RBF_MAXD
