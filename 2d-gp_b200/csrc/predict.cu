@@ -50,37 +50,112 @@ constexpr int PRED_GROUPS = 8;
 
 // shared memory: operand ring | mbarriers | group column sums [8][2][128] | mean partials [4][64][2]
 constexpr int PRED_MAX_ROWBLOCKS = 1024;          // npad <= 131072
-constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_ROWBLOCKS / 2;
+constexpr int PRED_STAGE_OBS = 256;                // observations staged in shared memory at a time (phase 1)
+constexpr int PRED_PARAM_DOUBLES = 64;             // shared-memory copy of HelmParams / RbfParams
+constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_ROWBLOCKS / 2 + 5 * PRED_STAGE_OBS + PRED_PARAM_DOUBLES;
+static_assert(sizeof(HelmParams) <= PRED_PARAM_DOUBLES * sizeof(double) && sizeof(RbfParams) <= PRED_PARAM_DOUBLES * sizeof(double), "parameter block");
 constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
-// Phase 1 of the scalar family, out of line: its register needs (two grid points x RBF_MAXD
-// coordinates, the component loop) must not push the accumulator loop into spilling.
-// Thread (gjl, os): grid points gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel row),
-// observations os, os + 4, ...
-__device__ __noinline__ void rbf_phase1(const PredictArgs& p, double* __restrict__ panel, int gp0, int gjl, int os,
-                                        double& mu0, double& mu1) {
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(WS_CONSUMERS) : "memory"); }
+
+// Phase 1 stages the observations through shared memory, 256 at a time: coordinates and alpha are
+// loaded once, coalesced, by the 256 consumer threads and then read as broadcasts.  Reading them
+// from global memory inside the pair loop put an L2 round trip at the head of every pair (the L1
+// is ~30 KB next to 221 KB of shared memory and the streaming panel stores keep evicting it): 58 %
+// of the phase-1 stall samples in the round-1 profile.
+//
+// Scalar family, out of line: its register needs (two grid points x RBF_MAXD coordinates, the
+// component loop) must not push the accumulator loop into spilling.  Thread (gjl, os): grid points
+// gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel row), observations os, os + 4, ...
+__device__ __noinline__ void rbf_phase1(const PredictArgs& p, const RbfParams& rp, double* __restrict__ panel,
+                                        double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
     constexpr int OS = WS_CONSUMERS / 64;
+    const int gjl = tid & 63, os = tid >> 6;
     const int gj = gp0 + 2 * gjl;
     const bool v0 = gj < p.M, v1 = gj + 1 < p.M;
     double b0[RBF_MAXD], b1[RBF_MAXD];
-    rbf_load_point(p.Xs, v0 ? gj : 0, p.rp.D, b0);
-    rbf_load_point(p.Xs, v1 ? gj + 1 : 0, p.rp.D, b1);
+    rbf_load_point(p.Xs, v0 ? gj : 0, rp.D, b0);
+    rbf_load_point(p.Xs, v1 ? gj + 1 : 0, rp.D, b1);
     double m0 = 0.0, m1 = 0.0;
-#pragma unroll 4
-    for (int o = os; o < p.npad; o += OS) {
-        double k0 = 0.0, k1 = 0.0;
-        if (o < p.N) {
+    for (int ob = 0; ob < p.npad; ob += PRED_STAGE_OBS) {
+        consumer_barrier();                     // the previous batch has been read
+        {
+            const int o = ob + tid;
             double a[RBF_MAXD];
-            rbf_load_point(p.X, o, p.rp.D, a);
-            if (v0) k0 = rbf_eval(p.rp, a, b0);
-            if (v1) k1 = rbf_eval(p.rp, a, b1);
-            const double al = __ldg(p.alpha + o);
-            m0 = fma(k0, al, m0);
-            m1 = fma(k1, al, m1);
+            rbf_load_point(p.X, o < p.N ? o : 0, rp.D, a);
+#pragma unroll
+            for (int d = 0; d < RBF_MAXD; ++d) stage[tid * 5 + d] = a[d];
+            stage[tid * 5 + 4] = o < p.N ? __ldg(p.alpha + o) : 0.0;
         }
-        *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
+        consumer_barrier();
+        const int nloc = min(PRED_STAGE_OBS, p.npad - ob);
+#pragma unroll 4
+        for (int ol = os; ol < nloc; ol += OS) {
+            const int o = ob + ol;
+            double k0 = 0.0, k1 = 0.0;
+            if (o < p.N) {
+                double a[RBF_MAXD];
+#pragma unroll
+                for (int d = 0; d < RBF_MAXD; ++d) a[d] = stage[ol * 5 + d];
+                if (v0) k0 = rbf_eval(rp, a, b0);
+                if (v1) k1 = rbf_eval(rp, a, b1);
+                const double al = stage[ol * 5 + 4];
+                m0 = fma(k0, al, m0);
+                m1 = fma(k1, al, m1);
+            }
+            *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
+        }
     }
     fence_proxy_async();
+    mu0 = m0;
+    mu1 = m1;
+}
+
+// Helmholtz family.  Thread (gjl, os): grid point gp0 + gjl (chunk gjl of every panel row),
+// observations os, os + 4, ...; rows 2o, 2o+1 of the panel.
+__device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams& hp, double* __restrict__ panel,
+                                         double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+    constexpr int OS = WS_CONSUMERS / 64;
+    const int gjl = tid & 63, os = tid >> 6;
+    const int gj = gp0 + gjl;
+    const bool gvalid = gj < p.M;
+    const HelmPoint gpt = helm_point(hp, p.Xs, gvalid ? gj : 0);
+    const int nobs_pad = p.npad >> 1;
+    double m0 = 0.0, m1 = 0.0;
+    for (int ob = 0; ob < nobs_pad; ob += PRED_STAGE_OBS) {
+        consumer_barrier();                     // the previous batch has been read
+        {
+            const int o = ob + tid;
+            const bool ov = o < p.N;
+            const HelmPoint q = helm_point(hp, p.X, ov ? o : 0);
+            stage[tid * 5 + 0] = q.a;
+            stage[tid * 5 + 1] = q.b;
+            stage[tid * 5 + 2] = q.t;
+            stage[tid * 5 + 3] = ov ? __ldg(p.alpha + 2 * o) : 0.0;
+            stage[tid * 5 + 4] = ov ? __ldg(p.alpha + 2 * o + 1) : 0.0;
+        }
+        consumer_barrier();
+        const int nloc = min(PRED_STAGE_OBS, nobs_pad - ob);
+#pragma unroll 4
+        for (int ol = os; ol < nloc; ol += OS) {
+            const int o = ob + ol;
+            double k11 = 0.0, k12 = 0.0, k22 = 0.0;
+            if (gvalid && o < p.N) {
+                HelmPoint q;
+                q.a = stage[ol * 5 + 0]; q.b = stage[ol * 5 + 1]; q.t = stage[ol * 5 + 2];
+                helm_block_pts(hp, q, gpt, k11, k12, k22);
+                const double a0 = stage[ol * 5 + 3], a1 = stage[ol * 5 + 4];
+                m0 = fma(k11, a0, fma(k12, a1, m0));
+                m1 = fma(k12, a0, fma(k22, a1, m1));
+            }
+            // rows k = 2o, 2o+1 of the MN-major tile image: 16-byte chunk gjl, swizzled by k & 3
+            double* r0 = panel + (size_t)(2 * o) * TILE;
+            const int sw = (o & 1) << 2;
+            *reinterpret_cast<double2*>(r0 + 2 * (gjl ^ sw)) = make_double2(k11, k12);
+            *reinterpret_cast<double2*>(r0 + TILE + 2 * (gjl ^ (sw | 2))) = make_double2(k12, k22);
+        }
+    }
+    fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
     mu0 = m0;
     mu1 = m1;
 }
@@ -98,6 +173,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
     double* sh_grp = reinterpret_cast<double*>(bars + 2 * WS_STAGES);   // [8][WM][128]
     double* sh_mu = sh_grp + PRED_GROUPS * WM * TILE;                   // [OS][64][2]
     int* sh_rb = reinterpret_cast<int*>(sh_mu + OS * 64 * 2);           // row blocks of the item: li | group << 16
+    double* sh_stage = reinterpret_cast<double*>(sh_rb + PRED_MAX_ROWBLOCKS);   // phase 1: 256 observations x 5 doubles
+    double* sh_par = sh_stage + 5 * PRED_STAGE_OBS;                    // kernel parameters (a noinline callee would
+                                                                       // otherwise read them through generic loads)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == WS_CONSUMERS / 32;
@@ -114,6 +192,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
     fa.init(wm, lane);
     fb.init(wn, lane);
     wb.init(tid, 1);
+    {
+        const double* src = FAM == FAM_HELM ? reinterpret_cast<const double*>(&p.hp) : reinterpret_cast<const double*>(&p.rp);
+        const int nd = (int)((FAM == FAM_HELM ? sizeof(HelmParams) : sizeof(RbfParams)) / sizeof(double));
+        if (tid < nd) sh_par[tid] = src[tid];
+    }
     __syncthreads();
 
     int rs = 0;            // ring cursor; both roles walk the same sequence of stages
@@ -126,28 +209,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
         const int gp0 = ct * PTS;
         // ---------------- phase 1 (consumer warps): K* panel + mean ------------------------
         double mu0 = 0.0, mu1 = 0.0;
-        if (!producer && FAM == FAM_RBF) rbf_phase1(p, panel, gp0, gjl, os, mu0, mu1);
-        if (!producer && FAM == FAM_HELM) {
-            const int gj = gp0 + gjl;
-            const bool gvalid = gj < p.M;
-            const HelmPoint gpt = helm_point(p.hp, p.Xs, gvalid ? gj : 0);
-            const int nobs_pad = p.npad >> 1;
-#pragma unroll 2
-            for (int o = os; o < nobs_pad; o += OS) {
-                double k11 = 0.0, k12 = 0.0, k22 = 0.0;
-                if (gvalid && o < p.N) {
-                    helm_block_pts(p.hp, helm_point(p.hp, p.X, o), gpt, k11, k12, k22);
-                    const double a0 = __ldg(p.alpha + 2 * o), a1 = __ldg(p.alpha + 2 * o + 1);
-                    mu0 = fma(k11, a0, fma(k12, a1, mu0));
-                    mu1 = fma(k12, a0, fma(k22, a1, mu1));
-                }
-                // rows k = 2o, 2o+1 of the MN-major tile image: 16-byte chunk gjl, swizzled by k & 3
-                double* r0 = panel + (size_t)(2 * o) * TILE;
-                const int sw = (o & 1) << 2;
-                *reinterpret_cast<double2*>(r0 + 2 * (gjl ^ sw)) = make_double2(k11, k12);
-                *reinterpret_cast<double2*>(r0 + TILE + 2 * (gjl ^ (sw | 2))) = make_double2(k12, k22);
-            }
-            fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
+        if (!producer) {
+            if (FAM == FAM_RBF) rbf_phase1(p, *reinterpret_cast<const RbfParams*>(sh_par), panel, sh_stage, gp0, tid, mu0, mu1);
+            else helm_phase1(p, *reinterpret_cast<const HelmParams*>(sh_par), panel, sh_stage, gp0, tid, mu0, mu1);
         }
         // the item's row blocks in processing order (both roles walk this list)
         int nrb = 0;
