@@ -772,6 +772,8 @@ int gp2d_dbg_set_small_tile_threshold(int t) { set_small_tile_threshold(t); retu
 
 int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; }
 
+int gp2d_dbg_set_predict_split(int s) { set_predict_split(s); return s; }
+
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,
                   void* stream) {

@@ -66,6 +66,7 @@ cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, c
                               const RbfParams& rp, const double* Xs, int M, double var_add, double* mean,
                               double* var, double* scratch, size_t scratch_bytes, cudaStream_t st);
 int predict_max_ctas();
+void set_predict_split(int s);          // bring-up override: 1, 2, 4, 8 (0 = heuristic)
 
 // grad.cu ---------------------------------------------------------------------------------
 // From Kinv (lower, interleaved, padded) and alpha_int: out6 = d LML / d(l_df, l_cf, ratio, tvar, lt, noise).

@@ -64,18 +64,38 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 // is ~30 KB next to 221 KB of shared memory and the streaming panel stores keep evicting it): 58 %
 // of the phase-1 stall samples in the round-1 profile.
 //
-// Scalar family, out of line: its register needs (two grid points x RBF_MAXD coordinates, the
-// component loop) must not push the accumulator loop into spilling.  Thread (gjl, os): grid points
-// gp0 + 2 gjl + {0,1} (one 16-byte chunk of every panel row), observations os, os + 4, ...
-__device__ __noinline__ void rbf_phase1(const PredictArgs& p, const RbfParams& rp, double* __restrict__ panel,
-                                        double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+// The pair loops are branch-free (validity is a 0/1 factor, the kernel variant is a template
+// parameter): with control flow in the body the compiler unrolls but does not interleave the
+// iterations, and one dependent FP64 chain per thread took ~840 cycles per pair.
+//
+// Scalar family.  Thread (gjl, os): grid points gp0 + 2 gjl + {0,1} (one 16-byte chunk of every
+// panel row), observations os, os + 4, ...
+template <int Q>
+__device__ __forceinline__ double rbf_eval_q(const RbfParams& p, const double (&a)[RBF_MAXD], const double (&b)[RBF_MAXD]) {
+    double k = 0.0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < RBF_MAXD; ++d) {
+            const double t = (a[d] - b[d]) * p.inv[q][d];
+            s = fma(t, t, s);
+        }
+        k = fma(p.var[q], exp_neg(-0.5 * s), k);
+    }
+    return k;
+}
+
+template <int Q>
+__device__ __forceinline__ void rbf_phase1_loop(const PredictArgs& p, const RbfParams& rp, double* __restrict__ panel,
+                                                double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
     constexpr int OS = WS_CONSUMERS / 64;
     const int gjl = tid & 63, os = tid >> 6;
     const int gj = gp0 + 2 * gjl;
-    const bool v0 = gj < p.M, v1 = gj + 1 < p.M;
+    const double w0 = gj < p.M ? 1.0 : 0.0, w1 = gj + 1 < p.M ? 1.0 : 0.0;
     double b0[RBF_MAXD], b1[RBF_MAXD];
-    rbf_load_point(p.Xs, v0 ? gj : 0, rp.D, b0);
-    rbf_load_point(p.Xs, v1 ? gj + 1 : 0, rp.D, b1);
+    rbf_load_point(p.Xs, gj < p.M ? gj : 0, rp.D, b0);
+    rbf_load_point(p.Xs, gj + 1 < p.M ? gj + 1 : 0, rp.D, b1);
     double m0 = 0.0, m1 = 0.0;
     for (int ob = 0; ob < p.npad; ob += PRED_STAGE_OBS) {
         consumer_barrier();                     // the previous batch has been read
@@ -92,17 +112,15 @@ __device__ __noinline__ void rbf_phase1(const PredictArgs& p, const RbfParams& r
 #pragma unroll 4
         for (int ol = os; ol < nloc; ol += OS) {
             const int o = ob + ol;
-            double k0 = 0.0, k1 = 0.0;
-            if (o < p.N) {
-                double a[RBF_MAXD];
+            double a[RBF_MAXD];
 #pragma unroll
-                for (int d = 0; d < RBF_MAXD; ++d) a[d] = stage[ol * 5 + d];
-                if (v0) k0 = rbf_eval(rp, a, b0);
-                if (v1) k1 = rbf_eval(rp, a, b1);
-                const double al = stage[ol * 5 + 4];
-                m0 = fma(k0, al, m0);
-                m1 = fma(k1, al, m1);
-            }
+            for (int d = 0; d < RBF_MAXD; ++d) a[d] = stage[ol * 5 + d];
+            const double wo = o < p.N ? 1.0 : 0.0;
+            const double k0 = rbf_eval_q<Q>(rp, a, b0) * (wo * w0);
+            const double k1 = rbf_eval_q<Q>(rp, a, b1) * (wo * w1);
+            const double al = stage[ol * 5 + 4];
+            m0 = fma(k0, al, m0);
+            m1 = fma(k1, al, m1);
             *reinterpret_cast<double2*>(panel + (size_t)o * TILE + 2 * (gjl ^ ((o & 3) << 1))) = make_double2(k0, k1);
         }
     }
@@ -111,15 +129,27 @@ __device__ __noinline__ void rbf_phase1(const PredictArgs& p, const RbfParams& r
     mu1 = m1;
 }
 
+// out of line: the register needs of the generators must not push the accumulator loop into spilling
+__device__ __noinline__ void rbf_phase1(const PredictArgs& p, const RbfParams& rp, double* __restrict__ panel,
+                                        double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+    switch (rp.Q) {
+        case 1: rbf_phase1_loop<1>(p, rp, panel, stage, gp0, tid, mu0, mu1); break;
+        case 2: rbf_phase1_loop<2>(p, rp, panel, stage, gp0, tid, mu0, mu1); break;
+        case 3: rbf_phase1_loop<3>(p, rp, panel, stage, gp0, tid, mu0, mu1); break;
+        default: rbf_phase1_loop<4>(p, rp, panel, stage, gp0, tid, mu0, mu1); break;
+    }
+}
+
 // Helmholtz family.  Thread (gjl, os): grid point gp0 + gjl (chunk gjl of every panel row),
 // observations os, os + 4, ...; rows 2o, 2o+1 of the panel.
-__device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams& hp, double* __restrict__ panel,
-                                         double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+template <bool SAME_LEN, bool HAS_T>
+__device__ __forceinline__ void helm_phase1_loop(const PredictArgs& p, const HelmParams& hp, double* __restrict__ panel,
+                                                 double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
     constexpr int OS = WS_CONSUMERS / 64;
     const int gjl = tid & 63, os = tid >> 6;
     const int gj = gp0 + gjl;
-    const bool gvalid = gj < p.M;
-    const HelmPoint gpt = helm_point(hp, p.Xs, gvalid ? gj : 0);
+    const double wg = gj < p.M ? 1.0 : 0.0;
+    const HelmPoint gpt = helm_point(hp, p.Xs, gj < p.M ? gj : 0);
     const int nobs_pad = p.npad >> 1;
     double m0 = 0.0, m1 = 0.0;
     for (int ob = 0; ob < nobs_pad; ob += PRED_STAGE_OBS) {
@@ -139,15 +169,25 @@ __device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams&
 #pragma unroll 4
         for (int ol = os; ol < nloc; ol += OS) {
             const int o = ob + ol;
-            double k11 = 0.0, k12 = 0.0, k22 = 0.0;
-            if (gvalid && o < p.N) {
-                HelmPoint q;
-                q.a = stage[ol * 5 + 0]; q.b = stage[ol * 5 + 1]; q.t = stage[ol * 5 + 2];
-                helm_block_pts(hp, q, gpt, k11, k12, k22);
-                const double a0 = stage[ol * 5 + 3], a1 = stage[ol * 5 + 4];
-                m0 = fma(k11, a0, fma(k12, a1, m0));
-                m1 = fma(k12, a0, fma(k22, a1, m1));
+            const double d1 = stage[ol * 5 + 0] - gpt.a, d2 = stage[ol * 5 + 1] - gpt.b;
+            // helm_block, specialised at compile time
+            const double a = d1 * d1, b = d2 * d2, c = d1 * d2, r2 = a + b;
+            const double E = exp_neg(-0.5 * hp.s_df * r2);
+            const double F = SAME_LEN ? E : exp_neg(-0.5 * hp.s_cf * r2);
+            double w = o < p.N ? wg : 0.0;
+            if (HAS_T) {
+                const double dt = stage[ol * 5 + 2] - gpt.t;
+                w *= hp.tvar * exp_neg(-hp.thalf * dt * dt);
             }
+            const double e = hp.w_df * E, f = hp.w_cf * F;
+            const double es = e * hp.s_df, fs = f * hp.s_cf;
+            double k11 = fma(-b, es, e) + fma(-a, fs, f);
+            double k22 = fma(-a, es, e) + fma(-b, fs, f);
+            double k12 = c * (es - fs);
+            k11 *= w; k12 *= w; k22 *= w;
+            const double a0 = stage[ol * 5 + 3], a1 = stage[ol * 5 + 4];
+            m0 = fma(k11, a0, fma(k12, a1, m0));
+            m1 = fma(k12, a0, fma(k22, a1, m1));
             // rows k = 2o, 2o+1 of the MN-major tile image: 16-byte chunk gjl, swizzled by k & 3
             double* r0 = panel + (size_t)(2 * o) * TILE;
             const int sw = (o & 1) << 2;
@@ -158,6 +198,17 @@ __device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams&
     fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
     mu0 = m0;
     mu1 = m1;
+}
+
+__device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams& hp, double* __restrict__ panel,
+                                         double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+    if (hp.has_t) {
+        if (hp.same_len) helm_phase1_loop<true, true>(p, hp, panel, stage, gp0, tid, mu0, mu1);
+        else helm_phase1_loop<false, true>(p, hp, panel, stage, gp0, tid, mu0, mu1);
+    } else {
+        if (hp.same_len) helm_phase1_loop<true, false>(p, hp, panel, stage, gp0, tid, mu0, mu1);
+        else helm_phase1_loop<false, false>(p, hp, panel, stage, gp0, tid, mu0, mu1);
+    }
 }
 
 // 8 consumer warps (phase 1 + DMMA) and one producer warp (bulk-copy ring), see pipeline.cuh.
@@ -375,12 +426,16 @@ int predict_max_ctas() {
 // Split of the row blocks of one column tile over CTAs.  An item costs its share of the DMMA work
 // plus a full phase 1 (every CTA of a split tile generates the whole panel), so the time is
 // ~ ceil(ntiles nsplit / SMs) * (1 / nsplit + phi) with phi = phase 1 / DMMA time of a whole tile
-// (measured: ~3 % at npad = 4096 for the Helmholtz block generator, ~4x that for the scalar
-// family, which needs one exponential per entry; both scale as 1 / npad).  The smallest nsplit in
+// (measured with tools/explore.py split at npad = 4096: 1.15 % for the Helmholtz block generator,
+// 3.4 % for the scalar family, which needs one exponential per entry; both scale as 1 / npad).  The smallest nsplit in
 // {1,2,4,8} within 3 % of the best estimate is taken.
+static int g_force_split = 0;
+void set_predict_split(int s) { g_force_split = (s == 1 || s == 2 || s == 4 || s == 8) ? s : 0; }
+
 int predict_choose_split(long ntiles, int npad, int fam) {
+    if (g_force_split) return g_force_split;      // bring-up override (calibration of phi)
     const long sms = predict_max_ctas();
-    const double phi = (fam == FAM_HELM ? 123.0 : 500.0) / (double)npad;
+    const double phi = (fam == FAM_HELM ? 47.0 : 140.0) / (double)npad;
     double best = 1e300;
     double r[4];
     for (int i = 0; i < 4; ++i) {

@@ -142,6 +142,32 @@ def rbf():
             N, M, t_fit * 1e3, t_pred * 1e3, fl / t_pred / 1e12, t_grad * 1e3))
 
 
+def split_calibration():
+    """predict time vs forced nsplit: slope = phase-1 time per item (phi of predict_choose_split)."""
+    lib.gp2d_dbg_set_predict_split.restype = C.c_int
+    lib.gp2d_dbg_set_predict_split.argtypes = [C.c_int]
+    X, y = synthetic.drifter_snapshot(2000, config_id=2)
+    Xs = synthetic.prediction_grid(X, 320, 320)
+    m = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+    m.fit()
+    Xsd = gp.as_dev(Xs)
+    rng = np.random.default_rng(1)
+    N, M = 4000, 102400
+    Xr = np.stack([rng.uniform(0, 24, N), rng.uniform(0, 40, N), rng.uniform(0, 40, N)], axis=1)
+    yr = np.sin(Xr[:, 1] / 5) + 0.05 * rng.normal(size=N)
+    Xrs = gp.as_dev(np.stack([np.full(M, 12.0), rng.uniform(0, 40, M), rng.uniform(0, 40, M)], axis=1))
+    g = gp.ScalarGP(Xr, yr, [0.05, 0.02], [[20.0, 6.0, 7.0], [3.0, 1.5, 2.0]], 0.0009, jitter=1e-10)
+    g.fit()
+    for s in (1, 2, 4, 8):
+        lib.gp2d_dbg_set_predict_split(s)
+        m._pws = None
+        g._pws = None
+        th = timeit(lambda: m.predict(Xsd))
+        tr = timeit(lambda: g.predict(Xrs))
+        print("nsplit=%d: helmholtz predict %.3f ms   rbf predict %.3f ms" % (s, th * 1e3, tr * 1e3))
+    lib.gp2d_dbg_set_predict_split(0)
+
+
 def gemm_small():
     """128-tile warp-specialised kernel vs 64-tile kernel on the small GEMMs of the Cholesky recursion."""
     lib.gp2d_dbg_gemm.restype = C.c_int
@@ -180,6 +206,8 @@ if __name__ == "__main__":
         potrf_sizes()
     if "gemm" in what:
         gemm()
+    if "split" in what:
+        split_calibration()
     if "rbf" in what:
         rbf()
     if "gemm_small" in what:
