@@ -766,8 +766,6 @@ int gp2d_dbg_fp64_mode(int mode, int iters, int ctas, double* out, void* stream)
     return cuda_rc(cudaGetLastError());
 }
 
-int gp2d_dbg_set_cta_threads(int nt) { set_cta_threads(nt); return get_cta_threads(); }
-
 int gp2d_dbg_set_small_tile_threshold(int t) { set_small_tile_threshold(t); return t; }
 
 int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; }

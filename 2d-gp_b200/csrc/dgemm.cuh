@@ -7,9 +7,10 @@
 //            B[k*ldb + n] (MN-major, i.e. C = A * B).
 // M, N are multiples of 128 and K of 16; triangular structure is exploited by clipping the
 // k-range per output tile (KR_* flags) and by skipping tiles above the diagonal
-// (lower_out).  TS x TS x 16 CTA tile (TS = 128 with 8 warps of 64x32, or TS = 64 with
-// 4 warps of 32x32 for problems too small to fill 148 SMs with 128-tiles), 4-stage cp.async
-// pipeline, XOR-swizzled shared memory, DMMA.8x8x4 register tiles.
+// (lower_out).  Two kernels: dgemm_ws_kernel, 128 x 128 x 16 tiles, warp-specialised
+// (pipeline.cuh), for everything that fills the GPU; dgemm_kernel<.., 128, 64>, 64 x 64 x 16 tiles
+// with 4 warps of 32x32, 4-stage cp.async pipeline and up to 3 CTAs per SM, for the small GEMMs of
+// the Cholesky recursion.  XOR-swizzled shared memory, DMMA.8x8x4 register tiles.
 #pragma once
 #include "common.cuh"
 #include "pipeline.cuh"
@@ -234,9 +235,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dgemm_ws_kernel(GemmArgs p) {
 // host launcher (linalg.cu)
 cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& args, cudaStream_t stream);
 cudaError_t dgemm_init();
-// CTA shape used by GEMM / predict launches: 256 (8 warps, 64x32 warp tiles) or 512.
-void set_cta_threads(int nt);
-int get_cta_threads();
 void set_small_tile_threshold(int tiles128);
 
 }  // namespace gp2d

@@ -25,10 +25,6 @@ namespace gp2d {
 // ------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------
-static int g_cta_threads = 256;
-void set_cta_threads(int) {}          // single CTA shape since the warp-specialised kernels
-int get_cta_threads() { return g_cta_threads; }
-
 template <bool A_MN, bool B_MN>
 static cudaError_t gemm_attr64() {
     return cudaFuncSetAttribute(dgemm_kernel<A_MN, B_MN, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

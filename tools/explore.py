@@ -16,8 +16,6 @@ from gp2d_b200._lib import lib
 dev = torch.device("cuda:0")
 lib.gp2d_dbg_fp64_mode.restype = C.c_int
 lib.gp2d_dbg_fp64_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-lib.gp2d_dbg_set_cta_threads.restype = C.c_int
-lib.gp2d_dbg_set_cta_threads.argtypes = [C.c_int]
 
 
 def ev():
@@ -64,8 +62,7 @@ def stages(N=2000, grid=(320, 320), theta=(1.3, 3.1, 0.2)):
     Xs = synthetic.prediction_grid(X, *grid)
     M = Xs.shape[0]
     n = 2 * N
-    for nt in (256, 512):
-        lib.gp2d_dbg_set_cta_threads(nt)
+    for nt in (288,):
         m = gp.HelmholtzGP(X, y, *theta, 0.05)
         Xsd = gp.as_dev(Xs)
         t_fit = timeit(lambda: m.fit_async())
@@ -77,12 +74,10 @@ def stages(N=2000, grid=(320, 320), theta=(1.3, 3.1, 0.2)):
         m2 = gp.HelmholtzGP(X, y, 2.0, 2.0, 0.5, 0.05)
         t_pred2 = timeit(lambda: m2.predict(Xsd))
         print("   equal length scales (one exp): predict %.3f ms (%.2f TF/s)" % (t_pred2 * 1e3, fl / t_pred2 / 1e12))
-    lib.gp2d_dbg_set_cta_threads(256)
 
 
 def potrf_sizes():
-    for nt in (256, 512):
-        lib.gp2d_dbg_set_cta_threads(nt)
+    for nt in (288,):
         for n in (1024, 4096, 8192, 16384):
             g = torch.Generator(device=dev).manual_seed(n)
             B = torch.randn(n, 256, generator=g, dtype=torch.float64, device=dev)
@@ -100,7 +95,6 @@ def potrf_sizes():
             t = timeit(run) - t_copy
             print("potrf nt=%d n=%d: %.3f ms  %.2f TF/s (n^3/3)  info=%d" % (nt, n, t * 1e3, n ** 3 / 3 / t / 1e12, int(info.item())))
             del A, B, Aw, ws
-    lib.gp2d_dbg_set_cta_threads(256)
 
 
 def gemm():
@@ -109,8 +103,7 @@ def gemm():
                                   C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                   C.c_int, C.c_void_p]
     st = torch.cuda.current_stream().cuda_stream
-    for nt in (256, 512):
-        lib.gp2d_dbg_set_cta_threads(nt)
+    for nt in (288,):
         for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 4096), (16384, 16384, 128), (2048, 2048, 2048)]:
             A = torch.randn(max(M, K), max(M, K), dtype=torch.float64, device=dev)
             B = torch.randn(max(N, K), max(N, K), dtype=torch.float64, device=dev)
@@ -122,7 +115,6 @@ def gemm():
                     print("gemm nt=%d %dx%dx%d a_mn=%d b_mn=%d beta=%g: %.3f ms %.2f TF/s" % (
                         nt, M, N, K, a_mn, b_mn, beta, t * 1e3, 2.0 * M * N * K / t / 1e12))
             del A, B, Cm
-    lib.gp2d_dbg_set_cta_threads(256)
 
 
 def rbf():
