@@ -29,15 +29,33 @@ def _ratio(divFree):
         return 1.0
     if divFree == 2:
         return 0.0
-    raise NotImplementedError("divFree must be 1 (divergence-free) or 2 (curl-free); the scalar "
-                              "squared-exponential branch (GP_scripts.py:67-68) is outside the GPU path")
+    raise ValueError("divFree must be 1 (divergence-free) or 2 (curl-free)")
 
 
 def nonDivK(xa, xb, sigma, divFree=1):
-    """2x2 covariance block between two points (GP_scripts.py:57-69)."""
+    """2x2 covariance block between two points; any other divFree gives the scalar
+    squared-exponential exp(-|xa-xb|^2 / 2 sigma^2) (GP_scripts.py:57-69)."""
     xa = np.asarray(xa, dtype=np.float64).reshape(1, 2)
     xb = np.asarray(xb, dtype=np.float64).reshape(1, 2)
+    if divFree not in (1, 2):
+        return float(engine.rbf_K(xa, xb, [1.0], [[float(sigma)] * 2]).cpu().numpy()[0, 0])
     return engine.kernel_K(xa, xb, float(sigma), float(sigma), _ratio(divFree)).cpu().numpy()
+
+
+def sqExp(x1, y1, x2, y2, sigma):
+    """Scalar squared-exponential between the points (x1, y1) and (x2, y2), [I,J]  (GP_scripts.py:125-134)."""
+    return engine.rbf_K(_pts(x1, y1), _pts(x2, y2), [1.0], [[float(sigma)] * 2]).cpu().numpy()
+
+
+def rbf(x1, x2, l=1, sigma=1, noise=0):
+    """sigma^2 exp(-(x2-x1)^2 / 2 l^2), plus noise on the diagonal when the sizes match
+    (GP_scripts.py:136-142)."""
+    a = np.reshape(np.asarray(x1, dtype=np.float64), [-1, 1])
+    b = np.reshape(np.asarray(x2, dtype=np.float64), [-1, 1])
+    K = engine.rbf_K(a, b, [float(sigma) ** 2], [[float(l)]]).cpu().numpy()
+    if a.size == b.size:
+        K = K + np.identity(a.size) * noise
+    return K
 
 
 def compute_K(x1, x2, sigma, divFree=1):
@@ -88,6 +106,36 @@ def generate_2D_gaussian(divFree=1):
     xm = (x[:-1] + x[1:]) / 2.
     ym = (x[:-1] + x[1:]) / 2.
     return x, y, phi, xm, ym, um, vm
+
+
+def rmse1(ys, y):
+    """Root-mean-square error (GP_scripts.py:172-176)."""
+    error = np.reshape(np.asarray(ys) - np.asarray(y), [-1])
+    return np.sqrt(np.mean(np.square(error)))
+
+
+def rmse(x1s, x2s, f1, f2, x1, x2, y1, y2, knd=''):
+    """RMSE of both components at the data points (GP_scripts.py:144-170).  Only the direct
+    comparison (knd='') and radial-basis interpolation (knd='rbf') are kept: scipy removed
+    interp2d, which the 'cubic' / 'linear' branches used."""
+    if knd == 'rbf':
+        from scipy.interpolate import Rbf
+        y1s, y2s = Rbf(x1s, x2s, f1)(x1, x2), Rbf(x1s, x2s, f2)(x1, x2)
+    elif knd in ('cubic', 'linear'):
+        raise NotImplementedError("scipy.interpolate.interp2d no longer exists")
+    else:
+        y1s, y2s = f1, f2
+    r1, r2 = rmse1(y1s, y1), rmse1(y2s, y2)
+    print(r1 / (np.max(y1) - np.min(y1)), r2 / (np.max(y2) - np.min(y2)))
+    return r1, r2
+
+
+def absoluteError(y, f, x1f, x2f, x1, x2):
+    """|y - f| and the distance of each grid point to the nearest observation (GP_scripts.py:178-200)."""
+    f, y = np.reshape(f, [-1]), np.reshape(y, [-1])
+    X1f, X1 = np.meshgrid(x1f, x1)
+    X2f, X2 = np.meshgrid(x2f, x2)
+    return np.abs(y - f), np.min(np.sqrt(np.square(X1 - X1f) + np.square(X2 - X2f)), 0)
 
 
 def vel_grad(x, y, u, v):

@@ -27,11 +27,11 @@ def _lines(fname, lo, hi):
 
 
 def gp_scripts():
-    """namespace with myKernel, getMean, getCov, nonDivK, compute_K, compute_Ks
-    (GP_scripts.py:1-3 imports + 6-123)."""
+    """namespace with myKernel, getMean, getCov, nonDivK, compute_K, compute_Ks, sqExp, rbf
+    (GP_scripts.py:1-3 imports + 6-142)."""
     ns = {}
-    code = "import numpy as np\n" + _lines("GP_scripts.py", 6, 123)
-    exec(compile(code, "GP_scripts.py[6:123]", "exec"), ns)
+    code = "import numpy as np\n" + _lines("GP_scripts.py", 6, 142)
+    exec(compile(code, "GP_scripts.py[6:142]", "exec"), ns)
     return ns
 
 

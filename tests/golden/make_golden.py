@@ -53,6 +53,10 @@ def kernel_small():
         k.update_gradients_full(W_x, X, X2)
         out["ref_grad_compat_x_%d" % t] = np.array(
             [k.length_df.gradient, k.length_cf.gradient, k.ratio.gradient])
+    # scalar squared-exponential helpers (GP_scripts.py:125-142; nonDivK's divFree=0 branch :67-68)
+    out["ref_sqExp"] = gs["sqExp"](X[:, 0], X[:, 1], X2[:, 0], X2[:, 1], 1.7)
+    out["ref_rbf_x"] = gs["rbf"](X[:, 0], X2[:, 0], l=1.3, sigma=0.8, noise=0.05)
+    out["ref_rbf_sym"] = gs["rbf"](X[:, 0], X[:, 0], l=1.3, sigma=0.8, noise=0.05)
     nd = rs.nondivk_class(1.7)
     out["ref_nonDivK"] = nd.K(X, X2)
     out["ref_nonDivK_diag"] = nd.Kdiag(X2)

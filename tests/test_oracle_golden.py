@@ -68,6 +68,15 @@ def test_correct_gradient_matches_central_differences(ks):
         np.testing.assert_allclose(gc[2], fd[2], rtol=1e-7)
 
 
+def test_scalar_helpers_match_reference(ks):
+    """GP_scripts.sqExp / rbf (GP_scripts.py:125-142) are instances of the scalar RBF family."""
+    X, X2 = ks["X"], ks["X2"]
+    np.testing.assert_allclose(orc.rbf_sum_K(X, X2, [1.0], [[1.7, 1.7]]), ks["ref_sqExp"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(orc.rbf_sum_K(X[:, :1], X2[:, :1], [0.64], [[1.3]]), ks["ref_rbf_x"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(orc.rbf_sum_K(X[:, :1], None, [0.64], [[1.3]]) + 0.05 * np.eye(X.shape[0]),
+                               ks["ref_rbf_sym"], rtol=1e-14, atol=1e-16)
+
+
 def test_known_answers():
     # K(0) = I / l^2; uu minimum -2 e^{-3/2} / l^2 at distance sqrt(3) l along y (div-free)
     l = 0.2

@@ -87,6 +87,13 @@ def test_gp_scripts_functions(ks):
         np.testing.assert_allclose(Ks, ks["ref_Ks_loops_%d" % t], rtol=0, atol=1e-14)
     blk = GP_scripts.nonDivK(X[0], X[3], 1.7, 1)
     np.testing.assert_allclose(blk, orc.helmholtz_K(X[0:1], X[3:4], 1.7, 1.7, 1.0), rtol=0, atol=1e-15)
+    # scalar squared-exponential helpers (GP_scripts.py:67-68,125-142)
+    np.testing.assert_allclose(GP_scripts.sqExp(X[:, 0], X[:, 1], X2[:, 0], X2[:, 1], 1.7), ks["ref_sqExp"], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(GP_scripts.rbf(X[:, 0], X2[:, 0], l=1.3, sigma=0.8, noise=0.05), ks["ref_rbf_x"], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(GP_scripts.rbf(X[:, 0], X[:, 0], l=1.3, sigma=0.8, noise=0.05), ks["ref_rbf_sym"], rtol=1e-13, atol=1e-16)
+    assert GP_scripts.nonDivK(X[0], X[3], 1.7, 0) == pytest.approx(
+                                                                   float(np.exp(-np.sum((X[0] - X[3]) ** 2) / (2 * 1.7 ** 2))), rel=1e-13)
+    assert GP_scripts.rmse1(np.array([1.0, 3.0]), np.zeros(2)) == pytest.approx(np.sqrt(5.0))
 
 
 def test_getMean_getCov_inverse_form(golden_dir):
