@@ -88,6 +88,13 @@ class _ScalarKern:
             return NotImplemented
         return Add(self.parts_list() + other.parts_list())
 
+    def __mul__(self, other):
+        if isinstance(self, RBF) and isinstance(other, RBF):
+            return Prod([self, other])
+        if isinstance(self, Prod) and isinstance(other, RBF):
+            return Prod(self.factors + [other])
+        return NotImplemented
+
     def parameters_changed(self):
         pass
 
@@ -135,3 +142,64 @@ class Add(_ScalarKern):
 
     def parts_list(self):
         return self.parts
+
+
+class Prod(_ScalarKern):
+    """Product of RBF kernels acting on disjoint input columns, ``k1 * k2`` in GPy
+    (GP_plots.py:738-740: ``RBF(1, active_dims=[0]) * RBF(1, active_dims=[1])``).  Such a product is
+    one anisotropic RBF over the union of the columns with variance prod(variance_i); GPy keeps
+    every factor's variance as its own (redundant) parameter, and so does this class."""
+
+    def __init__(self, factors, name="mul"):
+        factors = [f.copy() for f in factors]
+        dims = [d for f in factors for d in f.active_dims]
+        if len(set(dims)) != len(dims):
+            raise NotImplementedError("only products of RBFs on disjoint input columns are on the GPU path")
+        if len(dims) > 4:
+            raise ValueError("at most 4 input dimensions")
+        self.factors, self.name = factors, name
+        self.active_dims = dims
+        self.input_dim = len(dims)
+        self.ARD = True
+
+    def parts_list(self):
+        return [self]
+
+    # the engine sees ONE anisotropic component over active_dims
+    def rbf_params(self):
+        return [float(np.prod([float(f.variance) for f in self.factors]))], \
+               [[l for f in self.factors for l in f._ls_vector()]]
+
+    def _slice(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        return X if X.shape[1] == len(self.active_dims) and self.active_dims == list(range(X.shape[1])) \
+            else X[:, self.active_dims]
+
+    @property
+    def parameters(self):
+        out = []
+        for f in self.factors:
+            out += [f.variance] + f.lengthscale
+        return out
+
+    def parameter_names(self):
+        names = []
+        for i, f in enumerate(self.factors):
+            base = "mul.%s" % (f.name if i == 0 else "%s_%d" % (f.name, i))
+            names.append(base + ".variance")
+            names += [base + ".lengthscale"] if len(f.lengthscale) == 1 else \
+                ["%s.lengthscale[%d]" % (base, d) for d in range(len(f.lengthscale))]
+        return names
+
+    def _scatter_gradient(self, g):
+        """g = (d/dvariance, d/dl_0 .. d/dl_{D-1}) of the combined component."""
+        total = float(np.prod([float(f.variance) for f in self.factors]))
+        o = 1
+        for f in self.factors:
+            f.variance.gradient = float(g[0]) * total / float(f.variance)
+            if f.ARD:
+                for d in range(f.input_dim):
+                    f.lengthscale[d].gradient = float(g[o + d])
+            else:
+                f.lengthscale[0].gradient = float(np.sum(g[o:o + f.input_dim]))
+            o += f.input_dim

@@ -19,7 +19,7 @@ import numpy as np
 import scipy.optimize as sopt
 
 from .engine import HelmholtzGP, LinAlgError, ScalarGP, SpaceTimeGP
-from .kern import RBF, Add, _ScalarKern
+from .kern import RBF, Add, Prod, _ScalarKern
 from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase, Kt, SpaceTimeKern
 from .params import Param
 
@@ -290,7 +290,12 @@ class GPRegression:
               "constraints": [p.constraint for p in self.parameters],
               "X": self.X, "Y": self.Y, "jitter": self.jitter,
               "runs": [r.__dict__ for r in self.optimization_runs]}
-        if self.scalar:
+        if self.scalar and isinstance(k, Prod):
+            # X is stored already sliced to k.active_dims: factor columns become positions in that list
+            st["factors"] = [{"input_dim": f.input_dim, "ARD": f.ARD, "name": f.name,
+                              "dims": [k.active_dims.index(d) for d in f.active_dims]} for f in k.factors]
+            st["active_dims"] = list(range(self.X.shape[1]))
+        elif self.scalar:
             st["parts"] = [{"input_dim": p.input_dim, "ARD": p.ARD, "name": p.name} for p in k.parts_list()]
             st["active_dims"] = list(range(self.X.shape[1]))      # X is stored already sliced
         elif self.spacetime:
@@ -320,6 +325,20 @@ def load(path, device=None):
                "nonRotK": lambda: nonRotK(2, [1, 2], p[2])}[st["space"]]()
         k = Kt(1, [0], p[0], p[1]) * kxy
         m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
+        for prm, c in zip(m.parameters, st["constraints"]):
+            prm.constraint = c
+        for d in st["runs"]:
+            r = _Run(None, None, None, None)
+            r.__dict__.update(d)
+            m.optimization_runs.append(r)
+        return m
+    if "factors" in st:
+        fs, o = [], 0
+        for d in st["factors"]:
+            nl = d["input_dim"] if d["ARD"] else 1
+            fs.append(RBF(d["input_dim"], p[o], p[o + 1:o + 1 + nl], ARD=d["ARD"], active_dims=d["dims"], name=d["name"]))
+            o += 1 + nl
+        m = GPRegression(st["X"], st["Y"], Prod(fs), noise_var=p[-1], jitter=st["jitter"], device=device)
         for prm, c in zip(m.parameters, st["constraints"]):
             prm.constraint = c
         for d in st["runs"]:

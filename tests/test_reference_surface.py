@@ -249,3 +249,73 @@ def test_krig_workflow(tmp_path):
     assert 0 < rv < 0.5 and 0 < ru < 0.5
     with pytest.raises(ValueError):
         krig.make_kernel(5)
+
+
+# ---- physical invariants and the reference's own end-to-end example ---------------------------------------------
+def test_divergence_free_kernel_gives_divergence_free_mean():
+    """SURVEY.md §4 'physical invariants' (report.tex:74-82): the posterior mean of the
+    divergence-free kernel has zero divergence, that of the curl-free kernel zero curl --
+    whatever the data.  Checked with centred differences on a fine grid against the size of the
+    velocity gradients themselves."""
+    rng = np.random.default_rng(7)
+    X = rng.uniform(-1, 1, (60, 2))
+    y = rng.normal(size=120)                                    # arbitrary data: the property is structural
+    h = 1e-3
+    g = np.linspace(-0.8, 0.8, 21)
+    GX, GY = np.meshgrid(g, g)
+    P = np.stack([GX.ravel(), GY.ravel()], axis=1)
+    pts = np.concatenate([P + [h, 0], P - [h, 0], P + [0, h], P - [0, h]])
+    for ratio, which in ((1.0, "div"), (0.0, "curl")):
+        m = gp.HelmholtzGP(X, y, 0.5, 0.5, ratio, 0.01)
+        m.fit()
+        mean, _ = m.predict(pts)
+        mean = mean.cpu().numpy()
+        n = pts.shape[0]
+        u, v = mean[:n].reshape(4, -1), mean[n:].reshape(4, -1)
+        ux, uy = (u[0] - u[1]) / (2 * h), (u[2] - u[3]) / (2 * h)
+        vx, vy = (v[0] - v[1]) / (2 * h), (v[2] - v[3]) / (2 * h)
+        scale = np.sqrt(np.mean(ux ** 2 + uy ** 2 + vx ** 2 + vy ** 2))
+        resid = (ux + vy) if which == "div" else (vx - uy)
+        assert np.max(np.abs(resid)) < 1e-5 * scale, (which, np.max(np.abs(resid)), scale)
+        other = (vx - uy) if which == "div" else (ux + vy)
+        assert np.max(np.abs(other)) > 1e-2 * scale                 # the other quantity is not constrained
+
+
+def test_run_example3_reconstructs_the_synthetic_field():
+    """GP_plots.run_example3 (GP_plots.py:705-779) end to end: product-of-RBF models per component and
+    the joint Helmholtz model after optimize_restarts; the vector kernel, which knows the field is
+    divergence-free, reconstructs it better from the same samples."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "run_example3", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "run_example3.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    rmsug, rmsvg, rmsfu, rmsfv, u_HP, v_HP, f_HP = ex.run_example3(nsamples=30, divFree=1, rms=1, num_restarts=3, seed=1)
+    x, y, phi, xm, ym, um, vm = GP_scripts.generate_2D_gaussian(1)
+    amp = np.sqrt(np.mean(um ** 2 + vm ** 2))
+    assert rmsfu < 0.05 * amp and rmsfv < 0.05 * amp
+    assert rmsfu + rmsfv < rmsug + rmsvg
+    assert u_HP.size == 5 and f_HP.size == 4
+    # the kernel has no amplitude parameter: the prior variances of its two parts are ratio / l_df^2 and
+    # (1 - ratio) / l_cf^2, and the fit puts (almost) all of it on the divergence-free part
+    w_df, w_cf = f_HP[2] / f_HP[0] ** 2, (1 - f_HP[2]) / f_HP[1] ** 2
+    assert w_df > 100 * w_cf
+
+
+def test_product_of_rbf_kernels_is_an_ard_rbf(tmp_path):
+    from gp2d_b200 import kern
+    rng = np.random.default_rng(2)
+    X = rng.uniform(0, 1, (50, 2))
+    y = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) + 0.01 * rng.normal(size=50)
+    k = kern.RBF(1, active_dims=[0], variance=2.0, lengthscale=0.3) * kern.RBF(1, active_dims=[1], variance=1.5, lengthscale=0.5)
+    np.testing.assert_allclose(k.K(X), orc.rbf_sum_K(X, None, [3.0], [[0.3, 0.5]]), rtol=1e-13, atol=1e-15)
+    m = models.GPRegression(X, y[:, None], k, noise_var=0.01)
+    lo, go = orc.rbf_lml_and_grad(X, y, [3.0], [[0.3, 0.5]], 0.01, jitter=1e-8)
+    assert abs(m.log_likelihood() - lo) <= 1e-6 * abs(lo)
+    # d/dv1 = v2 d/dvar, d/dv2 = v1 d/dvar (the product's variance is v1 v2)
+    np.testing.assert_allclose([p.gradient for p in m.parameters], [go[0] * 1.5, go[1], go[0] * 2.0, go[2], go[3]], rtol=1e-6, atol=1e-7)
+    p = str(tmp_path / "prod.pkl")
+    m.pickle(p)
+    m2 = models.load(p)
+    np.testing.assert_array_equal(m2.param_array, m.param_array)
+    assert m2.log_likelihood() == pytest.approx(m.log_likelihood(), rel=1e-12)
