@@ -259,6 +259,16 @@ struct PotriSide {
         ok = true;
         return true;
     }
+    // worker threads (concurrent restarts) come and go: give the streams back when the thread ends;
+    // at process exit the context may already be gone, errors are ignored
+    ~PotriSide() {
+        if (!ok) return;
+        for (int i = 0; i < POTRI_MAX_DEPTH; ++i) {
+            cudaStreamDestroy(stream[i]);
+            cudaEventDestroy(forked[i]);
+            cudaEventDestroy(joined[i]);
+        }
+    }
 };
 static thread_local PotriSide g_side;
 static bool g_potri_overlap = true;

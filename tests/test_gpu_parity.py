@@ -483,3 +483,41 @@ def test_no_writes_outside_buffers_rbf(N, M, D, Q):
     mo, vo = orc.rbf_predict(X, f, var_h, ls_h, Xs, var_add=0.01)
     np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-8 * max(np.abs(mo).max(), 1e-3))
     np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+
+
+def test_config3_full_size_properties():
+    """BASELINE.json configs[2]: N=16384 observations (32768 x 32768 fp64 covariance).  The oracle
+    cannot factorise this in test time, so parity rests on size-independent properties: the GP
+    identity K alpha = y - noise alpha at observation sites (ties covariance build, Cholesky, L^-1,
+    alpha and the predictive mean together), the interpolation property of the variance, bounds,
+    grid-partition invariance, and agreement of the two likelihood entry points."""
+    N = 16384
+    X, y = synthetic.drifter_snapshot(N, config_id=3)
+    theta, noise = (1.3, 3.1, 0.2), 0.05
+    m = gp.HelmholtzGP(X, y, *theta, noise)
+    lml = m.fit()
+    assert np.isfinite(lml)
+    sel = np.random.default_rng(0).choice(N, 512, replace=False)
+    pm, pv = m.predict(X[sel])
+    al = m.alpha()
+    idx = torch.as_tensor(sel, device=DEV)
+    rhs = torch.cat([m.y[idx], m.y[N + idx]]) - noise * torch.cat([al[idx], al[N + idx]])
+    torch.testing.assert_close(pm, rhs, rtol=1e-9, atol=1e-11)
+    # at an observation site var = k** - k*' (K + noise I)^-1 k*  lies in (0, noise): the data pin the field
+    # down to better than the noise level, never exactly
+    kss = orc.helmholtz_Kdiag(1, *theta)[0]
+    assert float(pv.min()) > 0.0 and float(pv.max()) < noise
+    # far outside the observations the prior variance is recovered
+    far = X.max(axis=0) + np.array([[60.0, 60.0], [90.0, 10.0]])
+    fm, fv = m.predict(far)
+    torch.testing.assert_close(fv, torch.full_like(fv, kss), rtol=1e-9, atol=0)
+    assert float(fm.abs().max()) < 1e-9
+    # partition invariance, bit for bit (one 600-point shard vs two)
+    G = synthetic.prediction_grid(X, 30, 20)
+    ma, va = m.predict(G)
+    m1, v1 = m.predict(G[:217])
+    m2, v2 = m.predict(G[217:])
+    assert torch.equal(torch.cat([m1[:217], m2[:383], m1[217:], m2[383:]]), ma)
+    assert torch.equal(torch.cat([v1[:217], v2[:383], v1[217:], v2[383:]]), va)
+    lml2, grad = m.lml_and_grad()
+    assert lml2 == lml and np.all(np.isfinite(grad))
