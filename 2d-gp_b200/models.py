@@ -75,6 +75,23 @@ class GPRegression:
         self._ll = None
         self.parameters_changed()          # GPy evaluates the likelihood in the constructor
 
+    # ---- GPy attribute idioms ---------------------------------------------------------------
+    def __setattr__(self, name, value):
+        # ``model.Gaussian_noise = 1.7e-7`` sets the value of the parameter (laser_io_methods.py:497,503)
+        if name == "Gaussian_noise" and "Gaussian_noise" in self.__dict__ and not isinstance(value, Param):
+            self.__dict__["Gaussian_noise"].value = float(np.asarray(value).reshape(-1)[0])
+            if "_gp" in self.__dict__:
+                self.parameters_changed()
+            return
+        object.__setattr__(self, name, value)
+
+    def __getattr__(self, name):
+        # ``model.rbf.lengthscale[0]`` / ``model.myKern.ratio``: the kernel under its GPy name
+        kern = self.__dict__.get("kern")
+        if kern is not None and name == getattr(kern, "name", None):
+            return kern
+        raise AttributeError(name)
+
     # ---- parameters -----------------------------------------------------------------------
     @property
     def parameters(self):

@@ -64,6 +64,10 @@ class Param:
     __rtruediv__ = lambda s, o: float(o) / s.value
     __pow__ = lambda s, o: s.value ** o
     __neg__ = lambda s: -s.value
+    __lt__ = lambda s, o: s.value < float(o)
+    __le__ = lambda s, o: s.value <= float(o)
+    __gt__ = lambda s, o: s.value > float(o)
+    __ge__ = lambda s, o: s.value >= float(o)
 
     # --- unconstrained <-> constrained (GPy Logexp / Logistic transforms) -------------------
     def to_free(self):

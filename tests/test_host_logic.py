@@ -55,6 +55,7 @@ def test_param_behaves_like_a_float():
     assert p * 2 == 5.0 and 2 * p == 5.0 and p ** 2 == 6.25 and 1 / p == 0.4
     p.gradient = 3.0
     assert p.gradient == 3.0
+    assert p > 2 and p >= 2.5 and p < 3 and p <= 2.5 and -p == -2.5
     f = Param("x", 1.0).constrain_fixed(4.0)
     f.from_free(9.0)
     assert f.value == 4.0

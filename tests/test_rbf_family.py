@@ -186,3 +186,26 @@ def test_krig_scalar_workflow_and_scikit_prior(tmp_path):
     fnc = netcdf_file(outFile, "r", mmap=False)
     np.testing.assert_allclose(fnc.variables["u"].data.reshape(-1), mo.astype(np.float32), rtol=1e-5, atol=1e-6)
     fnc.close()
+
+
+def test_one_dimensional_track_model_with_gpy_idioms():
+    """The per-drifter 1-D GP of laser_io_methods.interp_kriging (laser_io_methods.py:464-531):
+    RBF(input_dim=1, variance, lengthscale) over time, noise set by assignment, predict, optimize,
+    then ``model.rbf.lengthscale[0]`` / ``model.Gaussian_noise[0]`` read back."""
+    rng = np.random.default_rng(3)
+    t = np.sort(rng.uniform(0, 48, 90))[:, None]
+    lon = (-88.0 + 0.01 * t[:, 0] + 0.02 * np.sin(t[:, 0] / 6.0) + 1e-4 * rng.normal(size=90))[:, None]
+    k = kern.RBF(input_dim=1, variance=1159.68, lengthscale=4.5)
+    m = models.GPRegression(t, lon, k)
+    m.Gaussian_noise = 1.75598244486e-07
+    assert m.Gaussian_noise[0] == 1.75598244486e-07
+    tg = np.arange(1.0, 47.0, 0.25)[:, None]
+    mean, var = m.predict(tg)
+    f = orc.rbf_fit(t, lon[:, 0], [1159.68], [[4.5]], 1.75598244486e-07, jitter=1e-8)
+    mo, vo = orc.rbf_predict(t, f, [1159.68], [[4.5]], tg, var_add=1.75598244486e-07)
+    # cond(K) ~ 1e10 here (variance 1e3 against noise 1e-7): compare at the accuracy the problem allows
+    np.testing.assert_allclose(mean[:, 0], mo, rtol=0, atol=1e-4)
+    assert np.all(var > 0)
+    m.optimize(max_iters=20)
+    assert m.rbf.lengthscale[0] > 0 and m.rbf.variance[0] > 0 and m.Gaussian_noise[0] > 0
+    assert m.rbf is m.kern
