@@ -7,7 +7,7 @@ namespace gp2d {
 
 constexpr int TILE = 128;      // every internal matrix dimension is padded to a multiple of this
 constexpr int BK = 16;         // k-depth of one shared-memory stage (doubles)
-constexpr int NTHREADS = 256;  // default CTA: 8 warps, 2 (M) x 4 (N), warp tile 64 x 32
+constexpr int NTHREADS = 256;  // CTA of the leaf / probe kernels (the GEMM-shaped kernels define their own shapes)
 // CTA shapes: NT threads = (NT/128) warps along M x 4 warps along N over a 128 x 128 tile;
 // a warp owns MB(NT) x 4 DMMA accumulator blocks (8 x 8 each): 64x32 at NT=256, 32x32 at NT=512.
 __host__ __device__ constexpr int warps_m(int nt) { return nt / 128; }

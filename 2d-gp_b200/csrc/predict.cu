@@ -1,20 +1,23 @@
-// Fused predictive pass.  A persistent CTA owns a tile of 64 grid points (128 stacked
-// columns) at a time and runs two phases on it:
-//   1. generate the K* panel [npad x 128] ONCE (1-2 exps per point pair give the four
-//      entries of a 2x2 block thanks to the pair-interleaved internal ordering), store it
-//      into the CTA's private scratch panel (written once, re-read from L2 by every row
-//      block) and accumulate mean = K* alpha on the way;
-//   2. V = Z K*^T on the DMMA pipe (Z = L^-1), row block after row block, with both
-//      operands streamed by cp.async; the column sums of V^2 stay in registers, so
-//      var = k** - colsumsq(V) needs no atomics, no partial buffers and is bit-reproducible.
+// Fused predictive pass.  Persistent CTAs (one per SM: 8 consumer warps + 1 producer warp) take work
+// items (column tile, split); a column tile is 64 grid points x 2 components = 128 stacked columns
+// (128 grid points for the scalar family).  Two phases per item:
+//   1. the consumer warps generate the K* panel [npad x 128] ONCE (1-2 exps per point pair give the
+//      four entries of a 2x2 block thanks to the pair-interleaved internal ordering), already in the
+//      swizzled shared-memory tile image, into the CTA's private scratch panel, and accumulate
+//      mean = K* alpha on the way (observations staged through shared memory, branch-free pair loop);
+//   2. V = Z K*^T on the DMMA pipe (Z = L^-1), row block after row block: one producer thread
+//      streams 16 KB tiles of Zt and of the panel with bulk copies into a 6-stage mbarrier ring,
+//      the consumers keep a 128 x 128 accumulator tile in registers and fold sum(v^2) per row
+//      block into fixed row-block groups, so var = k** - colsumsq(V) needs no atomics and is
+//      bit-reproducible for any grid size, partition or split.
 // Replaces GPy model.predict (krig.py:543-544; GP_plots.py:768), GP_scripts.getMean +
 // the diagonal of GP_laser.py:129-131, and sklearn predict(return_std=True)
 // (krig.py:194; algebra of _gpr.py:446-491).
 //
 // Why a scratch panel: DMMA and DFMA share one FP64 pipe on sm_100a (measured: 37 TF/s
 // each, 36 TF/s mixed).  Regenerating K* tiles inside the k-loop of every row block cost
-// 2 x (n/256) exps per pair and 20% of the kernel; generating once costs < 1% and the
-// re-reads (n/256 x 1 KB per panel row, from L2) ride on otherwise idle bandwidth.
+// 2 x (n/256) exps per pair and 20% of the kernel; generating once costs ~1% and the
+// re-reads (once per row block, from L2 / DRAM) use 15 % of the DRAM bandwidth.
 // The full K* (n x 2M) still never exists: only one [npad x 128] panel per resident CTA.
 #include "common.cuh"
 #include "dgemm.cuh"
