@@ -33,6 +33,65 @@ def load_tracks(path="simulTracks.pkl", class_dir=None):
         return pickle.load(f, encoding="latin1")
 
 
+def laser(ts=20, nsteps=8, l_df=5, l_cf=5, tau=1, rate=0.5, noise=0.0025, nsamples=1, tracks=None,
+          path="interp_ALL_2016_2_7.pkl"):
+    """GP_laser.laser (GP_laser.py:16-142) on the GPU: LASER drifter tracks (positions, velocities,
+    drogue status on a 15-minute grid) -> observations of ``nsteps`` time steps from ``ts`` ->
+    every third one kept for the fit, the rest for verification -> posterior mean and variance on
+    a 0.5 km grid and the mean at the verification points.
+
+    Host side as in the reference: undrogued samples and |u|,|v| > 2 m/s dropped, EPSG:3452
+    projection to km, origin shifted to (2, 2) km.  Device side: one fit, one fused predictive pass
+    for the grid (mean and marginal variance: the reference forms the full 2M x 2M ``Kss`` and
+    ``Cov`` only to take their diagonals, GP_laser.py:128-131) and one for the verification points.
+    ``tracks`` may carry the unpickled ``interpolated_tracks`` object (the LASER pickle is not
+    shipped upstream).  Returns x, y, uf, vf, xo, yo, uo, vo, uvar, vvar, xt, yt, ut, vt, uft, vft."""
+    from .projection import NAD83
+    tr = tracks if tracks is not None else load_tracks(path, os.path.dirname(os.path.abspath(path)))
+    st = 0
+    et = st + (96 * 7) + 1
+    latt, lont = np.array(tr.lat)[:, st:et], np.array(tr.lon)[:, st:et]
+    drogue = np.array(tr.drogueStat)[:, st:et]
+    uob, vob = np.array(tr.u, dtype=np.float64)[:, st:et], np.array(tr.v, dtype=np.float64)[:, st:et]
+    uob[np.where(drogue == 0)] = np.nan
+    vob[np.where(drogue == 0)] = np.nan
+    xob, yob = NAD83(lont, latt)                       # NaN positions stay NaN
+    xo = np.reshape(xob[:, ts:ts + nsteps], [-1]) / 1000.
+    yo = np.reshape(yob[:, ts:ts + nsteps], [-1]) / 1000.
+    uo = np.reshape(uob[:, ts:ts + nsteps], [-1])
+    vo = np.reshape(vob[:, ts:ts + nsteps], [-1])
+    with np.errstate(invalid="ignore"):
+        uo[np.where(np.abs(uo) > 2)] = np.nan
+        vo[np.where(np.abs(vo) > 2)] = np.nan
+    ok = np.where((~np.isnan(uo)) & (~np.isnan(vo)) & (~np.isnan(xo)) & (~np.isnan(yo)))
+    uo, vo, xo, yo = uo[ok], vo[ok], xo[ok], yo[ok]
+    xo = xo - xo.min() + 2
+    yo = yo - yo.min() + 2
+    if nsamples > 0:
+        samples = np.arange(0, xo.size, 3)
+        test = np.array(sorted(set(range(xo.size)) - set(samples)), dtype=int)
+        xt, yt, ut, vt = xo[test], yo[test], uo[test], vo[test]
+        xo, yo, uo, vo = xo[samples], yo[samples], uo[samples], vo[samples]
+    else:
+        xt = yt = ut = vt = np.array([0])
+    dx = 0.5
+    x = np.arange(np.min([xo.min(), xt.min()]) - 5, np.max([xo.max(), xt.max()]) + 5, dx)
+    y = np.arange(np.min([yo.min(), yt.min()]) - 5, np.max([yo.max(), yt.max()]) + 5, dx)
+    X, Y = np.meshgrid(x, y)
+    Xs = np.stack([np.reshape(X, [X.size]), np.reshape(Y, [Y.size])], axis=1)
+    gp = HelmholtzGP(np.stack([xo, yo], axis=1), np.concatenate([uo, vo]), l_df, l_cf, rate, noise)
+    gp.fit()
+    mean, var = gp.predict(Xs)
+    f, var = mean.cpu().numpy(), var.cpu().numpy()
+    uf, vf = np.reshape(f[:f.size // 2], [y.size, -1]), np.reshape(f[f.size // 2:], [y.size, -1])
+    uvar, vvar = np.reshape(var[:X.size], [y.size, -1]), np.reshape(var[X.size:], [y.size, -1])
+    ft = gp.predict(np.stack([xt, yt], axis=1))[0].cpu().numpy()
+    return x, y, uf, vf, xo, yo, uo, vo, uvar, vvar, xt, yt, ut, vt, ft[:ft.size // 2], ft[ft.size // 2:]
+
+
+laser2 = laser          # GP_laser.laser2 (GP_laser.py:195-321) is a verbatim copy of laser upstream
+
+
 def simLaser(ts=0, l_df=2, l_cf=2, rate=0.5, noise=0.05, tracks=None, path="simulTracks.pkl",
              simlaser_compat=False, return_var=False):
     """Returns X, Y, uf, vf, xob, yob, u, v like the reference (plus uvar, vvar on request).

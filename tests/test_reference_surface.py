@@ -319,3 +319,37 @@ def test_product_of_rbf_kernels_is_an_ard_rbf(tmp_path):
     m2 = models.load(p)
     np.testing.assert_array_equal(m2.param_array, m.param_array)
     assert m2.log_likelihood() == pytest.approx(m.log_likelihood(), rel=1e-12)
+
+
+def test_laser_workflow_on_synthetic_tracks():
+    """GP_laser.laser (GP_laser.py:16-142) with an injected tracks object: the reference's explicit-
+    inverse pipeline (compute_K, inv, compute_Ks, getMean, diag of Kss - Ks Ki Ks^T) restated by the
+    oracle on the same filtered observations."""
+    rng = np.random.default_rng(12)
+    nd, nt = 45, 40
+    lat = 28.8 + rng.uniform(0.0, 0.25, size=(nd, 1)) + 0.0005 * np.arange(nt)[None, :]
+    lon = -88.55 + rng.uniform(0.0, 0.25, size=(nd, 1)) + 0.0004 * np.arange(nt)[None, :]
+    u = 0.3 * np.sin(25 * (lat - 28.8)) + rng.normal(0, 0.02, size=lat.shape)
+    v = 0.3 * np.cos(25 * (lon + 88.55)) + rng.normal(0, 0.02, size=lat.shape)
+    drogue = np.ones((nd, nt))
+    drogue[3, :] = 0                      # an undrogued drifter is dropped
+    u[5, 22] = 3.5                        # a spike above 2 m/s is dropped
+    lat[7, 21], lon[7, 21] = np.nan, np.nan
+    tr = types.SimpleNamespace(lat=lat, lon=lon, u=u, v=v, drogueStat=drogue, time=np.arange(nt) * 900.0)
+    out = GP_laser.laser(ts=20, nsteps=4, l_df=5, l_cf=4, rate=0.4, noise=0.0025, nsamples=1, tracks=tr)
+    x, y, uf, vf, xo, yo, uo, vo, uvar, vvar, xt, yt, ut, vt, uft, vft = out
+    n_all = (nd - 1) * 4 - 2              # one drifter out, one spike, one missing position
+    assert xo.size == len(range(0, n_all, 3)) and xt.size == n_all - xo.size
+    assert xo.min() >= 2.0 and uf.shape == (y.size, x.size) and uvar.shape == uf.shape
+    X = np.stack([xo, yo], axis=1)
+    Xg, Yg = np.meshgrid(x, y)
+    Xs = np.stack([Xg.reshape(-1), Yg.reshape(-1)], axis=1)
+    mo, vo_ = orc.fit_predict_inverse_form(X, np.concatenate([uo, vo]), 5, 4, 0.4, 0.0025, Xs)
+    M = Xs.shape[0]
+    scale = np.abs(mo).max()
+    np.testing.assert_allclose(uf.reshape(-1), mo[:M], rtol=1e-7, atol=1e-8 * scale)
+    np.testing.assert_allclose(vf.reshape(-1), mo[M:], rtol=1e-7, atol=1e-8 * scale)
+    np.testing.assert_allclose(uvar.reshape(-1), vo_[:M], rtol=1e-6, atol=1e-10)
+    mt, _ = orc.fit_predict_inverse_form(X, np.concatenate([uo, vo]), 5, 4, 0.4, 0.0025, np.stack([xt, yt], axis=1), want_var=False)
+    np.testing.assert_allclose(np.concatenate([uft, vft]), mt, rtol=1e-7, atol=1e-8 * scale)
+    assert GP_laser.laser2 is GP_laser.laser
