@@ -46,3 +46,25 @@ def case(name, HP, N=180, M=90, seed=11):
 if __name__ == "__main__":
     case("sklearn_rbf1", np.array([0.09, 8.0, 4.0, 5.0, 0.0009]))
     case("sklearn_rbf2", np.array([0.05, 20.0, 6.0, 7.0, 0.02, 3.0, 1.5, 2.0, 0.0009]), seed=12)
+
+
+def optimised_case():
+    """scikit-learn's default behaviour (optimizer='fmin_l_bfgs_b'; testKrig.py:139-140): the
+    hyper-parameters are fitted by maximising the log-marginal likelihood over log(theta)."""
+    rng = np.random.default_rng(21)
+    N, M = 150, 60
+    XT = np.stack([rng.uniform(0, 12, N), rng.uniform(0, 15, N), rng.uniform(-5, 15, N)], axis=1)
+    u = (0.3 * np.sin(XT[:, 1] / 3.0) * np.cos(XT[:, 2] / 4.0) + 0.05 * XT[:, 0] / 12.0 + rng.normal(0, 0.03, N))
+    Xg = np.stack([np.full(M, 6.0), rng.uniform(1, 15, M), rng.uniform(-5, 15, M)], axis=1)
+    k = 0.1 * kernels.RBF(length_scale=[5.0, 3.0, 3.0]) + kernels.WhiteKernel(noise_level=0.01)
+    m = GaussianProcessRegressor(kernel=k, n_restarts_optimizer=0).fit(XT, u)
+    U, Ustd = m.predict(Xg, return_std=True)
+    np.savez_compressed(os.path.join(HERE, "sklearn_rbf_opt.npz"), XT=XT, u=u, Xg=Xg,
+                        start=np.array([0.1, 5.0, 3.0, 3.0, 0.01]), ref_theta=m.kernel_.theta,
+                        ref_lml=m.log_marginal_likelihood_value_, ref_mean=U, ref_var=Ustd ** 2,
+                        sklearn_version=sklearn.__version__)
+    print("sklearn_rbf_opt", m.kernel_, m.log_marginal_likelihood_value_)
+
+
+if __name__ == "__main__":
+    optimised_case()

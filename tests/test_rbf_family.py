@@ -63,7 +63,7 @@ def test_sklearn_pipeline_as_scikit_prior_builds_it(gold):
     np.testing.assert_allclose(Ustd ** 2, gold["ref_var"], rtol=1e-8)
     assert abs(m.log_marginal_likelihood_value_ - float(gold["ref_lml"])) <= 1e-6 * abs(float(gold["ref_lml"]))
     with pytest.raises(NotImplementedError):
-        GaussianProcessRegressor(kernel=k, optimizer="fmin_l_bfgs_b")
+        GaussianProcessRegressor(kernel=k, optimizer="my_optimizer")
 
 
 def test_lml_gradient_matches_sklearn(gold):
@@ -209,3 +209,24 @@ def test_one_dimensional_track_model_with_gpy_idioms():
     m.optimize(max_iters=20)
     assert m.rbf.lengthscale[0] > 0 and m.rbf.variance[0] > 0 and m.Gaussian_noise[0] > 0
     assert m.rbf is m.kern
+
+
+def test_sklearn_default_optimizer_reaches_sklearns_optimum(golden_dir):
+    """scikit-learn's default (optimizer='fmin_l_bfgs_b'; testKrig.py:139-140): maximise the LML over
+    log(theta) from the kernel's initial values.  Same start, same bounds, same optimiser: the search
+    ends in scikit-learn's optimum (golden from live scikit-learn)."""
+    g = np.load(os.path.join(golden_dir, "sklearn_rbf_opt.npz"))
+    s = g["start"]
+    k = s[0] * kernels.RBF(length_scale=[s[1], s[2], s[3]]) + kernels.WhiteKernel(noise_level=s[4])
+    m = GaussianProcessRegressor(kernel=k, n_restarts_optimizer=0).fit(g["XT"], g["u"])
+    assert abs(m.log_marginal_likelihood_value_ - float(g["ref_lml"])) <= 1e-6 * abs(float(g["ref_lml"]))
+    np.testing.assert_allclose(m.theta_, g["ref_theta"], rtol=0, atol=2e-3)
+    U, Ustd = m.predict(g["Xg"], return_std=True)
+    assert U.shape == (g["Xg"].shape[0],)
+    np.testing.assert_allclose(U, g["ref_mean"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(Ustd ** 2, g["ref_var"], rtol=1e-3)
+    # the initial kernel object is left untouched, as in scikit-learn
+    assert k.k2.noise_level == s[4]
+    # restarts only ever improve on it
+    m2 = GaussianProcessRegressor(kernel=k, n_restarts_optimizer=2, random_state=0).fit(g["XT"], g["u"])
+    assert m2.log_marginal_likelihood_value_ >= m.log_marginal_likelihood_value_ - 1e-9
