@@ -26,6 +26,18 @@ constexpr int TILE_DOUBLES = TILE * BK;   // 2048 doubles = 16 KB per operand st
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Function attributes (opt-in shared memory) are per device: remember which devices were set up.
+// Racing first calls repeat an idempotent cudaFuncSetAttribute, nothing worse.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    // returns the device slot to initialise, or -1 when this device is already set up
+    int pending() const {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+        return done[dev] ? -1 : dev;
+    }
+};
+
 // ---- cp.async (LDGSTS) -------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -37,8 +37,9 @@ static cudaError_t gemm_attr_ws() {
 }
 
 cudaError_t dgemm_init() {
-    static bool done = false;
-    if (done) return cudaSuccess;
+    static PerDeviceOnce once;
+    const int slot = once.pending();
+    if (slot < 0) return cudaSuccess;
     cudaError_t e;
     if ((e = gemm_attr64<false, false>()) != cudaSuccess) return e;
     if ((e = gemm_attr64<false, true>()) != cudaSuccess) return e;
@@ -48,7 +49,7 @@ cudaError_t dgemm_init() {
     if ((e = gemm_attr_ws<false, true>()) != cudaSuccess) return e;
     if ((e = gemm_attr_ws<true, true>()) != cudaSuccess) return e;
     if ((e = gemm_attr_ws<true, false>()) != cudaSuccess) return e;
-    done = true;
+    once.done[slot] = true;
     return cudaSuccess;
 }
 
@@ -342,11 +343,12 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
                         bool need_inv, bool keep_L, double* W, cudaStream_t st) {
     if (n % TILE || n <= 0) return cudaErrorInvalidValue;
-    static bool leaf_init = false;
-    if (!leaf_init) {
+    static PerDeviceOnce leaf_once;
+    const int slot = leaf_once.pending();
+    if (slot >= 0) {
         cudaError_t e0 = cudaFuncSetAttribute(potri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
         if (e0 != cudaSuccess) return e0;
-        leaf_init = true;
+        leaf_once.done[slot] = true;
     }
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;

@@ -463,11 +463,12 @@ size_t predict_scratch_bytes(int npad, int M, int pts_per_tile) {
 
 template <int FAM>
 static cudaError_t predict_launch(PredictArgs& a, double* scratch, size_t scratch_bytes, cudaStream_t st) {
-    static bool init = false;
-    if (!init) {
+    static PerDeviceOnce once;
+    const int slot = once.pending();
+    if (slot >= 0) {
         cudaError_t e = cudaFuncSetAttribute(predict_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        init = true;
+        once.done[slot] = true;
     }
     constexpr int PTS = FAM == FAM_HELM ? 64 : 128;
     a.ntiles = (a.M + PTS - 1) / PTS;

@@ -521,3 +521,24 @@ def test_config3_full_size_properties():
     assert torch.equal(torch.cat([v1[:217], v2[:383], v1[217:], v2[383:]]), va)
     lml2, grad = m.lml_and_grad()
     assert lml2 == lml and np.all(np.isfinite(grad))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """Function attributes, side streams and SM counts are set up per device: a model on cuda:1 in
+    a process that already used cuda:0 gives the same bits."""
+    X, y = synthetic.drifter_snapshot(600, config_id=13)
+    Xs = synthetic.prediction_grid(X, 40, 30)
+    a = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05, device="cuda:0")
+    la, ga = a.lml_and_grad()
+    ma, va = a.predict(Xs)
+    b = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05, device="cuda:1")
+    lb, gb = b.lml_and_grad()
+    mb, vb = b.predict(Xs)
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert la == lb and np.array_equal(ga, gb)
+    assert torch.equal(ma.cpu(), mb.cpu()) and torch.equal(va.cpu(), vb.cpu())
+    g = gp.ScalarGP(np.c_[X, X[:, :1]], y[:600], [0.5], [[2.0, 2.0, 3.0]], 0.01, device="cuda:1")
+    g.fit()
+    assert g.predict(np.c_[Xs, Xs[:, :1]])[0].device.index == 1
