@@ -221,6 +221,8 @@ def test_simlaser_fit_predict(golden_dir, ts):
 
 
 @pytest.mark.parametrize("N,M,theta", [(1, 3, THETAS[0]), (7, 1, THETAS[1]), (64, 64, THETAS[0]),
+                                       (16, 70, THETAS[1]), (40, 65, THETAS[2]), (48, 129, THETAS[1]), (80, 64, THETAS[3]),
+                                       (1040, 300, THETAS[1]), (1072, 90, THETAS[0]),
                                        (65, 130, THETAS[1]), (300, 517, THETAS[2]), (513, 200, THETAS[3])])
 def test_fit_predict_vs_oracle(N, M, theta):
     X, y = synthetic.drifter_snapshot(N, config_id=9, seed_offset=N)
