@@ -360,6 +360,9 @@ def run_ours(args):
                 "cholesky_TFLOPps": (n ** 3 / 3.0) / t_potrf / 1e12,
                 "cholesky_frac_of_fp64_peak": (n ** 3 / 3.0) / t_potrf / 1e12 / peak_tf,
                 "potrf_ms": t_potrf * 1e3, "build_ms": t_build * 1e3,
+                "note": "at configs[1] size both probes are latency-bound (a 128 MB build is one 25 us launch; the "
+                        "Cholesky of a 4000 x 4000 matrix is a chain of 32 diagonal blocks and ~120 small GEMMs); the "
+                        "stage targets of BASELINE.json are quoted at N=16384, see targets_at_N16384",
             },
             "targets_at_N16384": {
                 "what": "BASELINE.json north-star stage targets, measured at configs[2] size (n=32768) on this GPU",
