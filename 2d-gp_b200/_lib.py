@@ -66,6 +66,20 @@ SIGNATURES = {
                                    c_dp, c_dp, C.c_void_p, C.c_size_t, c_st]),
     "gp2d_rbf_lml_grad": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double,
                                     C.c_void_p, C.c_size_t, c_dp, c_ip, c_st]),
+    "gp2d_hsum_kernel_build": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_dp, C.c_double, c_dp,
+                                         C.c_int64, c_st]),
+    "gp2d_hsum_kdiag": (C.c_int, [C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_st]),
+    "gp2d_hsum_kernel_grad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gp2d_hsum_kernel_grad": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, C.c_int64,
+                                        C.c_void_p, C.c_size_t, c_dp, c_st]),
+    "gp2d_hsum_fit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gp2d_hsum_fit_predict_state": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "gp2d_hsum_fit": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_dp, C.c_double, C.c_double,
+                                C.c_void_p, C.c_size_t, c_dp, c_dp, c_ip, c_st]),
+    "gp2d_hsum_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, C.c_int, C.c_int64,
+                                    C.c_double, c_dp, c_dp, C.c_void_p, C.c_size_t, c_st]),
+    "gp2d_hsum_lml_grad": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_dp, C.c_double, C.c_double,
+                                     C.c_void_p, C.c_size_t, c_dp, c_ip, c_st]),
     "gp2d_fit_predict_host": (C.c_int, [c_dp, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_double, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
 }

@@ -701,6 +701,181 @@ int gp2d_rbf_lml_grad(const double* X, int N, int D, const double* y, int Q, con
     return 0;
 }
 
+/* ---- sum of space-time Helmholtz terms (hsum.cuh; krig.py:396-407) ------------------------------- */
+
+namespace {
+FitLayout hsum_layout(int N, int ldx, int Q) {
+    return fit_layout_general(2 * (size_t)N, (size_t)ldx * N, hsum_lml_grad_partial_doubles(round_up(2 * N, TILE), Q));
+}
+
+cudaError_t hsum_fit_core(const double* X, int N, const double* y, const HsumParams& sp, double diag_add, void* ws,
+                          const FitLayout& L, cudaStream_t st) {
+    double* A = at<double>(ws, L.off_A);
+    double* Z = at<double>(ws, L.off_Z);
+    cudaError_t e;
+    e = cudaMemcpyAsync(at<double>(ws, L.off_X), X, (size_t)sp.ldx * N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = hsum_build_interleaved_lower(X, N, sp, diag_add, A, L.npad, L.npad, st);
+    if (e != cudaSuccess) return e;
+    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
+                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    if (e != cudaSuccess) return e;
+    e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
+    if (e != cudaSuccess) return e;
+    return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+                           at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
+                           at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+}
+}  // namespace
+
+int gp2d_hsum_kernel_build(const double* X, int N, const double* X2, int M, int ldx, int Q, const int* type,
+                           const double* params, double diag_add, double* K, int64_t ldk, void* stream) {
+    if (!X) return -1;
+    if (N < 0) return -2;
+    if (M < 0 || (X2 == nullptr && M != N)) return -4;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -5;
+    if (!K && N > 0 && M > 0) return -10;
+    if (ldk < 2 * (int64_t)M) return -11;
+    return cuda_rc(hsum_build_block_layout(X, N, X2, M, sp, diag_add, K, (long)ldk, (cudaStream_t)stream));
+}
+
+int gp2d_hsum_kdiag(int M, int ldx, int Q, const int* type, const double* params, double* out, void* stream) {
+    if (M < 0) return -1;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -2;
+    if (M == 0) return 0;
+    if (!out) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    fill_kernel<<<(M + 255) / 256, 256, 0, st>>>(out, M, sp.kss0);
+    fill_kernel<<<(M + 255) / 256, 256, 0, st>>>(out + M, M, sp.kss1);
+    return cuda_rc(cudaGetLastError());
+}
+
+size_t gp2d_hsum_kernel_grad_workspace_bytes(int N, int M, int Q) {
+    if (N <= 0 || M <= 0 || Q < 1 || Q > HSUM_MAXQ) return 256;
+    return align256(sizeof(double) * HSUM_NP * (size_t)Q * (size_t)grad_sums_block_partials(N, M));
+}
+
+int gp2d_hsum_kernel_grad(const double* X, int N, const double* X2, int M, int ldx, int Q, const int* type,
+                          const double* params, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                          double* out, void* stream) {
+    if (!X) return -1;
+    if (N <= 0) return -2;
+    if (M <= 0 || (X2 == nullptr && M != N)) return -4;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -5;
+    if (!dL_dK) return -9;
+    if (ld < 2 * (int64_t)M) return -10;
+    if (!ws || ws_bytes < gp2d_hsum_kernel_grad_workspace_bytes(N, M, Q)) return -12;
+    if (!out) return -13;
+    return cuda_rc(hsum_grad_sums(X, N, X2, M, sp, dL_dK, (long)ld, (double*)ws, ws_bytes / sizeof(double), out,
+                                  (cudaStream_t)stream));
+}
+
+size_t gp2d_hsum_fit_workspace_bytes(int N, int ldx, int Q) {
+    if (!size_ok(2L * N) || (ldx != 2 && ldx != 3) || Q < 1 || Q > HSUM_MAXQ) return 0;
+    return hsum_layout(N, ldx, Q).total;
+}
+
+int gp2d_hsum_fit_predict_state(int N, int ldx, int Q, size_t* offset, size_t* bytes) {
+    if (N <= 0) return -1;
+    if (ldx != 2 && ldx != 3) return -2;
+    if (Q < 1 || Q > HSUM_MAXQ) return -3;
+    if (!offset) return -4;
+    if (!bytes) return -5;
+    FitLayout L = hsum_layout(N, ldx, Q);
+    *offset = L.off_Zt;
+    *bytes = L.total - L.off_Zt;
+    return 0;
+}
+
+int gp2d_hsum_fit(const double* X, int N, int ldx, const double* y, int Q, const int* type, const double* params,
+                  double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out, double* lml_out,
+                  int* info, void* stream) {
+    if (!X) return -1;
+    if (!size_ok(2L * N)) return -2;
+    if (!y) return -4;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -5;
+    if (!(noise >= 0.0)) return -8;
+    if (!(jitter >= 0.0)) return -9;
+    FitLayout L = hsum_layout(N, ldx, Q);
+    if (!ws) return -10;
+    if (ws_bytes < L.total) return -11;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = hsum_fit_core(X, N, y, sp, noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (alpha_out) {
+        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (lml_out) {
+        e = cudaMemcpyAsync(lml_out, at<double>(ws, L.off_scal), sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
+int gp2d_hsum_predict(const void* fit_ws, int N, int ldx, int Q, const int* type, const double* params,
+                      const double* Xs, int M, int64_t out_stride, double var_add, double* mean, double* var,
+                      void* ws, size_t ws_bytes, void* stream) {
+    if (!fit_ws) return -1;
+    if (!size_ok(2L * N)) return -2;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -3;
+    if (M < 0) return -8;
+    if (M == 0) return 0;
+    if (!Xs) return -7;
+    if (out_stride < M) return -9;
+    if (!mean) return -11;
+    if (!var) return -12;
+    FitLayout L = hsum_layout(N, ldx, Q);
+    if (!ws) return -13;
+    if (ws_bytes < predict_panel_bytes(L.npad)) return -14;
+    return cuda_rc(predict_fused_hsum(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
+                                      at<double>(fit_ws, L.off_X), N, sp, Xs, M, (long)out_stride, var_add, mean, var,
+                                      (double*)ws, ws_bytes, (cudaStream_t)stream));
+}
+
+int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, const int* type, const double* params,
+                       double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream) {
+    if (!X) return -1;
+    if (!size_ok(2L * N)) return -2;
+    if (!y) return -4;
+    HsumParams sp;
+    if (!make_hsum(ldx, Q, type, params, &sp)) return -5;
+    if (!(noise >= 0.0)) return -8;
+    if (!(jitter >= 0.0)) return -9;
+    FitLayout L = hsum_layout(N, ldx, Q);
+    if (!ws) return -10;
+    if (ws_bytes < L.total) return -11;
+    if (!out) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = hsum_fit_core(X, N, y, sp, noise + jitter, ws, L, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* Z = at<double>(ws, L.off_Z);
+    double* Kinv = at<double>(ws, L.off_A);
+    e = launch_dgemm(true, true, GemmArgs{Z, L.npad, Z, L.npad, Kinv, L.npad, L.npad, L.npad, L.npad, 1.0, 0.0, 1, KR_GE_M}, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    double* scal = at<double>(ws, L.off_scal);
+    // the gradient goes straight to the caller's buffer: out = (LML, d/d(var, lt, la, lb)_q ..., d/dnoise)
+    e = hsum_lml_grad_reduce(Kinv, L.npad, L.npad, at<double>(ws, L.off_alpha), at<double>(ws, L.off_X), N, sp,
+                             at<double>(ws, L.off_partial), out + 1, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemcpyAsync(out, scal, sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (info) {
+        e = cudaMemcpyAsync(info, at<int>(ws, L.off_info), sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return 0;
+}
+
 int gp2d_fit_predict_host(const double* X, int N, const double* y, double l_df, double l_cf,
                           double ratio, double noise, double jitter, const double* Xs, int M,
                           int include_noise, double* mean, double* var, double* lml) {

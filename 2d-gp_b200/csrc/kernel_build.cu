@@ -10,8 +10,19 @@
 #include "linalg.h"
 #include "reduce.cuh"
 #include "rbf.cuh"
+#include "hsum.cuh"
 
 namespace gp2d {
+
+// the two matrix-valued families share the build kernels: points and 2x2 blocks by overload
+__device__ __forceinline__ HelmPoint kp_point(const HelmParams& p, const double* __restrict__ X, long i) { return helm_point(p, X, i); }
+__device__ __forceinline__ HelmPoint kp_point(const HsumParams& p, const double* __restrict__ X, long i) { return hsum_point(p, X, i); }
+__device__ __forceinline__ void kp_block(const HelmParams& p, const HelmPoint& x, const HelmPoint& y, double& k11, double& k12, double& k22) {
+    helm_block_pts(p, x, y, k11, k12, k22);
+}
+__device__ __forceinline__ void kp_block(const HsumParams& p, const HelmPoint& x, const HelmPoint& y, double& k11, double& k12, double& k22) {
+    hsum_block_pts(p, x, y, k11, k12, k22);
+}
 
 // ---------------------------------------------------------------------------------------
 // reference block layout
@@ -19,25 +30,25 @@ namespace gp2d {
 // ---------------------------------------------------------------------------------------
 constexpr int BB_J = 128, BB_I = 32;
 
-template <bool VEC>
+template <bool VEC, class KP>
 __global__ void __launch_bounds__(256)
 build_block_kernel(const double* __restrict__ X, int N, const double* __restrict__ X2, int M,
-                   HelmParams hp, double diag_add, int symmetric, double* __restrict__ K, long ldk) {
+                   const __grid_constant__ KP hp, double diag_add, int symmetric, double* __restrict__ K, long ldk) {
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j0 = blockIdx.x * BB_J + tx * 2;
     const int i0 = blockIdx.y * BB_I + ty * 8;
     if (j0 >= M) return;
     const bool has1 = (j0 + 1 < M);
-    const HelmPoint q0 = helm_point(hp, X2, j0);
-    const HelmPoint q1 = has1 ? helm_point(hp, X2, j0 + 1) : q0;
+    const HelmPoint q0 = kp_point(hp, X2, j0);
+    const HelmPoint q1 = has1 ? kp_point(hp, X2, j0 + 1) : q0;
 #pragma unroll 2
     for (int r = 0; r < 8; ++r) {
         const int i = i0 + r;
         if (i >= N) break;
-        const HelmPoint pa = helm_point(hp, X, i);
+        const HelmPoint pa = kp_point(hp, X, i);
         double a11, a12, a22, b11, b12, b22;
-        helm_block_pts(hp, pa, q0, a11, a12, a22);
-        helm_block_pts(hp, pa, q1, b11, b12, b22);
+        kp_block(hp, pa, q0, a11, a12, a22);
+        kp_block(hp, pa, q1, b11, b12, b22);
         if (symmetric) {
             if (i == j0) { a11 += diag_add; a22 += diag_add; }
             if (i == j0 + 1) { b11 += diag_add; b22 += diag_add; }
@@ -56,24 +67,35 @@ build_block_kernel(const double* __restrict__ X, int N, const double* __restrict
     }
 }
 
-cudaError_t build_block_layout(const double* X, int N, const double* X2, int M, const HelmParams& hp,
-                               double diag_add, double* K, long ldk, cudaStream_t st) {
+template <class KP>
+static cudaError_t build_block_layout_t(const double* X, int N, const double* X2, int M, const KP& hp,
+                                        double diag_add, double* K, long ldk, cudaStream_t st) {
     if (N <= 0 || M <= 0) return cudaSuccess;
     const int symmetric = (X2 == nullptr);
     if (symmetric) X2 = X;
     dim3 grid((M + BB_J - 1) / BB_J, (N + BB_I - 1) / BB_I);
     const bool vec = (M % 2 == 0) && (ldk % 2 == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
-    if (vec) build_block_kernel<true><<<grid, 256, 0, st>>>(X, N, X2, M, hp, diag_add, symmetric, K, ldk);
-    else build_block_kernel<false><<<grid, 256, 0, st>>>(X, N, X2, M, hp, diag_add, symmetric, K, ldk);
+    if (vec) build_block_kernel<true, KP><<<grid, 256, 0, st>>>(X, N, X2, M, hp, diag_add, symmetric, K, ldk);
+    else build_block_kernel<false, KP><<<grid, 256, 0, st>>>(X, N, X2, M, hp, diag_add, symmetric, K, ldk);
     return cudaGetLastError();
+}
+
+cudaError_t build_block_layout(const double* X, int N, const double* X2, int M, const HelmParams& hp,
+                               double diag_add, double* K, long ldk, cudaStream_t st) {
+    return build_block_layout_t(X, N, X2, M, hp, diag_add, K, ldk, st);
+}
+cudaError_t hsum_build_block_layout(const double* X, int N, const double* X2, int M, const HsumParams& hp,
+                                    double diag_add, double* K, long ldk, cudaStream_t st) {
+    return build_block_layout_t(X, N, X2, M, hp, diag_add, K, ldk, st);
 }
 
 // ---------------------------------------------------------------------------------------
 // internal layout: pair-interleaved, padded, lower tiles.  One CTA per 128x128 tile
 // (64x64 point pairs); a warp writes 512 contiguous bytes per matrix row.
 // ---------------------------------------------------------------------------------------
+template <class KP>
 __global__ void __launch_bounds__(256)
-build_interleaved_kernel(const double* __restrict__ X, int N, HelmParams hp, double diag_add,
+build_interleaved_kernel(const double* __restrict__ X, int N, const __grid_constant__ KP hp, double diag_add,
                          double* __restrict__ K, long ldk) {
     int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
@@ -83,13 +105,13 @@ build_interleaved_kernel(const double* __restrict__ X, int N, HelmParams hp, dou
     const int jj = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = J * 64 + jj;
     const bool jv = j < N;
-    const HelmPoint qb = helm_point(hp, X, jv ? j : 0);
+    const HelmPoint qb = kp_point(hp, X, jv ? j : 0);
 #pragma unroll 4
     for (int ii = ty; ii < 64; ii += 4) {
         const int i = I * 64 + ii;
         double k11, k12, k22;
         if (jv && i < N) {
-            helm_block_pts(hp, helm_point(hp, X, i), qb, k11, k12, k22);
+            kp_block(hp, kp_point(hp, X, i), qb, k11, k12, k22);
             if (i == j) { k11 += diag_add; k22 += diag_add; }
         } else {
             k12 = 0.0;
@@ -104,7 +126,13 @@ build_interleaved_kernel(const double* __restrict__ X, int N, HelmParams hp, dou
 cudaError_t build_interleaved_lower(const double* X, int N, const HelmParams& hp, double diag_add,
                                     double* K, long ldk, int npad, cudaStream_t st) {
     const int T = npad / TILE;
-    build_interleaved_kernel<<<T * (T + 1) / 2, 256, 0, st>>>(X, N, hp, diag_add, K, ldk);
+    build_interleaved_kernel<HelmParams><<<T * (T + 1) / 2, 256, 0, st>>>(X, N, hp, diag_add, K, ldk);
+    return cudaGetLastError();
+}
+cudaError_t hsum_build_interleaved_lower(const double* X, int N, const HsumParams& hp, double diag_add,
+                                         double* K, long ldk, int npad, cudaStream_t st) {
+    const int T = npad / TILE;
+    build_interleaved_kernel<HsumParams><<<T * (T + 1) / 2, 256, 0, st>>>(X, N, hp, diag_add, K, ldk);
     return cudaGetLastError();
 }
 
@@ -289,6 +317,52 @@ cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(out, full, (hp.has_t ? 5 : 3) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// sum of space-time Helmholtz terms (hsum.cuh): out[Q][4] = sum(dK/d(var, lt, la, lb)_q * dL_dK).
+// grid (column blocks, row blocks, Q): one term per z-slice, so the accumulator count is fixed.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hsum_grad_sums_kernel(const double* __restrict__ X, int N, const double* __restrict__ X2, int M,
+                      const __grid_constant__ HsumParams hp, const double* __restrict__ W, long ld,
+                      double* __restrict__ partial) {
+    __shared__ double sh[HSUM_NP * 32];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int j = blockIdx.x * GS_J + tx;
+    const HsumTerm term = hp.t[blockIdx.z];
+    double acc[HSUM_NP] = {0.0, 0.0, 0.0, 0.0};
+    if (j < M) {
+        const HelmPoint qb = hsum_point(hp, X2, j);
+        for (int r = 0; r < 8; ++r) {
+            const int i = blockIdx.y * GS_I + ty * 8 + r;
+            if (i >= N) break;
+            const HelmPoint pa = hsum_point(hp, X, i);
+            const double d1 = pa.a - qb.a, d2 = pa.b - qb.b, dt = pa.t - qb.t;
+            const double* w0 = W + (long)i * ld + j;
+            const double* w1 = W + ((long)N + i) * ld + j;
+            hsum_term_grad(term, dt * dt, d1 * d1, d2 * d2, d1 * d2, w0[0], w0[M] + w1[0], w1[M], acc);
+        }
+    }
+    block_reduce<HSUM_NP>(acc, sh);
+    if (threadIdx.x == 0) {
+        const long nblk = (long)gridDim.x * gridDim.y;
+        double* o = partial + HSUM_NP * (blockIdx.z * nblk + (long)blockIdx.y * gridDim.x + blockIdx.x);
+#pragma unroll
+        for (int p = 0; p < HSUM_NP; ++p) o[p] = acc[p];
+    }
+}
+
+// partial holds HSUM_NP * Q * grad_sums_block_partials(N, M) doubles
+cudaError_t hsum_grad_sums(const double* X, int N, const double* X2, int M, const HsumParams& hp, const double* dL_dK,
+                           long ld, double* partial, size_t partial_doubles, double* out, cudaStream_t st) {
+    if (X2 == nullptr) X2 = X;
+    dim3 grid((M + GS_J - 1) / GS_J, (N + GS_I - 1) / GS_I, hp.Q);
+    const int count = grid.x * grid.y;
+    if ((size_t)HSUM_NP * count * hp.Q > partial_doubles) return cudaErrorInvalidValue;
+    hsum_grad_sums_kernel<<<grid, 256, 0, st>>>(X, N, X2, M, hp, dL_dK, ld, partial);
+    strided_final_reduce_kernel<HSUM_NP><<<hp.Q, 1024, 0, st>>>(partial, count, out, HSUM_NP);
+    return cudaGetLastError();
 }
 
 }  // namespace gp2d

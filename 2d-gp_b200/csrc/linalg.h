@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "helmholtz.cuh"
 #include "rbf.cuh"
+#include "hsum.cuh"
 
 namespace gp2d {
 
@@ -52,6 +53,15 @@ int rbf_grad_partials(int N, int M);
 cudaError_t rbf_grad_sums(const double* X, int N, const double* X2, int M, const RbfParams& rp, const double* dL_dK,
                           long ld, double* partial, int partial_cap, double* out, cudaStream_t st);
 
+// sum of space-time Helmholtz terms (hsum.cuh): same layouts as the Helmholtz entry points above;
+// out[Q][4] = sum(dK/d(var, lt, la, lb)_q * dL_dK), partial holds 4 Q grad_sums_block_partials doubles
+cudaError_t hsum_build_block_layout(const double* X, int N, const double* X2, int M, const HsumParams& hp,
+                                    double diag_add, double* K, long ldk, cudaStream_t st);
+cudaError_t hsum_build_interleaved_lower(const double* X, int N, const HsumParams& hp, double diag_add,
+                                         double* K, long ldk, int npad, cudaStream_t st);
+cudaError_t hsum_grad_sums(const double* X, int N, const double* X2, int M, const HsumParams& hp, const double* dL_dK,
+                           long ld, double* partial, size_t partial_doubles, double* out, cudaStream_t st);
+
 // predict.cu ------------------------------------------------------------------------------
 // scratch: one [npad x 128] K* panel per resident CTA (at most one CTA per SM is launched;
 // fewer panels only reduce the grid).
@@ -65,6 +75,10 @@ size_t predict_scratch_bytes(int npad, int M, int pts_per_tile);   // full paral
 cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, const double* X, int N,
                               const RbfParams& rp, const double* Xs, int M, double var_add, double* mean,
                               double* var, double* scratch, size_t scratch_bytes, cudaStream_t st);
+// sum of space-time Helmholtz terms: same tiles and ordering as predict_fused
+cudaError_t predict_fused_hsum(const double* Zt, int npad, const double* alpha_int, const double* X, int N,
+                               const HsumParams& sp, const double* Xs, int M, long out_stride, double var_add,
+                               double* mean, double* var, double* scratch, size_t scratch_bytes, cudaStream_t st);
 int predict_max_ctas();
 void set_predict_split(int s);          // bring-up override: 1, 2, 4, 8 (0 = heuristic)
 
@@ -78,5 +92,10 @@ int lml_grad_partials(int npad);
 int rbf_lml_grad_partial_doubles(int npad);
 cudaError_t rbf_lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha, const double* X, int N,
                                 const RbfParams& rp, double* partial, double* out, cudaStream_t st);
+
+// sum of space-time Helmholtz terms: out[4 Q + 1] = d LML / d(var, lt, la, lb)_q, then d LML / d noise
+size_t hsum_lml_grad_partial_doubles(int npad, int Q);
+cudaError_t hsum_lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha_int, const double* X, int N,
+                                 const HsumParams& hp, double* partial, double* out, cudaStream_t st);
 
 }  // namespace gp2d

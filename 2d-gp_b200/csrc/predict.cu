@@ -34,9 +34,10 @@ struct PredictArgs {
     const double* X; int N;       // observation points [N,2] (Helmholtz) or [N,D] (RBF)
     HelmParams hp;
     RbfParams rp;
+    HsumParams sp; int use_hsum;  // FAM_HELM tiles with the term-sum generator (hsum.cuh)
     const double* Xs; int M;
     long out_stride;              // component stride of mean/var
-    double kss, var_add;
+    double kss, kss1, var_add;    // prior variance of component 0 (and of the scalar family) / component 1
     double* mean; double* var;
     double* scratch;              // gridDim.x panels of npad x 128 doubles
     double* partial;              // [ntiles][8 groups][128] column sums (nsplit > 1)
@@ -56,7 +57,8 @@ constexpr int PRED_MAX_ROWBLOCKS = 1024;          // npad <= 131072
 constexpr int PRED_STAGE_OBS = 256;                // observations staged in shared memory at a time (phase 1)
 constexpr int PRED_PARAM_DOUBLES = 64;             // shared-memory copy of HelmParams / RbfParams
 constexpr int PRED_RED_DOUBLES = PRED_GROUPS * 2 * TILE + 4 * 64 * 2 + PRED_MAX_ROWBLOCKS / 2 + 5 * PRED_STAGE_OBS + PRED_PARAM_DOUBLES;
-static_assert(sizeof(HelmParams) <= PRED_PARAM_DOUBLES * sizeof(double) && sizeof(RbfParams) <= PRED_PARAM_DOUBLES * sizeof(double), "parameter block");
+static_assert(sizeof(HelmParams) <= PRED_PARAM_DOUBLES * sizeof(double) && sizeof(RbfParams) <= PRED_PARAM_DOUBLES * sizeof(double) &&
+              sizeof(HsumParams) <= PRED_PARAM_DOUBLES * sizeof(double), "parameter block");
 constexpr int PRED_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES + PRED_RED_DOUBLES * (int)sizeof(double);
 
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(WS_CONSUMERS) : "memory"); }
@@ -214,6 +216,83 @@ __device__ __noinline__ void helm_phase1(const PredictArgs& p, const HelmParams&
     }
 }
 
+// Sum of space-time Helmholtz terms: same thread mapping and panel image as helm_phase1_loop; one
+// exponential per term and pair.  NQ > 0: compile-time term count (unrolled); NQ == 0: run-time loop.
+template <int NQ, bool HAS_T>
+__device__ __forceinline__ void hsum_phase1_loop(const PredictArgs& p, const HsumParams& sp, double* __restrict__ panel,
+                                                 double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+    constexpr int OS = WS_CONSUMERS / 64;
+    const int gjl = tid & 63, os = tid >> 6;
+    const int gj = gp0 + gjl;
+    const double wg = gj < p.M ? 1.0 : 0.0;
+    const HelmPoint gpt = hsum_point(sp, p.Xs, gj < p.M ? gj : 0);
+    const int nobs_pad = p.npad >> 1;
+    const int nq = NQ > 0 ? NQ : sp.Q;
+    double m0 = 0.0, m1 = 0.0;
+    for (int ob = 0; ob < nobs_pad; ob += PRED_STAGE_OBS) {
+        consumer_barrier();                     // the previous batch has been read
+        {
+            const int o = ob + tid;
+            const bool ov = o < p.N;
+            const HelmPoint q = hsum_point(sp, p.X, ov ? o : 0);
+            stage[tid * 5 + 0] = q.a;
+            stage[tid * 5 + 1] = q.b;
+            stage[tid * 5 + 2] = q.t;
+            stage[tid * 5 + 3] = ov ? __ldg(p.alpha + 2 * o) : 0.0;
+            stage[tid * 5 + 4] = ov ? __ldg(p.alpha + 2 * o + 1) : 0.0;
+        }
+        consumer_barrier();
+        const int nloc = min(PRED_STAGE_OBS, nobs_pad - ob);
+#pragma unroll 2
+        for (int ol = os; ol < nloc; ol += OS) {
+            const int o = ob + ol;
+            const double d1 = stage[ol * 5 + 0] - gpt.a, d2 = stage[ol * 5 + 1] - gpt.b;
+            const double a = d1 * d1, b = d2 * d2, c = d1 * d2;
+            double dt2 = 0.0;
+            if (HAS_T) {
+                const double dt = stage[ol * 5 + 2] - gpt.t;
+                dt2 = dt * dt;
+            }
+            double k11 = 0.0, k12 = 0.0, k22 = 0.0;
+            if (NQ > 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) hsum_term_add(sp.t[q], dt2, a, b, c, k11, k12, k22);
+            } else {
+                for (int q = 0; q < nq; ++q) hsum_term_add(sp.t[q], dt2, a, b, c, k11, k12, k22);
+            }
+            const double w = o < p.N ? wg : 0.0;
+            k11 *= w; k12 *= w; k22 *= w;
+            const double a0 = stage[ol * 5 + 3], a1 = stage[ol * 5 + 4];
+            m0 = fma(k11, a0, fma(k12, a1, m0));
+            m1 = fma(k12, a0, fma(k22, a1, m1));
+            double* r0 = panel + (size_t)(2 * o) * TILE;
+            const int sw = (o & 1) << 2;
+            *reinterpret_cast<double2*>(r0 + 2 * (gjl ^ sw)) = make_double2(k11, k12);
+            *reinterpret_cast<double2*>(r0 + TILE + 2 * (gjl ^ (sw | 2))) = make_double2(k12, k22);
+        }
+    }
+    fence_proxy_async();      // the panel is read back by bulk (async-proxy) copies
+    mu0 = m0;
+    mu1 = m1;
+}
+
+__device__ __noinline__ void hsum_phase1(const PredictArgs& p, const HsumParams& sp, double* __restrict__ panel,
+                                         double* __restrict__ stage, int gp0, int tid, double& mu0, double& mu1) {
+    if (sp.has_t) {
+        switch (sp.Q) {
+            case 1: hsum_phase1_loop<1, true>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+            case 2: hsum_phase1_loop<2, true>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+            default: hsum_phase1_loop<0, true>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+        }
+    } else {
+        switch (sp.Q) {
+            case 1: hsum_phase1_loop<1, false>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+            case 2: hsum_phase1_loop<2, false>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+            default: hsum_phase1_loop<0, false>(p, sp, panel, stage, gp0, tid, mu0, mu1); break;
+        }
+    }
+}
+
 // 8 consumer warps (phase 1 + DMMA) and one producer warp (bulk-copy ring), see pipeline.cuh.
 // FAM selects the covariance family of phase 1: the matrix-valued Helmholtz kernel (a column tile
 // is 64 grid points x 2 components) or the scalar ARD-RBF sum (a column tile is 128 grid points).
@@ -247,8 +326,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
     fb.init(wn, lane);
     wb.init(tid, 1);
     {
-        const double* src = FAM == FAM_HELM ? reinterpret_cast<const double*>(&p.hp) : reinterpret_cast<const double*>(&p.rp);
-        const int nd = (int)((FAM == FAM_HELM ? sizeof(HelmParams) : sizeof(RbfParams)) / sizeof(double));
+        const bool hsum = FAM == FAM_HELM && p.use_hsum;
+        const double* src = FAM == FAM_RBF ? reinterpret_cast<const double*>(&p.rp)
+                            : hsum ? reinterpret_cast<const double*>(&p.sp) : reinterpret_cast<const double*>(&p.hp);
+        const int nd = (int)((FAM == FAM_RBF ? sizeof(RbfParams) : hsum ? sizeof(HsumParams) : sizeof(HelmParams)) / sizeof(double));
         if (tid < nd) sh_par[tid] = src[tid];
     }
     __syncthreads();
@@ -265,6 +346,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
         double mu0 = 0.0, mu1 = 0.0;
         if (!producer) {
             if (FAM == FAM_RBF) rbf_phase1(p, *reinterpret_cast<const RbfParams*>(sh_par), panel, sh_stage, gp0, tid, mu0, mu1);
+            else if (p.use_hsum) hsum_phase1(p, *reinterpret_cast<const HsumParams*>(sh_par), panel, sh_stage, gp0, tid, mu0, mu1);
             else helm_phase1(p, *reinterpret_cast<const HelmParams*>(sh_par), panel, sh_stage, gp0, tid, mu0, mu1);
         }
         // the item's row blocks in processing order (both roles walk this list)
@@ -376,7 +458,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
                 if (j < p.M) {
                     double ss = 0.0;
                     for (int g = 0; g < PRED_GROUPS; ++g) ss += sh_grp[g * WM * TILE + tid] + sh_grp[g * WM * TILE + TILE + tid];
-                    double v = p.kss - ss;
+                    double v = (FAM == FAM_HELM && c ? p.kss1 : p.kss) - ss;
                     v = v < 0.0 ? 0.0 : v;
                     p.var[oidx] = v + p.var_add;
                 }
@@ -406,7 +488,7 @@ __global__ void __launch_bounds__(TILE) predict_finish_kernel(PredictArgs p) {
     if (j >= p.M) return;
     double ss = 0.0;
     for (int g = 0; g < PRED_GROUPS; ++g) ss += p.partial[((size_t)ct * PRED_GROUPS + g) * TILE + tid];
-    double v = p.kss - ss;
+    double v = (FAM == FAM_HELM && c ? p.kss1 : p.kss) - ss;
     v = v < 0.0 ? 0.0 : v;
     p.var[oidx] = v + p.var_add;
 }
@@ -502,7 +584,19 @@ cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
     PredictArgs a{};
     a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
-    a.kss = hp.tvar * (hp.w_df + hp.w_cf);   // ratio/l_df^2 + (1-ratio)/l_cf^2 (myKernel.py:55-57), times the time variance
+    a.kss = a.kss1 = hp.tvar * (hp.w_df + hp.w_cf);   // ratio/l_df^2 + (1-ratio)/l_cf^2 (myKernel.py:55-57), times the time variance
+    a.var_add = var_add; a.mean = mean; a.var = var;
+    return predict_launch<FAM_HELM>(a, scratch, scratch_bytes, st);
+}
+
+cudaError_t predict_fused_hsum(const double* Zt, int npad, const double* alpha_int, const double* X, int N,
+                               const HsumParams& sp, const double* Xs, int M, long out_stride, double var_add,
+                               double* mean, double* var, double* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    PredictArgs a{};
+    a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.sp = sp; a.use_hsum = 1;
+    a.Xs = Xs; a.M = M; a.out_stride = out_stride;
+    a.kss = sp.kss0; a.kss1 = sp.kss1;
     a.var_add = var_add; a.mean = mean; a.var = var;
     return predict_launch<FAM_HELM>(a, scratch, scratch_bytes, st);
 }
@@ -514,7 +608,7 @@ cudaError_t predict_fused_rbf(const double* Zt, int npad, const double* alpha, c
     PredictArgs a{};
     a.Zt = Zt; a.npad = npad; a.alpha = alpha; a.X = X; a.N = N; a.rp = rp;
     a.Xs = Xs; a.M = M; a.out_stride = M;
-    a.kss = rp.kss;
+    a.kss = a.kss1 = rp.kss;
     a.var_add = var_add; a.mean = mean; a.var = var;
     return predict_launch<FAM_RBF>(a, scratch, scratch_bytes, st);
 }

@@ -40,4 +40,21 @@ __global__ void final_reduce_kernel(const double* __restrict__ partial, int coun
         for (int q = 0; q < NV; ++q) out[q] = acc[q];
 }
 
+// one CTA per term: out[q][0..NV) = sum over that term's `count` partial rows
+template <int NV>
+__global__ void strided_final_reduce_kernel(const double* __restrict__ partial, int count, double* __restrict__ out, int out_stride) {
+    __shared__ double sh[NV * 32];
+    const double* src = partial + (size_t)blockIdx.x * count * NV;
+    double acc[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] += src[(long)i * NV + q];
+    block_reduce<NV>(acc, sh);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) out[(long)blockIdx.x * out_stride + q] = acc[q];
+}
+
 }  // namespace gp2d

@@ -537,6 +537,177 @@ class ScalarGP:
         return self.lml, host[1:1 + ng].copy()
 
 
+# ------------------------------------------------------------------------------------------
+# sum of space-time Helmholtz terms (krig.py:396-407: myKernel2.divFreeK / curlFreeK, their sum,
+# nKernels copies)
+# ------------------------------------------------------------------------------------------
+HSUM_MAXQ = 8
+
+
+def _hsum_params(types, params):
+    """Host arrays type[Q] (0 divergence-free, 1 curl-free) and params[Q,4] = (var, lt, la, lb)."""
+    ty = np.ascontiguousarray(np.atleast_1d(np.asarray(types)).astype(np.int32))
+    pr = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=np.float64)))
+    Q = int(ty.shape[0])
+    if not (1 <= Q <= HSUM_MAXQ):
+        raise ValueError("between 1 and %d terms" % HSUM_MAXQ)
+    if pr.shape != (Q, 4):
+        raise ValueError("params must be [Q,4] rows (var, lt, la, lb)")
+    if np.any((ty != 0) & (ty != 1)):
+        raise ValueError("term types are 0 (divergence-free) or 1 (curl-free)")
+    return ty, pr, Q
+
+
+def _points23(X, device=None) -> torch.Tensor:
+    t = as_dev(X, device)
+    if t.dim() != 2 or t.shape[1] not in (2, 3):
+        raise ValueError("points must be [N,2] rows (a, b) or [N,3] rows (t, a, b)")
+    return t
+
+
+def hsum_K(X, X2, types, params, diag_add=0.0) -> torch.Tensor:
+    """[2N,2M] block matrix of the term sum (device tensor)."""
+    Xd = _points23(X)
+    X2d = None if X2 is None else _points23(X2, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    ldx = int(Xd.shape[1])
+    if X2d is not None and X2d.shape[1] != ldx:
+        raise ValueError("X and X2 must have the same number of columns")
+    ty, pr, Q = _hsum_params(types, params)
+    out = torch.empty((2 * N, 2 * M), dtype=torch.float64, device=Xd.device)
+    if N and M:
+        with torch.cuda.device(Xd.device):
+            check(lib.gp2d_hsum_kernel_build(_ptr(Xd), N, _ptr(X2d), M, ldx, Q, ty.ctypes.data, pr.ctypes.data, diag_add,
+                                             _ptr(out), out.stride(0), _stream()), "gp2d_hsum_kernel_build")
+    return out
+
+
+def hsum_Kdiag(M, ldx, types, params, device=None) -> torch.Tensor:
+    ty, pr, Q = _hsum_params(types, params)
+    dev = device or _device()
+    out = torch.empty(2 * M, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gp2d_hsum_kdiag(M, ldx, Q, ty.ctypes.data, pr.ctypes.data, _ptr(out), _stream()), "gp2d_hsum_kdiag")
+    return out
+
+
+def hsum_grad_sums(dL_dK, X, X2, types, params) -> torch.Tensor:
+    """sum(dK/d(var, lt, la, lb)_q * dL_dK) -> device tensor [Q,4]."""
+    Xd = _points23(X)
+    X2d = None if X2 is None else _points23(X2, Xd.device)
+    N, M = Xd.shape[0], (Xd.shape[0] if X2d is None else X2d.shape[0])
+    ldx = int(Xd.shape[1])
+    ty, pr, Q = _hsum_params(types, params)
+    W = as_dev(dL_dK, Xd.device)
+    if tuple(W.shape) != (2 * N, 2 * M):
+        raise ValueError("dL_dK must be [2N,2M]")
+    nb = lib.gp2d_hsum_kernel_grad_workspace_bytes(N, M, Q)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    out = torch.empty((Q, 4), dtype=torch.float64, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        check(lib.gp2d_hsum_kernel_grad(_ptr(Xd), N, _ptr(X2d), M, ldx, Q, ty.ctypes.data, pr.ctypes.data, _ptr(W),
+                                        W.stride(0), _ptr(ws), nb, _ptr(out), _stream()), "gp2d_hsum_kernel_grad")
+    return out
+
+
+class HelmholtzSumGP:
+    """Fit state of a GP whose covariance is a sum of divergence-free / curl-free space-time terms;
+    same life cycle as HelmholtzGP through gp2d_hsum_*.  Points [N,2] (a, b) or [N,3] (t, a, b)."""
+
+    def __init__(self, X, y, types, params, noise, jitter=0.0, device=None):
+        self.X = _points23(X, device)
+        self.N, self.ldx = int(self.X.shape[0]), int(self.X.shape[1])
+        self.y = as_dev(y, self.X.device).reshape(-1)
+        if self.y.numel() != 2 * self.N:
+            raise ValueError("y must stack both components: length 2N")
+        self.set_params(types, params, noise)
+        self.jitter = float(jitter)
+        self.ws_bytes = lib.gp2d_hsum_fit_workspace_bytes(self.N, self.ldx, self.Q)
+        if not self.ws_bytes:
+            raise ValueError("problem size out of range")
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.X.device)
+        self._scal = torch.zeros(2 + 4 * HSUM_MAXQ, dtype=torch.float64, device=self.X.device)
+        self._info = torch.zeros(1, dtype=torch.int32, device=self.X.device)
+        self._pws = None
+        self.lml = None
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def set_params(self, types, params, noise):
+        ty, pr, Q = _hsum_params(types, params)
+        if getattr(self, "Q", Q) != Q:
+            raise ValueError("the number of terms is fixed at construction (workspace layout)")
+        self.types, self.params, self.Q = ty, pr, Q
+        self.noise = float(noise)
+        self.fitted = False
+
+    def fit_async(self, alpha_out=None):
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_hsum_fit(_ptr(self.X), self.N, self.ldx, _ptr(self.y), self.Q, self.types.ctypes.data,
+                                    self.params.ctypes.data, self.noise, self.jitter, _ptr(self.ws), self.ws_bytes,
+                                    _ptr(alpha_out), _ptr(self._scal), _ptr(self._info), _stream()), "gp2d_hsum_fit")
+        self.fitted = True
+
+    def fit(self):
+        self.fit_async()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(self._scal[0].item())
+        return self.lml
+
+    def alpha(self) -> torch.Tensor:
+        out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
+        self.fit_async(alpha_out=out)
+        return out
+
+    def predict_state(self) -> torch.Tensor:
+        import ctypes as C
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(lib.gp2d_hsum_fit_predict_state(self.N, self.ldx, self.Q, C.byref(off), C.byref(nb)),
+              "gp2d_hsum_fit_predict_state")
+        return self.ws[off.value:off.value + nb.value]
+
+    def predict(self, Xs, include_noise=False, out_mean=None, out_var=None):
+        if not self.fitted:
+            self.fit()
+        Xsd = _points23(Xs, self.device)
+        if Xsd.shape[1] != self.ldx:
+            raise ValueError("prediction points must have %d columns" % self.ldx)
+        M = int(Xsd.shape[0])
+        mean = out_mean if out_mean is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        var = out_var if out_var is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        if M:
+            with torch.cuda.device(self.device):
+                nb = lib.gp2d_predict_workspace_bytes(self.N, M)
+                if self._pws is None or self._pws.numel() < nb:
+                    self._pws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+                check(lib.gp2d_hsum_predict(_ptr(self.ws), self.N, self.ldx, self.Q, self.types.ctypes.data,
+                                            self.params.ctypes.data, _ptr(Xsd), M, M,
+                                            self.noise if include_noise else 0.0, _ptr(mean), _ptr(var),
+                                            _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_hsum_predict")
+        return mean, var
+
+    def lml_and_grad(self):
+        """(LML, grad) with grad over (var, lt, la, lb)_q for every term, then the noise variance."""
+        ng = 4 * self.Q + 1
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_hsum_lml_grad(_ptr(self.X), self.N, self.ldx, _ptr(self.y), self.Q, self.types.ctypes.data,
+                                         self.params.ctypes.data, self.noise, self.jitter, _ptr(self.ws), self.ws_bytes,
+                                         _ptr(self._scal), _ptr(self._info), _stream()), "gp2d_hsum_lml_grad")
+        self.fitted = True
+        host = self._scal[:1 + ng].cpu().numpy()
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
+        self.lml = float(host[0])
+        return self.lml, host[1:1 + ng].copy()
+
+
 def fit_predict_host(X, y, l_df, l_cf, ratio, noise, Xs, jitter=0.0, include_noise=False):
     """Whole pipeline through the host-pointer C entry point (numpy in, numpy out)."""
     import ctypes as C

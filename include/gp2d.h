@@ -185,6 +185,39 @@ int gp2d_rbf_predict(const void* fit_ws, int N, int D, int Q, const double* var,
 int gp2d_rbf_lml_grad(const double* X, int N, int D, const double* y, int Q, const double* var, const double* ls,
                       double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream);
 
+/* ---- sum of space-time Helmholtz terms ----------------------------------------------------------
+ * K = sum_{q<Q} var_q exp(-dt^2/2lt_q^2 - da^2/2la_q^2 - db^2/2lb_q^2) * G_q(da, db), Q <= 8, with
+ *   G (type 0, divergence-free) = [[(1 - db^2/lb^2)/lb^2,  da db/(la^2 lb^2)], [., (1 - da^2/la^2)/la^2]]
+ *   G (type 1, curl-free)       = [[(1 - da^2/la^2)/la^2, -da db/(la^2 lb^2)], [., (1 - db^2/lb^2)/lb^2]]
+ * These are the kernels krig.kriging(kernelType = 2, 3, 4, nKernels) builds from the module myKernel2
+ * that is missing from the reference (krig.py:396-407): divFreeK / curlFreeK(input_dim=3, var, lt, ly, lx),
+ * their sum, and nKernels copies of it.  With la == lb, ldx == 2 and the two terms
+ * {type 0, var = ratio} + {type 1, var = 1 - ratio} the matrix equals gp2d_kernel_build's
+ * (myKernel.py:27-53).  type[Q] and params[Q*4] = (var, lt, la, lb) per term are HOST arrays (read
+ * before the call returns); ldx = 3: points are [N,3] rows (t, a, b); ldx = 2: rows (a, b), lt unused.
+ * Layouts, stacking, workspaces and return codes as in the Helmholtz functions above;
+ * gp2d_predict_workspace_bytes sizes the prediction scratch.
+ * gp2d_hsum_kdiag: out[2M] = prior variances (first M: component 0).
+ * gp2d_hsum_kernel_grad: out[Q*4] = sum(dK/d(var, lt, la, lb)_q * dL_dK) (0 for lt when ldx == 2).
+ * gp2d_hsum_lml_grad: out[2 + 4Q] = (LML, the 4Q derivatives in the same order, d/dnoise). */
+int gp2d_hsum_kernel_build(const double* X, int N, const double* X2, int M, int ldx, int Q, const int* type,
+                           const double* params, double diag_add, double* K, int64_t ldk, void* stream);
+int gp2d_hsum_kdiag(int M, int ldx, int Q, const int* type, const double* params, double* out, void* stream);
+size_t gp2d_hsum_kernel_grad_workspace_bytes(int N, int M, int Q);
+int gp2d_hsum_kernel_grad(const double* X, int N, const double* X2, int M, int ldx, int Q, const int* type,
+                          const double* params, const double* dL_dK, int64_t ld, void* ws, size_t ws_bytes,
+                          double* out, void* stream);
+size_t gp2d_hsum_fit_workspace_bytes(int N, int ldx, int Q);
+int gp2d_hsum_fit_predict_state(int N, int ldx, int Q, size_t* offset, size_t* bytes);
+int gp2d_hsum_fit(const double* X, int N, int ldx, const double* y, int Q, const int* type, const double* params,
+                  double noise, double jitter, void* ws, size_t ws_bytes, double* alpha_out, double* lml_out,
+                  int* info, void* stream);
+int gp2d_hsum_predict(const void* fit_ws, int N, int ldx, int Q, const int* type, const double* params,
+                      const double* Xs, int M, int64_t out_stride, double var_add, double* mean, double* var,
+                      void* ws, size_t ws_bytes, void* stream);
+int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, const int* type, const double* params,
+                       double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream);
+
 /* ---- host-buffer convenience (allocates, copies, synchronises) -------------------- */
 
 /* Whole fit + predict with HOST pointers on the current device; returns info (> 0) or an

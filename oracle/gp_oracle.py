@@ -295,6 +295,115 @@ def st_lml_and_grad(X3, y, l_df, l_cf, ratio, tvar, lt, noise, jitter=0.0):
 
 
 # --------------------------------------------------------------------------------------
+# sum of space-time Helmholtz terms: what krig.kriging(kernelType = 2, 3, 4, nKernels) asks the
+# module myKernel2 for (krig.py:396-407): divFreeK / curlFreeK(input_dim=3, var, lt, ly, lx), their
+# sum, nKernels copies with independent parameters.  myKernel2 is NOT in the reference repository,
+# so the anisotropic / time-dependent formula is specified here ("parity unpinned"): the stream
+# function / potential construction of myKernel.py:39-52 applied to
+#   s = var exp(-dt^2/2lt^2 - da^2/2la^2 - db^2/2lb^2).
+# What IS pinned: with la == lb, no time and {div-free var=ratio} + {curl-free var=1-ratio} it must
+# equal helmholtz_K (the golden-checked restatement of myKernel.py:27-53), and with a shared lt it
+# must equal st_K; tests/test_oracle_golden.py checks both.
+# --------------------------------------------------------------------------------------
+def _hsum_split(X):
+    X = np.asarray(X, dtype=np.float64)
+    if X.shape[1] == 3:
+        return X[:, 0], X[:, 1], X[:, 2]
+    return np.zeros(X.shape[0]), X[:, 0], X[:, 1]
+
+
+def _hsum_term(dt, d1, d2, ty, var, lt, la, lb, has_t):
+    """(k, P, R, C): scalar envelope and the (1 - s1)/la^2, (1 - s2)/lb^2, +-d1 d2/(la lb)^2 factors."""
+    a1, a2 = 1.0 / la ** 2, 1.0 / lb ** 2
+    s1, s2 = d1 * d1 * a1, d2 * d2 * a2
+    e = 0.5 * (s1 + s2)
+    if has_t:
+        e = e + 0.5 * dt * dt / lt ** 2
+    k = var * np.exp(-e)
+    sgn = -1.0 if ty else 1.0
+    return k, a1 * (1.0 - s1), a2 * (1.0 - s2), sgn * d1 * d2 * a1 * a2, s1, s2
+
+
+def hsum_K(X, X2, types, params):
+    """[2N,2M] block matrix; types[q] in {0 div-free, 1 curl-free}; params[q] = (var, lt, la, lb)."""
+    t, a, b = _hsum_split(X)
+    t2, a2_, b2_ = (t, a, b) if X2 is None else _hsum_split(X2)
+    has_t = np.asarray(X).shape[1] == 3
+    dt, d1, d2 = t[:, None] - t2[None, :], a[:, None] - a2_[None, :], b[:, None] - b2_[None, :]
+    K = 0.0
+    for ty, (var, lt, la, lb) in zip(types, np.atleast_2d(params)):
+        k, P, R, C, _, _ = _hsum_term(dt, d1, d2, ty, var, lt, la, lb, has_t)
+        K = K + (_blk(k * P, k * C, k * C, k * R) if ty else _blk(k * R, k * C, k * C, k * P))
+    return K
+
+
+def hsum_Kdiag(M, types, params):
+    """Prior variances, first M entries component 0."""
+    v0 = v1 = 0.0
+    for ty, (var, lt, la, lb) in zip(types, np.atleast_2d(params)):
+        v0 += var / (la ** 2 if ty else lb ** 2)
+        v1 += var / (lb ** 2 if ty else la ** 2)
+    return np.concatenate([np.full(M, v0), np.full(M, v1)])
+
+
+def hsum_dK(X, X2, types, params):
+    """List over terms of [dK/dvar, dK/dlt, dK/dla, dK/dlb] (analytic)."""
+    t, a, b = _hsum_split(X)
+    t2, a2_, b2_ = (t, a, b) if X2 is None else _hsum_split(X2)
+    has_t = np.asarray(X).shape[1] == 3
+    dt, d1, d2 = t[:, None] - t2[None, :], a[:, None] - a2_[None, :], b[:, None] - b2_[None, :]
+    out = []
+    for ty, (var, lt, la, lb) in zip(types, np.atleast_2d(params)):
+        k, P, R, C, s1, s2 = _hsum_term(dt, d1, d2, ty, var, lt, la, lb, has_t)
+
+        def blk(p, r, c):
+            return _blk(p, c, c, r) if ty else _blk(r, c, c, p)
+        E = k / var if var != 0.0 else _hsum_term(dt, d1, d2, ty, 1.0, lt, la, lb, has_t)[0]
+        dvar = blk(E * P, E * R, E * C)
+        tt = (dt * dt / lt ** 3) if has_t else np.zeros_like(dt)
+        dlt = blk(k * P * tt, k * R * tt, k * C * tt)
+        # d(kP)/dla = k/la [s1 P + (4 s1 - 2)/la^2]; d(kR)/dla = k/la s1 R; d(kC)/dla = k/la (s1 - 2) C
+        dla = blk(k / la * (s1 * P + (4.0 * s1 - 2.0) / la ** 2), k / la * s1 * R, k / la * (s1 - 2.0) * C)
+        dlb = blk(k / lb * s2 * P, k / lb * (s2 * R + (4.0 * s2 - 2.0) / lb ** 2), k / lb * (s2 - 2.0) * C)
+        out.append([dvar, dlt, dla, dlb])
+    return out
+
+
+def hsum_kernel_grad_sums(dL_dK, X, X2, types, params):
+    return np.array([[np.sum(d * dL_dK) for d in term] for term in hsum_dK(X, X2, types, params)])
+
+
+def hsum_fit(X, y, types, params, noise, jitter=0.0):
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = hsum_K(X, None, types, params)
+    n = K.shape[0]
+    K[np.diag_indices(n)] += noise + jitter
+    L = sla.cholesky(K, lower=True, check_finite=False)
+    alpha = sla.cho_solve((L, True), y, check_finite=False)
+    val = -0.5 * float(y @ alpha) - float(np.sum(np.log(np.diag(L)))) - 0.5 * n * LOG_2PI
+    return {"L": L, "alpha": alpha, "lml": val}
+
+
+def hsum_predict(X, fitres, types, params, Xs, var_add=0.0):
+    Xs = np.asarray(Xs, dtype=np.float64)
+    Ks = hsum_K(Xs, X, types, params)
+    mean = Ks @ fitres["alpha"]
+    V = sla.solve_triangular(fitres["L"], Ks.T, lower=True, check_finite=False)
+    var = hsum_Kdiag(Xs.shape[0], types, params) - np.einsum("ij,ij->j", V, V)
+    return mean, np.where(var < 0.0, 0.0, var) + var_add
+
+
+def hsum_lml_and_grad(X, y, types, params, noise, jitter=0.0):
+    """(LML, [d/d(var, lt, la, lb)_q ..., d/dnoise])."""
+    f = hsum_fit(X, y, types, params, noise, jitter)
+    n = f["L"].shape[0]
+    Kinv = sla.cho_solve((f["L"], True), np.eye(n), check_finite=False)
+    W = 0.5 * (np.outer(f["alpha"], f["alpha"]) - Kinv)
+    g = hsum_kernel_grad_sums(W, X, None, types, params).reshape(-1)
+    return f["lml"], np.concatenate([g, [np.trace(W)]])
+
+
+# --------------------------------------------------------------------------------------
 # scalar ARD-RBF sum family: the reference's production kernels.  GPy.kern.RBF(input_dim=3,
 # ARD=True) summed nKernels times (krig.py:388,405-407); sklearn HP[0]*RBF([..]) + HP[4]*RBF([..])
 # + WhiteKernel(noise) (krig.py:174-181).  Pinned against live scikit-learn in

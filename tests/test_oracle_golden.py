@@ -234,3 +234,50 @@ def test_spacetime_oracle_consistency():
         e = np.zeros(5); e[i] = h
         fdl = (orc.st_fit(X3, y, *(theta + e), 0.1)["lml"] - orc.st_fit(X3, y, *(theta - e), 0.1)["lml"]) / (2 * h)
         assert abs(g[i] - fdl) <= 1e-5 * max(1.0, abs(fdl))
+
+
+# ---- sum of space-time Helmholtz terms (krig.py:396-407; module myKernel2 missing upstream) ----------
+def test_hsum_oracle_reduces_to_the_pinned_kernels():
+    """The term-sum restatement has no reference code to be pinned against, but its isotropic
+    subspace is the golden-checked Helmholtz kernel (myKernel.py:27-53) and, with a shared time
+    scale, the space-time product (scratch.py:506-508)."""
+    rng = np.random.default_rng(11)
+    X, X2 = rng.uniform(0, 8, (23, 2)), rng.uniform(0, 8, (17, 2))
+    for (l_df, l_cf, ratio) in [(2.0, 2.0, 0.5), (1.3, 3.1, 0.2), (0.8, 1.9, 1.0), (0.8, 1.9, 0.0)]:
+        types, params = [0, 1], [[ratio, 1.0, l_df, l_df], [1 - ratio, 1.0, l_cf, l_cf]]
+        np.testing.assert_allclose(orc.hsum_K(X, X2, types, params), orc.helmholtz_K(X, X2, l_df, l_cf, ratio), rtol=0, atol=2e-15)
+        np.testing.assert_allclose(orc.hsum_Kdiag(5, types, params), orc.helmholtz_Kdiag(5, l_df, l_cf, ratio), rtol=1e-15)
+    X3, X3b = np.c_[rng.uniform(0, 3, 23), X], np.c_[rng.uniform(0, 3, 17), X2]
+    params = [[0.2 * 1.7, 0.9, 1.3, 1.3], [0.8 * 1.7, 0.9, 3.1, 3.1]]
+    np.testing.assert_allclose(orc.hsum_K(X3, X3b, [0, 1], params), orc.st_K(X3, X3b, 1.3, 3.1, 0.2, 1.7, 0.9), rtol=0, atol=2e-15)
+
+
+def test_hsum_oracle_gradient_and_validity():
+    rng = np.random.default_rng(12)
+    X3, X3b = rng.uniform(0, 6, (14, 3)), rng.uniform(0, 6, (9, 3))
+    types = [0, 1, 0]
+    P = np.array([[0.8, 1.1, 1.3, 0.7], [1.2, 0.6, 2.1, 1.5], [0.5, 2.0, 0.9, 1.9]])
+    d = orc.hsum_dK(X3, X3b, types, P)
+    for q in range(3):
+        for j in range(4):
+            Pp, Pm = P.copy(), P.copy()
+            Pp[q, j] += 1e-6
+            Pm[q, j] -= 1e-6
+            fd = (orc.hsum_K(X3, X3b, types, Pp) - orc.hsum_K(X3, X3b, types, Pm)) / 2e-6
+            np.testing.assert_allclose(d[q][j], fd, rtol=0, atol=2e-9 * max(1.0, np.abs(fd).max()))
+    # a valid covariance: symmetric, positive semi-definite, diagonal = Kdiag
+    K = orc.hsum_K(X3, None, types, P)
+    np.testing.assert_array_equal(K, K.T)
+    assert np.linalg.eigvalsh(K).min() > -1e-12
+    np.testing.assert_allclose(np.diag(K), orc.hsum_Kdiag(14, types, P), rtol=1e-14)
+    # the LML gradient is the derivative of the LML
+    y = rng.normal(size=28)
+    l0, g0 = orc.hsum_lml_and_grad(X3, y, types, P, 0.1)
+    for q, j in [(0, 0), (1, 1), (2, 2), (1, 3)]:
+        Pp, Pm = P.copy(), P.copy()
+        Pp[q, j] += 1e-6
+        Pm[q, j] -= 1e-6
+        fd = (orc.hsum_fit(X3, y, types, Pp, 0.1)["lml"] - orc.hsum_fit(X3, y, types, Pm, 0.1)["lml"]) / 2e-6
+        assert abs(fd - g0[4 * q + j]) <= 1e-6 * max(1.0, abs(fd))
+    fd = (orc.hsum_fit(X3, y, types, P, 0.1 + 1e-6)["lml"] - orc.hsum_fit(X3, y, types, P, 0.1 - 1e-6)["lml"]) / 2e-6
+    assert abs(fd - g0[-1]) <= 1e-6 * max(1.0, abs(fd))
