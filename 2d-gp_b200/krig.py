@@ -9,8 +9,11 @@
 Host preprocessing follows the reference (krig.py:42-86,259-381,648-678) in Python 3; the
 numerical core (covariance, Cholesky, likelihood, prediction) is ``models.GPRegression`` over
 libgp2d.  Deviations, all forced by what the reference tree lacks:
-  * kernelType 2 / 3 / 4 map to nonDivK / nonRotK / myKernel over the horizontal position
-    (y, x): the reference's 3-D ``myKernel2`` is not in its repository;
+  * kernelType 2 / 3 / 4 build myKernel2.divFreeK / curlFreeK / their sum over (t, y, x) with the
+    constructor calls of krig.py:396-404; the reference's ``myKernel2`` module is not in its
+    repository, so the covariance is the one specified in myKernel2.py / csrc/hsum.cuh (the
+    stream-function / potential construction of myKernel.py:39-52 on an anisotropic space-time
+    squared exponential); nKernels copies are summed as krig.py:405-407 (at most 8 terms);
   * kernelType 1 (scalar ARD RBF over t,y,x; krig.py:388) builds one scalar model per velocity
     component (``_v.pkl`` / ``_u.pkl``) on the GPU RBF family; ``scikit_prior`` rebuilds the
     optimised kernel through the scikit-learn look-alike (sklearn_like.py) as krig.py:174-194;
@@ -29,7 +32,7 @@ import scipy.io as sio
 from . import dist as gdist
 from . import models
 from .kern import RBF
-from .myKernel import myKernel, nonDivK, nonRotK
+from . import myKernel2
 from .sklearn_like import GaussianProcessRegressor, kernels
 from .printNCFiles import createNC, openNC, writeNC
 from .projection import NAD83
@@ -108,11 +111,11 @@ def make_kernel(kernelType):
     if kernelType == 1:
         return RBF(input_dim=3, ARD=True)                      # krig.py:388
     if kernelType == 2:
-        return nonDivK(2, [1, 2], 1.)
+        return myKernel2.divFreeK(input_dim=3, active_dims=[0, 1, 2], var=1., lt=1., ly=1., lx=1.)     # krig.py:397
     if kernelType == 3:
-        return nonRotK(2, [1, 2], 1.)
+        return myKernel2.curlFreeK(input_dim=3, active_dims=[0, 1, 2], var=1., lt=1., ly=1., lx=1.)    # krig.py:401
     if kernelType == 4:
-        return myKernel(2, [1, 2], 1., 1., 0.5)
+        return myKernel2.divFreeK(input_dim=3) + myKernel2.curlFreeK(input_dim=3)                      # krig.py:404
     raise ValueError("kernelType must be 1 (scalar ARD RBF), 2 (divergence-free), 3 (curl-free) or 4 (both)")
 
 
@@ -155,10 +158,10 @@ def kriging(st, et, lalim=[0, 0], lolim=[0, 0], sample_step=5, skip=5, nKernels=
         obs = np.concatenate([o["v"], o["u"]], axis=1)
         obst = np.concatenate([t["v"], t["u"]], axis=1)
     else:
-        if nKernels != 1:
-            print('nKernels > 1: a sum of identical Helmholtz kernels is one kernel with rescaled '
-                  'weights; a single kernel is used')
-        model = models.GPRegression(X, obs, k2)
+        k = k2.copy()
+        for _ in range(nKernels - 1):                           # krig.py:405-407
+            k = k + k2
+        model = models.GPRegression(X, obs, k)
         model.pickle(output + _SUFFIX[kernelType])
     sio.savemat(output + '.mat', {'Xo': X, 'obs': obs, 'Xt': Xt,
                                   'LL_o': np.concatenate([o["t"], o["lat"], o["lon"]], axis=1),
@@ -235,7 +238,9 @@ def predict(filename, tlim=[0, 0], ylim=[0, 0], xlim=[0, 0], dt=0.5, dx=0.5, xL=
     inc = yp.size * xp.size
     V, U, VVar, UVar = [], [], [], []
     for i in range(tp.size):
-        Xp2 = Xp[i * inc:(i + 1) * inc, 1:3]
+        Xp2 = Xp[i * inc:(i + 1) * inc]                       # rows (t, y, x) of this time slice (krig.py:541-543)
+        if not (model.hsum or model.spacetime):
+            Xp2 = Xp2[:, 1:3]                                 # purely spatial kernels see (y, x)
         mean, var = gdist.predict_sharded(model._gp, Xp2, include_noise=True)     # GPy adds the noise
         mean, var = mean.cpu().numpy(), var.cpu().numpy()
         V.append(mean[:inc]); U.append(mean[inc:]); VVar.append(var[:inc]); UVar.append(var[inc:])

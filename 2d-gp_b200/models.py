@@ -18,9 +18,10 @@ import pickle
 import numpy as np
 import scipy.optimize as sopt
 
-from .engine import HelmholtzGP, LinAlgError, ScalarGP, SpaceTimeGP
+from .engine import HelmholtzGP, HelmholtzSumGP, LinAlgError, ScalarGP, SpaceTimeGP
 from .kern import RBF, Add, Prod, _ScalarKern
 from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase, Kt, SpaceTimeKern
+from .myKernel2 import _HelmholtzSumKern, HelmholtzSum, divFreeK, curlFreeK
 from .params import Param
 
 GPY_JITTER = 1e-8       # GPy adds 1e-8 to the diagonal before factorising
@@ -39,11 +40,13 @@ class GPRegression:
         Y = np.asarray(Y, dtype=np.float64)
         if kernel is None:
             kernel = myKernel(2, [0, 1], 1.0, 1.0, 0.5)
-        if not isinstance(kernel, (_HelmholtzBase, _ScalarKern, SpaceTimeKern)):
-            raise TypeError("kernel must be myKernel / nonDivK / nonRotK, Kt * one of them, or an RBF (sum)")
+        if not isinstance(kernel, (_HelmholtzBase, _ScalarKern, SpaceTimeKern, _HelmholtzSumKern)):
+            raise TypeError("kernel must be myKernel / nonDivK / nonRotK, Kt * one of them, a sum of "
+                            "myKernel2.divFreeK / curlFreeK terms, or an RBF (sum)")
         self.kern = kernel
         self.scalar = isinstance(kernel, _ScalarKern)
         self.spacetime = isinstance(kernel, SpaceTimeKern)
+        self.hsum = isinstance(kernel, _HelmholtzSumKern)
         self.Y = Y.reshape(-1, 1)
         self.Gaussian_noise = Param("Gaussian_noise.variance", noise_var).constrain_positive()
         self.likelihood = self
@@ -57,6 +60,13 @@ class GPRegression:
                 raise ValueError("Y must hold one observation per row of X: shape [N,1]")
             self._gp = ScalarGP(self.X, self.Y.reshape(-1), *self.kern.rbf_params(), float(self.Gaussian_noise),
                                 jitter=self.jitter, device=device)
+        elif self.hsum:
+            # sum of divFreeK / curlFreeK terms over (t, y, x), stacked [v; u] (krig.py:392-407)
+            self.X = self.kern.points(X)
+            if self.Y.shape[0] != 2 * self.X.shape[0]:
+                raise ValueError("Y must stack both velocity components: shape [2N,1] (krig.py:392)")
+            self._gp = HelmholtzSumGP(self.X, self.Y.reshape(-1), *self.kern.hsum_params(), float(self.Gaussian_noise),
+                                      jitter=self.jitter, device=device)
         elif self.spacetime:
             # Kt(t) * Helmholtz(y, x): points (t, a, b), stacked components (scratch.py:495-510)
             self.X = self.kern.points3(X)
@@ -102,7 +112,7 @@ class GPRegression:
         return np.array([float(p) for p in self.parameters])
 
     def parameter_names(self):
-        if self.scalar or self.spacetime:
+        if self.scalar or self.spacetime or self.hsum:
             return self.kern.parameter_names() + ["Gaussian_noise.variance"]
         return ["%s.%s" % (self.kern.name, p.name) for p in self.kern.parameters] + ["Gaussian_noise.variance"]
 
@@ -114,6 +124,8 @@ class GPRegression:
             self._gp.set_params(*self.kern.rbf_params(), float(self.Gaussian_noise))
         elif self.spacetime:
             self._gp.set_params(*self.kern.theta5(), float(self.Gaussian_noise))
+        elif self.hsum:
+            self._gp.set_params(*self.kern.hsum_params(), float(self.Gaussian_noise))
         else:
             self._gp.set_params(*self.kern._theta(), float(self.Gaussian_noise))
 
@@ -135,6 +147,16 @@ class GPRegression:
             try:
                 self._ll, g = self._gp.lml_and_grad()
                 self.kern._scatter_gradient(g[:-1])
+                self.Gaussian_noise.gradient = float(g[-1])
+            except LinAlgError:
+                self._ll = -np.inf
+                for p in self.parameters:
+                    p.gradient = 0.0
+            return self._ll
+        if self.hsum:
+            try:
+                self._ll, g = self._gp.lml_and_grad()
+                self.kern.scatter_gradient(g[:-1])
                 self.Gaussian_noise.gradient = float(g[-1])
             except LinAlgError:
                 self._ll = -np.inf
@@ -197,7 +219,11 @@ class GPRegression:
 
     def _clone(self):
         """Independent model on the same data and device (own fit workspace), for concurrent restarts."""
-        m = GPRegression(self.X, self.Y, self.kern.copy(), noise_var=float(self.Gaussian_noise), jitter=self.jitter,
+        k = self.kern.copy()
+        if self.hsum:                       # self.X is already sliced to the kernel's columns
+            for t in k.terms_list() + [k]:
+                t.active_dims = list(range(t.input_dim))
+        m = GPRegression(self.X, self.Y, k, noise_var=float(self.Gaussian_noise), jitter=self.jitter,
                          device=self._gp.device)
         for a, b in zip(m.parameters, self.parameters):
             a.constraint = b.constraint
@@ -292,6 +318,8 @@ class GPRegression:
             Xnew = self.kern._slice(Xnew)
         elif self.spacetime:
             Xnew = self.kern.points3(Xnew)
+        elif self.hsum:
+            Xnew = self.kern.points(Xnew)
         elif Xnew.shape[1] != 2:
             Xnew = Xnew[:, self.kern.active_dims]
         if not self._gp.fitted:
@@ -318,6 +346,10 @@ class GPRegression:
         elif self.spacetime:
             st["space"] = type(k.kxy).__name__                    # X is stored as (t, a, b)
             st["active_dims"] = [0, 1, 2]
+        elif self.hsum:
+            st["terms"] = [t.TYPE for t in k.terms_list()]        # X is stored already sliced
+            st["input_dim"] = k.terms_list()[0].input_dim
+            st["active_dims"] = list(range(self.X.shape[1]))
         else:
             st["reference_compat"] = k.reference_compat
         return st
@@ -337,6 +369,22 @@ def load(path, device=None):
         st = pickle.load(f)
     p = st["params"]
     name = st["kernel"]
+    if "terms" in st:
+        D, np_term = st["input_dim"], (4 if st["input_dim"] == 3 else 3)
+        terms = []
+        for q, ty in enumerate(st["terms"]):
+            v = p[q * np_term:(q + 1) * np_term]
+            kw = dict(var=v[0], lt=v[1], ly=v[2], lx=v[3]) if D == 3 else dict(var=v[0], ly=v[1], lx=v[2])
+            terms.append((curlFreeK if ty else divFreeK)(input_dim=D, **kw))
+        k = terms[0] if name != "HelmholtzSum" else HelmholtzSum(terms)
+        m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
+        for prm, c in zip(m.parameters, st["constraints"]):
+            prm.constraint = c
+        for d in st["runs"]:
+            r = _Run(None, None, None, None)
+            r.__dict__.update(d)
+            m.optimization_runs.append(r)
+        return m
     if "space" in st:
         kxy = {"myKernel": lambda: myKernel(2, [1, 2], p[2], p[3], p[4]), "nonDivK": lambda: nonDivK(2, [1, 2], p[2]),
                "nonRotK": lambda: nonRotK(2, [1, 2], p[2])}[st["space"]]()

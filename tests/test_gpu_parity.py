@@ -544,3 +544,34 @@ def test_second_device_in_the_same_process():
     g = gp.ScalarGP(np.c_[X, X[:, :1]], y[:600], [0.5], [[2.0, 2.0, 3.0]], 0.01, device="cuda:1")
     g.fit()
     assert g.predict(np.c_[Xs, Xs[:, :1]])[0].device.index == 1
+
+
+def test_results_do_not_depend_on_previous_workspace_contents():
+    """Every kernel family: the workspace is scratch, whatever it held before (zeros, NaN patterns,
+    huge numbers) the likelihood, its gradient and the prediction come out bit-identical -- i.e. no
+    kernel reads a tile it did not write (the upper tiles of the factor are never initialised)."""
+    rng = np.random.default_rng(0)
+    N = 300
+    X = rng.uniform(0, 10, (N, 3))
+    y = rng.normal(size=2 * N)
+    Xs = rng.uniform(0, 10, (500, 3))
+    makers = {
+        "helm": (lambda: gp.HelmholtzGP(X[:, 1:], y, 1.3, 3.1, 0.2, 0.05), Xs[:, 1:]),
+        "st": (lambda: gp.SpaceTimeGP(X, y, 1.3, 3.1, 0.2, 1.5, 0.8, 0.05), Xs),
+        "hsum": (lambda: gp.HelmholtzSumGP(X, y, [0, 1], [[0.6, 1.5, 1.3, 2.0], [1.4, 0.7, 3.1, 2.2]], 0.05), Xs),
+        "rbf": (lambda: gp.ScalarGP(X, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], 0.05), Xs),
+    }
+    for name, (make, P) in makers.items():
+        outs = []
+        for fill in (0, 0xFF, None):
+            g = make()
+            if fill is None:
+                g.ws.view(torch.float64)[:] = torch.randn(g.ws.numel() // 8, dtype=torch.float64, device=g.ws.device) * 1e30
+            else:
+                g.ws.fill_(fill)
+            l, gr = g.lml_and_grad()
+            m, v = g.predict(P)
+            outs.append((l, gr.copy(), m.clone(), v.clone()))
+        for o in outs[1:]:
+            assert o[0] == outs[0][0] and np.array_equal(o[1], outs[0][1]), name
+            assert torch.equal(o[2], outs[0][2]) and torch.equal(o[3], outs[0][3]), name

@@ -134,3 +134,76 @@ def test_argument_checks():
     g = gp.HelmholtzSumGP(X, y, [0], [[0.0, 1, 1, 1]], 0.0)
     with pytest.raises(gp.LinAlgError):
         g.fit()
+
+
+# ---- the reference-facing surface: myKernel2.divFreeK / curlFreeK and krig.kriging(kernelType=2..4) -------
+def test_mykernel2_classes_and_model(tmp_path):
+    """krig.py:396-411: k2 = divFreeK(input_dim=3) + curlFreeK(input_dim=3); k = k2 + k2; GPRegression(X, obs, k)."""
+    from gp2d_b200 import models, myKernel2
+    X, Xs, y = _data(150, 60, 31, ldx=3)
+    kd = myKernel2.divFreeK(input_dim=3, active_dims=[0, 1, 2], var=1., lt=1., ly=1., lx=1.)      # krig.py:397 verbatim
+    assert [p.name for p in kd.parameters] == ["var", "lt", "ly", "lx"] and kd.parameter_names()[0] == "divFreeK.var"
+    np.testing.assert_allclose(kd.K(X, Xs), orc.hsum_K(X, Xs, [0], [[1, 1, 1, 1]]), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(kd.Kdiag(Xs), orc.hsum_Kdiag(60, [0], [[1, 1, 1, 1]]))
+    k2 = myKernel2.divFreeK(input_dim=3, var=0.6, lt=1.5, ly=1.3, lx=2.0) + myKernel2.curlFreeK(input_dim=3, var=1.4, lt=0.7, ly=3.1, lx=2.2)
+    k = k2.copy()
+    k = k + k2                                                                                    # nKernels = 2 (krig.py:405-407)
+    assert len(k.terms_list()) == 4 and len(k.parameters) == 16
+    assert k.parameter_names()[:5] == ["sum.divFreeK.var", "sum.divFreeK.lt", "sum.divFreeK.ly", "sum.divFreeK.lx", "sum.curlFreeK.var"]
+    assert k.parameter_names()[8] == "sum.divFreeK_1.var"
+    # the copies are independent parameters
+    k.terms_list()[2].ly.value = 0.6
+    assert float(k.terms_list()[0].ly) == 1.3
+    types, params = k.hsum_params()
+    m = models.GPRegression(X, y[:, None], k, noise_var=0.02)
+    lo, go = orc.hsum_lml_and_grad(X, y, types, params, 0.02, jitter=1e-8)
+    assert abs(m.log_likelihood() - lo) <= 1e-6 * abs(lo)
+    np.testing.assert_allclose([p.gradient for p in m.parameters], go, rtol=1e-6, atol=1e-7)
+    # plug-in gradient protocol (what GPy would call)
+    W = np.random.default_rng(0).normal(size=(300, 120))
+    k.update_gradients_full(W, X, Xs)
+    np.testing.assert_allclose([p.gradient for p in k.parameters], orc.hsum_kernel_grad_sums(W, X, Xs, types, params).reshape(-1),
+                               rtol=1e-10, atol=1e-10)
+    ll0 = m.log_likelihood()
+    m.optimize(max_iters=25)
+    assert m.log_likelihood() > ll0
+    path = str(tmp_path / "k2.pkl")
+    m.pickle(path)
+    m2 = models.load(path)
+    np.testing.assert_array_equal(m2.param_array, m.param_array)
+    assert m2.parameter_names() == m.parameter_names()
+    a, b = m.predict(Xs), m2.predict(Xs)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    types, params = m.kern.hsum_params()
+    nz = float(m.Gaussian_noise)
+    f = orc.hsum_fit(X, y, types, params, nz, jitter=1e-8)
+    mo, vo = orc.hsum_predict(X, f, types, params, Xs, var_add=nz)
+    np.testing.assert_allclose(a[0][:, 0], mo, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(a[1][:, 0], vo, rtol=1e-7, atol=1e-10)
+    # restarts, sequential and concurrent, agree
+    m3 = models.GPRegression(X, y[:, None], k2.copy(), noise_var=0.02)      # the model optimises its kernel in place
+    m3.optimize_restarts(num_restarts=3, verbose=False, max_iters=15, seed=5)
+    m4 = models.GPRegression(X, y[:, None], k2.copy(), noise_var=0.02)
+    m4.optimize_restarts(num_restarts=3, verbose=False, max_iters=15, seed=5, parallel=3)
+    np.testing.assert_allclose(m3.param_array, m4.param_array, rtol=1e-9)
+
+
+def test_mykernel2_two_dimensional_and_column_selection():
+    from gp2d_b200 import models, myKernel2
+    X, Xs, y = _data(80, 30, 33, ldx=3)
+    # input_dim=2 on columns (1, 2) of the (t, y, x) rows: no time factor, 3 parameters per term
+    k = myKernel2.curlFreeK(input_dim=2, active_dims=[1, 2], var=0.8, ly=1.2, lx=2.5)
+    assert [p.name for p in k.parameters] == ["var", "ly", "lx"]
+    np.testing.assert_allclose(k.K(X, Xs), orc.hsum_K(X[:, 1:], Xs[:, 1:], [1], [[0.8, 1.0, 1.2, 2.5]]), rtol=0, atol=1e-13)
+    m = models.GPRegression(X, y[:, None], k, noise_var=0.05)
+    lo, go = orc.hsum_lml_and_grad(X[:, 1:], y, [1], [[0.8, 1.0, 1.2, 2.5]], 0.05, jitter=1e-8)
+    assert abs(m.log_likelihood() - lo) <= 1e-6 * abs(lo)
+    np.testing.assert_allclose([p.gradient for p in m.parameters], [go[0], go[2], go[3], go[4]], rtol=1e-6, atol=1e-7)
+    m.optimize_restarts(num_restarts=2, verbose=False, max_iters=10, seed=1, parallel=2)
+    mean, var = m.predict(Xs)
+    assert mean.shape == (60, 1) and np.all(var > 0)
+    with pytest.raises(ValueError):
+        myKernel2.divFreeK(input_dim=3) + myKernel2.divFreeK(input_dim=2)
+    with pytest.raises(ValueError):
+        myKernel2.HelmholtzSum([myKernel2.divFreeK()] * 9)
