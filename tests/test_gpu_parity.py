@@ -487,6 +487,53 @@ def test_no_writes_outside_buffers_rbf(N, M, D, Q):
     np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
 
 
+@pytest.mark.parametrize("N,M,ldx,Q", [(1, 1, 3, 1), (127, 129, 2, 2), (500, 3000, 3, 4), (513, 700, 3, 8)])
+def test_no_writes_outside_buffers_hsum(N, M, ldx, Q):
+    from gp2d_b200.engine import _stream
+    rng = np.random.default_rng(N)
+    X, Xs = rng.uniform(0, 12, (N, ldx)), rng.uniform(0, 12, (M, ldx))
+    y = np.concatenate([np.sin(X[:, -1]), np.cos(X[:, -2])]) + 0.1 * rng.normal(size=2 * N)
+    ty_h = np.ascontiguousarray(rng.integers(0, 2, Q).astype(np.int32))
+    pr_h = np.ascontiguousarray(np.c_[rng.uniform(0.2, 1.5, Q), rng.uniform(1.0, 5.0, (Q, 3))])
+    Xd, yd, Xsd = dev(X), dev(y), dev(Xs)
+    wsW, ws = _guarded(lib.gp2d_hsum_fit_workspace_bytes(N, ldx, Q))
+    pwW, pws = _guarded(lib.gp2d_predict_workspace_bytes(N, M))
+    ng = 2 + 4 * Q
+    outW, out = _guarded(8 * (4 * M + 2 * N + ng + 1 + 4 * Q))
+    o = out.view(torch.float64)
+    mean, var, alpha = o[:2 * M], o[2 * M:4 * M], o[4 * M:4 * M + 2 * N]
+    scal = o[4 * M + 2 * N:4 * M + 2 * N + ng]
+    lml1 = o[4 * M + 2 * N + ng:4 * M + 2 * N + ng + 1]
+    gsum = o[4 * M + 2 * N + ng + 1:4 * M + 2 * N + ng + 1 + 4 * Q]
+    info = torch.zeros(1, dtype=torch.int32, device=DEV)
+    tp, pp = ty_h.ctypes.data, pr_h.ctypes.data
+    assert lib.gp2d_hsum_lml_grad(Xd.data_ptr(), N, ldx, yd.data_ptr(), Q, tp, pp, 0.01, 1e-8, ws.data_ptr(), ws.numel(),
+                                  scal.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_hsum_fit(Xd.data_ptr(), N, ldx, yd.data_ptr(), Q, tp, pp, 0.01, 1e-8, ws.data_ptr(), ws.numel(),
+                             alpha.data_ptr(), lml1.data_ptr(), info.data_ptr(), _stream()) == 0
+    assert lib.gp2d_hsum_predict(ws.data_ptr(), N, ldx, Q, tp, pp, Xsd.data_ptr(), M, M, 0.01, mean.data_ptr(), var.data_ptr(),
+                                 pws.data_ptr(), pws.numel(), _stream()) == 0
+    ld = 2 * M + 4
+    KW, Kb = _guarded(8 * 2 * N * ld)
+    assert lib.gp2d_hsum_kernel_build(Xd.data_ptr(), N, Xsd.data_ptr(), M, ldx, Q, tp, pp, 0.0, Kb.data_ptr(), ld, _stream()) == 0
+    Wd = dev(rng.normal(size=(2 * N, 2 * M)))
+    gW, gws = _guarded(lib.gp2d_hsum_kernel_grad_workspace_bytes(N, M, Q))
+    assert lib.gp2d_hsum_kernel_grad(Xd.data_ptr(), N, Xsd.data_ptr(), M, ldx, Q, tp, pp, Wd.data_ptr(), 2 * M, gws.data_ptr(),
+                                     gws.numel(), gsum.data_ptr(), _stream()) == 0
+    torch.cuda.synchronize()
+    assert _intact(wsW) and _intact(pwW) and _intact(outW) and _intact(KW) and _intact(gW)
+    Kv = Kb.view(torch.float64)[:2 * N * ld].view(2 * N, ld)
+    assert bool((Kv[:, 2 * M:].contiguous().view(torch.uint8) == 0xA5).all())
+    np.testing.assert_allclose(Kv[:, :2 * M].cpu().numpy(), orc.hsum_K(X, Xs, ty_h, pr_h), rtol=0, atol=1e-13)
+    f = orc.hsum_fit(X, y, ty_h, pr_h, 0.01, jitter=1e-8)
+    mo, vo = orc.hsum_predict(X, f, ty_h, pr_h, Xs, var_add=0.01)
+    np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-8 * max(np.abs(mo).max(), 1e-3))
+    np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+    assert abs(float(lml1[0]) - f["lml"]) <= 1e-6 * abs(f["lml"]) and float(scal[0]) == float(lml1[0])
+    np.testing.assert_allclose(gsum.cpu().numpy().reshape(Q, 4), orc.hsum_kernel_grad_sums(Wd.cpu().numpy(), X, Xs, ty_h, pr_h),
+                               rtol=1e-9, atol=1e-9 * np.sqrt(N * M))
+
+
 def test_config3_full_size_properties():
     """BASELINE.json configs[2]: N=16384 observations (32768 x 32768 fp64 covariance).  The oracle
     cannot factorise this in test time, so parity rests on size-independent properties: the GP

@@ -186,6 +186,30 @@ def gemm_small():
     lib.gp2d_dbg_set_small_tile_threshold(-1)
 
 
+def hsum(N=2000, grid=(320, 320)):
+    """Term-sum family at the configs[1] size: fit, likelihood gradient and prediction against the
+    Helmholtz family on the same data (Q = 2 terms, with and without the time factor)."""
+    X, y = synthetic.drifter_snapshot(N, config_id=2)
+    Xs = synthetic.prediction_grid(X, *grid)
+    M, n = Xs.shape[0], 2 * N
+    fl = float(n) * n * 2 * M
+    rng = np.random.default_rng(0)
+    X3 = np.ascontiguousarray(np.c_[rng.uniform(0, 6, N), X])
+    Xs3 = np.ascontiguousarray(np.c_[np.full(M, 3.0), Xs])
+    Xd, Xsd, X3d, Xs3d = (gp.as_dev(a) for a in (X, Xs, X3, Xs3))
+    ref = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+    t_fit, t_pred, t_grad = timeit(ref.fit_async), timeit(lambda: ref.predict(Xsd)), timeit(ref.lml_and_grad)
+    print("helmholtz        : fit %.3f ms, lml+grad %.3f ms, predict %.3f ms (%.2f TF/s)" % (t_fit * 1e3, t_grad * 1e3, t_pred * 1e3, fl / t_pred / 1e12))
+    for name, pts, gpts, types, params in (
+            ("hsum Q=2 (y,x)  ", Xd, Xsd, [0, 1], [[0.2, 1, 1.3, 1.3], [0.8, 1, 3.1, 3.1]]),
+            ("hsum Q=2 (t,y,x)", X3d, Xs3d, [0, 1], [[0.2, 2.0, 1.3, 1.5], [0.8, 3.0, 3.1, 2.7]]),
+            ("hsum Q=4 (t,y,x)", X3d, Xs3d, [0, 1, 0, 1], [[0.2, 2.0, 1.3, 1.5], [0.8, 3.0, 3.1, 2.7], [0.1, 1.0, 0.7, 0.6], [0.3, 5.0, 6.0, 5.0]]),
+            ("hsum Q=8 (t,y,x)", X3d, Xs3d, [0, 1] * 4, [[0.2 + 0.05 * q, 2.0 + q, 1.3 + 0.2 * q, 1.5 + 0.1 * q] for q in range(8)])):
+        g = gp.HelmholtzSumGP(pts, y, types, params, 0.05)
+        t_fit, t_pred, t_grad = timeit(g.fit_async), timeit(lambda: g.predict(gpts)), timeit(g.lml_and_grad)
+        print("%s: fit %.3f ms, lml+grad %.3f ms, predict %.3f ms (%.2f TF/s)" % (name, t_fit * 1e3, t_grad * 1e3, t_pred * 1e3, fl / t_pred / 1e12))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["micro", "stages", "potrf"]
     if "micro" in what:
@@ -202,5 +226,7 @@ if __name__ == "__main__":
         split_calibration()
     if "rbf" in what:
         rbf()
+    if "hsum" in what:
+        hsum()
     if "gemm_small" in what:
         gemm_small()

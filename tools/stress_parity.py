@@ -1,5 +1,5 @@
 """Randomised parity sweep (not part of the test suite): many random sizes / hyper-parameters for the
-three kernel families, CUDA path against the CPU oracle at the BASELINE.json tolerances.
+four kernel families, CUDA path against the CPU oracle at the BASELINE.json tolerances.
 Usage: python tools/stress_parity.py [cases] [seed]"""
 import os
 import sys
@@ -22,7 +22,7 @@ def rel(a, b, floor):
 
 
 for c in range(cases):
-    fam = c % 3
+    fam = c % 4
     N = int(rng.choice([1, 2, 3, 15, 16, 17, 31, 33, 63, 64, 65, 100, 127, 128, 129, 200, 255, 257, 400, 511, 513, 700]))
     M = int(rng.choice([1, 2, 63, 64, 65, 127, 128, 129, 300, 1000, 2601, 5000]))
     noise = float(10 ** rng.uniform(-3, -1))
@@ -51,6 +51,20 @@ for c in range(cases):
             lo, go = orc.rbf_lml_and_grad(X, y, v, ls, noise, jitter=1e-8)
             f = orc.rbf_fit(X, y, v, ls, noise, jitter=1e-8)
             mo, vo = orc.rbf_predict(X, f, v, ls, Xs)
+        elif fam == 3:
+            ldx, Q = int(rng.choice([2, 3])), int(rng.integers(1, 9))
+            X = np.c_[rng.uniform(0, 6, N), rng.uniform(0, side, (N, 2))][:, 3 - ldx:]
+            Xs = np.c_[rng.uniform(0, 6, M), rng.uniform(-1, side + 1, (M, 2))][:, 3 - ldx:]
+            X, Xs = np.ascontiguousarray(X), np.ascontiguousarray(Xs)
+            y = rng.normal(size=2 * N) * 0.3
+            ty = rng.integers(0, 2, Q)
+            pr = np.c_[rng.uniform(0.05, 1.5, Q), rng.uniform(0.5, 5, Q), rng.uniform(0.4, 3, (Q, 2))]
+            g = gp.HelmholtzSumGP(X, y, ty, pr, noise, jitter=1e-8)
+            lml, grad = g.lml_and_grad()
+            mean, var = g.predict(Xs)
+            lo, go = orc.hsum_lml_and_grad(X, y, ty, pr, noise, jitter=1e-8)
+            f = orc.hsum_fit(X, y, ty, pr, noise, jitter=1e-8)
+            mo, vo = orc.hsum_predict(X, f, ty, pr, Xs)
         else:
             X = np.c_[rng.uniform(0, 6, N), rng.uniform(0, side, (N, 2))]
             Xs = np.c_[rng.uniform(0, 6, M), rng.uniform(-1, side + 1, (M, 2))]
