@@ -72,6 +72,27 @@ bool theta_ok(double l_df, double l_cf, double ratio) {
     return l_df > 0.0 && l_cf > 0.0 && ratio >= 0.0 && ratio <= 1.0 && isfinite(l_df) && isfinite(l_cf);
 }
 
+// Robust mode of the factorisation.  The recursion forms every panel of L with the explicit inverse of
+// the block above it, so its error grows with the condition number; cond(K + d I) <= n k** / d is
+// known from the arguments alone.  Past 1e7 (parity at 1e-8 is no longer safe) the panels are refined
+// against the factor (potri_lower, t_refine): +2 GEMMs per panel, no side-stream overlap.  The GP
+// configurations of BASELINE.json sit at 1e4-1e5; the per-drifter track models at 1e12-1e13.
+constexpr double ROBUST_COND = 1e7;
+int refine_steps_for(double kss, long n_scalar, double diag_add) {
+    if (!(diag_add > 0.0)) return 1;
+    return (kss * (double)n_scalar / diag_add > ROBUST_COND) ? 1 : 0;
+}
+
+// factor + inverse of the padded covariance in ws (A destroyed or replaced by L), robust when asked
+cudaError_t factor_ws(void* ws, const FitLayout& L, int refine, cudaStream_t st) {
+    double* A = at<double>(ws, L.off_A);
+    double* Z = at<double>(ws, L.off_Z);
+    // robust mode keeps L in A and borrows the packed-tile region (written after the factorisation,
+    // npad (npad + 128) / 2 doubles >= (npad / 2)^2) as panel scratch
+    return potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
+                       /*need_inv=*/true, /*keep_L=*/refine > 0, refine > 0 ? at<double>(ws, L.off_Zt) : nullptr, st, refine);
+}
+
 __global__ void fill_kernel(double* out, int n, double v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
@@ -150,8 +171,7 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     if (e != cudaSuccess) return e;
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
-                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    e = factor_ws(ws, L, refine_steps_for(hp.tvar * (hp.w_df + hp.w_cf), 2L * N, diag_add), st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
@@ -250,7 +270,7 @@ int gp2d_potrf(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* in
 size_t gp2d_spd_inverse_workspace_bytes(int n) {
     if (n <= 0) return 256;
     size_t np = (size_t)round_up(n, TILE);
-    return align256(np * np * 8) * 2 + align256(np * 8);
+    return align256(np * np * 8) * 2 + align256((np / 2) * (np / 2) * 8 + 256) + align256(np * 8);
 }
 
 int gp2d_spd_inverse(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* info, void* stream) {
@@ -264,11 +284,13 @@ int gp2d_spd_inverse(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, i
     size_t o = 0;
     double* P = at<double>(ws, o); o += align256((size_t)np * np * 8);
     double* Z = at<double>(ws, o); o += align256((size_t)np * np * 8);
+    double* W = at<double>(ws, o); o += align256((size_t)(np / 2) * (np / 2) * 8 + 256);
     double* logdiag = at<double>(ws, o);
     pad_lower_kernel<<<592, 256, 0, st>>>(A, (long)lda, n, P, np);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_rc(e);
-    e = potri_lower(P, np, Z, np, np, logdiag, info, /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    // a general-purpose inverse has to cope with ill-conditioned input: factor panels refined (linalg.h)
+    e = potri_lower(P, np, Z, np, np, logdiag, info, /*need_inv=*/true, /*keep_L=*/true, W, st, /*t_refine=*/1);
     if (e != cudaSuccess) return cuda_rc(e);
     e = launch_dgemm(true, true, GemmArgs{Z, np, Z, np, P, np, np, np, np, 1.0, 0.0, 1, KR_GE_M}, st);
     if (e != cudaSuccess) return cuda_rc(e);
@@ -552,8 +574,7 @@ cudaError_t rbf_fit_core(const double* X, int N, const double* y, const RbfParam
     if (e != cudaSuccess) return e;
     e = rbf_build_padded_lower(X, N, rp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
-                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    e = factor_ws(ws, L, refine_steps_for(rp.kss, (long)N, diag_add), st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
@@ -717,8 +738,7 @@ cudaError_t hsum_fit_core(const double* X, int N, const double* y, const HsumPar
     if (e != cudaSuccess) return e;
     e = hsum_build_interleaved_lower(X, N, sp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
-                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st);
+    e = factor_ws(ws, L, refine_steps_for(sp.kss0 > sp.kss1 ? sp.kss0 : sp.kss1, 2L * N, diag_add), st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;

@@ -208,7 +208,8 @@ potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int
     // L = q * diag(1/sqrt(d)) back to A (lower), Z = diag(1/sqrt(d)) * Y
     for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
         const int r = idx >> 7, c = idx & 127;
-        if (c <= r) A[(long)r * lda + c] = S[r * LEAF_LD + c] * dsave[c];
+        // the strict upper triangle is cleared: with keep_L the refinement GEMMs read whole diagonal tiles of L
+        A[(long)r * lda + c] = (c <= r) ? S[r * LEAF_LD + c] * dsave[c] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -284,6 +285,7 @@ struct PotriCtx {
     cudaStream_t st;
     cudaError_t err;
     PotriSide* side;    // nullptr: everything on st
+    int t_refine;       // refinement steps of every panel T (needs keep_L), see potri_lower
 };
 
 static void gemm_checked(PotriCtx& c, bool a_mn, bool b_mn, const GemmArgs& g, cudaStream_t st) {
@@ -313,6 +315,20 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
     potri_rec(c, off, n1, true, depth + 1);
     // T = A21 * Z11^T -> Z21 (scratch use of the block that will later hold Z21)
     gemm_checked(c, false, false, GemmArgs{A21, c.lda, Z11, c.ldz, Z21, c.ldz, n2, n1, n1, 1.0, 0.0, 0, KR_LE_N}, c.st);
+    // T was formed with the EXPLICIT inverse of L11, so its error grows with cond(L11); the Schur
+    // complement A22 - T T^T of an ill-conditioned covariance (entries ~ noise level under entries
+    // ~ prior variance) does not survive that.  One step of iterative refinement against the factor
+    // itself, T += (A21 - T L11^T) Z11^T, brings T L11^T = A21 down to rounding level -- the
+    // backward-stable result a triangular solve would give -- with two more GEMMs on the DMMA pipe.
+    for (int it = 0; it < c.t_refine && c.keep_L; ++it) {
+        const double* L11 = c.A + (long)off * (c.lda + 1);
+        if (c.err == cudaSuccess) {
+            copy2d_kernel<<<296, 256, 0, c.st>>>(A21, c.lda, c.W, n1, n2, n1);
+            c.err = cudaGetLastError();
+        }
+        gemm_checked(c, false, false, GemmArgs{Z21, c.ldz, L11, c.lda, c.W, n1, n2, n1, n1, -1.0, 1.0, 0, KR_LE_N}, c.st);
+        gemm_checked(c, false, false, GemmArgs{c.W, n1, Z11, c.ldz, Z21, c.ldz, n2, n1, n1, 1.0, 1.0, 0, KR_LE_N}, c.st);
+    }
     // U = T * Z11 into A21 (free once T is formed) on the side stream of this depth
     const bool fork = need_inv && !c.keep_L && c.side && depth < POTRI_MAX_DEPTH && n >= 4 * TILE;
     if (fork && c.err == cudaSuccess) {
@@ -341,7 +357,7 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
 }
 
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
-                        bool need_inv, bool keep_L, double* W, cudaStream_t st) {
+                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine) {
     if (n % TILE || n <= 0) return cudaErrorInvalidValue;
     static PerDeviceOnce leaf_once;
     const int slot = leaf_once.pending();
@@ -353,7 +369,8 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     PotriSide* side = (g_potri_overlap && !keep_L && need_inv && n >= 4 * TILE && g_side.init()) ? &g_side : nullptr;
-    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess, side};
+    if (t_refine > 0 && (!keep_L || !W)) return cudaErrorInvalidValue;
+    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess, side, t_refine};
     potri_rec(c, 0, n, need_inv, 0);
     return c.err;
 }

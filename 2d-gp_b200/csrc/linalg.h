@@ -12,8 +12,10 @@ namespace gp2d {
 // Z = L^-1 (lower; upper off-diagonal tiles untouched).  A is destroyed unless keep_L
 // (then its lower triangle holds L and W must be an (n/2)^2 scratch).  logdiag[n] receives
 // log(L_ii); *info the 1-based index of the first non-positive pivot, else 0.
+// t_refine > 0 (needs keep_L and W): every off-diagonal panel of L gets that many steps of iterative
+// refinement against the factor (robust mode for ill-conditioned matrices, see potri_rec).
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
-                        bool need_inv, bool keep_L, double* W, cudaStream_t st);
+                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine = 0);
 void set_potri_overlap(bool on);      // bring-up switch: side-stream overlap of the inverse GEMMs
 // alpha = Z^T Z y and LML from Z, logdiag.  y_block is the caller's vector: stacked [u;v] of
 // length 2N (ncomp = 2) or N scalar observations (ncomp = 1); everything else is internal

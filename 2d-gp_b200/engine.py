@@ -520,6 +520,35 @@ class ScalarGP:
                       "gp2d_rbf_predict")
         return mean, var
 
+    def predict_refined(self, Xs, include_noise=False, steps=3):
+        """Prediction for ILL-CONDITIONED covariances (prior variance many orders of magnitude above
+        the noise: the per-drifter track models of laser_io_methods.py:464-503 have cond(K) ~ 1e13).
+        The fused path applies the explicit inverse factor, whose error grows with cond(K); here the
+        (refined) inverse is only a preconditioner and both solves are iterated against fp64
+        residuals,  alpha += P (y - K alpha),  W += P (K*^T - K W),  var = k** - colsum(K*^T o W),
+        which ends at the accuracy of a backward-stable Cholesky solve.  Everything is kernel builds
+        and DMMA GEMMs of this library; K* [M,N] and W [N,M] are materialised, so this is for the
+        small problems where it is needed, not for the gridded hot path."""
+        Xsd = _coords(Xs, self.device)
+        if Xsd.shape[1] != self.D:
+            raise ValueError("prediction points must have %d columns" % self.D)
+        Kh = rbf_K(self.X, None, self.var, self.ls, diag_add=self.noise + self.jitter)
+        try:
+            P = spd_inverse(Kh)
+        except LinAlgError:
+            raise
+        Ks = rbf_K(Xsd, self.X, self.var, self.ls)                    # [M, N]
+        KsT = Ks.t().contiguous()
+        a = matmul(P, self.y)
+        W = matmul(P, KsT)
+        for _ in range(int(steps)):
+            a = a + matmul(P, self.y - matmul(Kh, a))
+            W = W + matmul(P, KsT - matmul(Kh, W))
+        mean = matmul(Ks, a)
+        var = float(np.sum(self.var)) - (KsT * W).sum(0)
+        var = torch.clamp(var, min=0.0) + (self.noise if include_noise else 0.0)
+        return mean, var
+
     def lml_and_grad(self):
         """(LML, grad) with grad over (variance_q, lengthscale_q[..])_q then the noise variance."""
         ng = self.Q * (1 + self.D) + 1
