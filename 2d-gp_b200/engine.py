@@ -158,6 +158,50 @@ def matmul(A, B) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# Iterated solves for ill-conditioned covariances (DESIGN.md §7 "Conditioning")
+# ------------------------------------------------------------------------------------------
+REFINE_CHUNK = 1 << 25      # doubles in one K* chunk (256 MB)
+ROBUST_COND = 1e7           # same threshold as csrc/capi.cu refine_steps_for
+
+
+def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3, chunk_elems=REFINE_CHUNK):
+    """Prediction whose accuracy does not degrade with cond(K): the fused kernel applies the explicit
+    inverse factor (error ~ cond(K) eps), here the refined inverse P is only a preconditioner and
+    both solves are iterated against fp64 residuals,
+        alpha += P (y - K alpha),   W += P (K*^T - K W),   var = k** - colsum(K*^T o W),
+    ending at the accuracy of a backward-stable Cholesky solve (three steps at cond 1e13).  Built
+    from this library's kernel builds, gp2d_spd_inverse and gp2d_dgemm; K* and W are materialised
+    chunk by chunk over the grid points, ~8x the flops of the fused pass.
+    K_fn(A, B, diag) -> covariance block (reference layout); ncomp = 2 for the stacked vector
+    kernels; kdiag_fn(m) -> prior variances of an m-point chunk in the same stacking."""
+    dev = X.device
+    N = int(X.shape[0])
+    n = ncomp * N
+    Kh = K_fn(X, None, diag_add)
+    P = spd_inverse(Kh)
+    a = matmul(P, y)
+    for _ in range(int(steps)):
+        a = a + matmul(P, y - matmul(Kh, a))
+    M = int(Xs.shape[0])
+    mean = torch.empty(ncomp * M, dtype=torch.float64, device=dev)
+    var = torch.empty(ncomp * M, dtype=torch.float64, device=dev)
+    step = max(1, int(chunk_elems) // max(n * ncomp, 1))
+    for lo in range(0, M, step):
+        hi = min(M, lo + step)
+        Ks = K_fn(Xs[lo:hi], X, 0.0)                       # [ncomp (hi-lo), n]
+        KsT = Ks.t().contiguous()
+        W = matmul(P, KsT)
+        for _ in range(int(steps)):
+            W = W + matmul(P, KsT - matmul(Kh, W))
+        mc = matmul(Ks, a)
+        vc = torch.clamp(kdiag_fn(hi - lo) - (KsT * W).sum(0), min=0.0) + var_add
+        for c in range(ncomp):
+            mean[c * M + lo:c * M + hi] = mc[c * (hi - lo):(c + 1) * (hi - lo)]
+            var[c * M + lo:c * M + hi] = vc[c * (hi - lo):(c + 1) * (hi - lo)]
+    return mean, var
+
+
+# ------------------------------------------------------------------------------------------
 class HelmholtzGP:
     """Fit state of one snapshot on one GPU.
 
@@ -238,6 +282,20 @@ class HelmholtzGP:
                                        self.noise if include_noise else 0.0, _ptr(mean), _ptr(var),
                                        _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_predict")
         return mean, var
+
+    def cond_bound(self):
+        """n k** / (noise + jitter) >= cond(K + (noise + jitter) I), from the arguments alone."""
+        d = self.noise + self.jitter
+        kss = self.ratio / self.l_df ** 2 + (1.0 - self.ratio) / self.l_cf ** 2
+        return float("inf") if d <= 0 else 2 * self.N * kss / d
+
+    def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
+        """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
+        Xsd = _points(Xs, self.device)
+        th = (self.l_df, self.l_cf, self.ratio)
+        return refined_predict(lambda A, B, d=0.0: kernel_K(A, B, *th, diag_add=d), self.X, self.y, Xsd, 2,
+                               lambda m: kernel_Kdiag(m, *th, device=self.device), self.noise + self.jitter,
+                               self.noise if include_noise else 0.0, steps, chunk_elems)
 
     def lml_and_grad(self, reference_compat=False):
         """(LML, grad[4]) with grad over (l_df, l_cf, ratio, noise) as host floats."""
@@ -366,6 +424,19 @@ class SpaceTimeGP:
                                           self.noise if include_noise else 0.0, _ptr(mean), _ptr(var), _ptr(self._pws),
                                           self._pws.numel(), _stream()), "gp2d_st_predict")
         return mean, var
+
+    def cond_bound(self):
+        l_df, l_cf, ratio, tvar, _ = self.theta
+        d = self.noise + self.jitter
+        return float("inf") if d <= 0 else 2 * self.N * tvar * (ratio / l_df ** 2 + (1.0 - ratio) / l_cf ** 2) / d
+
+    def predict_refined(self, Xs3, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
+        """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
+        Xsd = _points3(Xs3, self.device)
+        l_df, l_cf, ratio, tvar, _ = self.theta
+        return refined_predict(lambda A, B, d=0.0: st_K(A, B, *self.theta, diag_add=d), self.X, self.y, Xsd, 2,
+                               lambda m: tvar * kernel_Kdiag(m, l_df, l_cf, ratio, device=self.device),
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
 
     def lml_and_grad(self):
         """(LML, grad[6]) over (l_df, l_cf, ratio, tvar, lt, noise)."""
@@ -520,34 +591,19 @@ class ScalarGP:
                       "gp2d_rbf_predict")
         return mean, var
 
-    def predict_refined(self, Xs, include_noise=False, steps=3):
-        """Prediction for ILL-CONDITIONED covariances (prior variance many orders of magnitude above
-        the noise: the per-drifter track models of laser_io_methods.py:464-503 have cond(K) ~ 1e13).
-        The fused path applies the explicit inverse factor, whose error grows with cond(K); here the
-        (refined) inverse is only a preconditioner and both solves are iterated against fp64
-        residuals,  alpha += P (y - K alpha),  W += P (K*^T - K W),  var = k** - colsum(K*^T o W),
-        which ends at the accuracy of a backward-stable Cholesky solve.  Everything is kernel builds
-        and DMMA GEMMs of this library; K* [M,N] and W [N,M] are materialised, so this is for the
-        small problems where it is needed, not for the gridded hot path."""
+    def cond_bound(self):
+        d = self.noise + self.jitter
+        return float("inf") if d <= 0 else self.N * float(np.sum(self.var)) / d
+
+    def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
+        """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
         Xsd = _coords(Xs, self.device)
         if Xsd.shape[1] != self.D:
             raise ValueError("prediction points must have %d columns" % self.D)
-        Kh = rbf_K(self.X, None, self.var, self.ls, diag_add=self.noise + self.jitter)
-        try:
-            P = spd_inverse(Kh)
-        except LinAlgError:
-            raise
-        Ks = rbf_K(Xsd, self.X, self.var, self.ls)                    # [M, N]
-        KsT = Ks.t().contiguous()
-        a = matmul(P, self.y)
-        W = matmul(P, KsT)
-        for _ in range(int(steps)):
-            a = a + matmul(P, self.y - matmul(Kh, a))
-            W = W + matmul(P, KsT - matmul(Kh, W))
-        mean = matmul(Ks, a)
-        var = float(np.sum(self.var)) - (KsT * W).sum(0)
-        var = torch.clamp(var, min=0.0) + (self.noise if include_noise else 0.0)
-        return mean, var
+        kss = float(np.sum(self.var))
+        return refined_predict(lambda A, B, d=0.0: rbf_K(A, B, self.var, self.ls, diag_add=d), self.X, self.y, Xsd, 1,
+                               lambda m: torch.full((m,), kss, dtype=torch.float64, device=self.device),
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
 
     def lml_and_grad(self):
         """(LML, grad) with grad over (variance_q, lengthscale_q[..])_q then the noise variance."""
@@ -719,6 +775,20 @@ class HelmholtzSumGP:
                                             self.noise if include_noise else 0.0, _ptr(mean), _ptr(var),
                                             _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_hsum_predict")
         return mean, var
+
+    def cond_bound(self):
+        d = self.noise + self.jitter
+        kss = float(hsum_Kdiag(1, self.ldx, self.types, self.params, device=self.device).max().item())
+        return float("inf") if d <= 0 else 2 * self.N * kss / d
+
+    def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
+        """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
+        Xsd = _points23(Xs, self.device)
+        if Xsd.shape[1] != self.ldx:
+            raise ValueError("prediction points must have %d columns" % self.ldx)
+        return refined_predict(lambda A, B, d=0.0: hsum_K(A, B, self.types, self.params, diag_add=d), self.X, self.y, Xsd, 2,
+                               lambda m: hsum_Kdiag(m, self.ldx, self.types, self.params, device=self.device),
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
 
     def lml_and_grad(self):
         """(LML, grad) with grad over (var, lt, la, lb)_q for every term, then the noise variance."""

@@ -121,7 +121,7 @@ def _track_model(X, Y, optimize, max_iters, device):
     return m
 
 
-def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None, refine_steps=3):
+def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
     """One drifter (laser_io_methods.py:637-700): dict with the interpolated lon / lat and their
     posterior variances on ``time`` (NaN outside the drifter's life span), centred-difference
     velocities, the per-interval data counts and the hyper-parameters of both models.  Times are
@@ -143,12 +143,11 @@ def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None, 
         for name, raw in (("Lon", dr.lon), ("Lat", dr.lat)):
             Y = np.asarray(raw, dtype=np.float64)[sel][:, None]
             m = _track_model(X, Y, optimize, max_iters, device)
-            # cond(K) ~ variance / noise ~ 1e10-1e13 for these models: the iterated solve, not the
-            # fused explicit-inverse path (engine.ScalarGP.predict_refined)
-            m._sync()
-            mean, var = m._gp.predict_refined(Tg, include_noise=True, steps=refine_steps)
-            out[name.lower()][it] = mean.cpu().numpy()
-            out["var" + name][it] = var.cpu().numpy()
+            # cond(K) ~ n variance / noise ~ 1e10-1e13 for these models: predict() takes the iterated
+            # solve by itself, not the fused explicit-inverse path (engine.refined_predict)
+            mean, var = m.predict(Tg)
+            out[name.lower()][it] = mean[:, 0]
+            out["var" + name][it] = var[:, 0]
             out["len" + name] = m.rbf.lengthscale[0]
             out["variance" + name] = m.rbf.variance[0]
             out["noise" + name] = m.Gaussian_noise[0]

@@ -18,7 +18,7 @@ import pickle
 import numpy as np
 import scipy.optimize as sopt
 
-from .engine import HelmholtzGP, HelmholtzSumGP, LinAlgError, ScalarGP, SpaceTimeGP
+from .engine import HelmholtzGP, HelmholtzSumGP, LinAlgError, ROBUST_COND, ScalarGP, SpaceTimeGP
 from .kern import RBF, Add, Prod, _ScalarKern
 from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase, Kt, SpaceTimeKern
 from .myKernel2 import _HelmholtzSumKern, HelmholtzSum, divFreeK, curlFreeK
@@ -310,7 +310,11 @@ class GPRegression:
         return self.optimization_runs
 
     # ---- prediction ------------------------------------------------------------------------
-    def predict(self, Xnew, full_cov=False, include_likelihood=True):
+    def predict(self, Xnew, full_cov=False, include_likelihood=True, refined=None):
+        """GPy's model.predict: ([M or 2M, 1] mean, variance), Gaussian noise included.  ``refined``:
+        None picks the iterated-solve path when the covariance is ill-conditioned
+        (n k** / (noise + jitter) > 1e7, engine.refined_predict; DESIGN.md §7 "Conditioning") and the
+        fused kernel otherwise; True / False force one of them."""
         if full_cov:
             raise NotImplementedError("only marginal variances (the reference never asks for full_cov)")
         Xnew = np.asarray(Xnew, dtype=np.float64)
@@ -325,7 +329,13 @@ class GPRegression:
         if not self._gp.fitted:
             self._sync()
             self._gp.fit()
-        mean, var = self._gp.predict(Xnew, include_noise=include_likelihood)
+        if refined is None:
+            refined = self._gp.cond_bound() > ROBUST_COND
+        if refined:
+            self._sync()
+            mean, var = self._gp.predict_refined(Xnew, include_noise=include_likelihood)
+        else:
+            mean, var = self._gp.predict(Xnew, include_noise=include_likelihood)
         return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
 
     # ---- persistence (krig.py:412,438,452) -----------------------------------------------------

@@ -622,3 +622,39 @@ def test_results_do_not_depend_on_previous_workspace_contents():
         for o in outs[1:]:
             assert o[0] == outs[0][0] and np.array_equal(o[1], outs[0][1]), name
             assert torch.equal(o[2], outs[0][2]) and torch.equal(o[3], outs[0][3]), name
+
+
+def test_refined_prediction_all_families():
+    """engine.refined_predict: on a well-conditioned problem it reproduces the fused kernel (and the
+    oracle); on an ill-conditioned one (noise 1e-9 under a unit prior variance, cond ~ 1e11) it stays
+    with the oracle's backward-stable solve where the fused explicit-inverse path drifts."""
+    rng = np.random.default_rng(2)
+    N, M = 260, 333
+    X3 = np.c_[rng.uniform(0, 4, N), rng.uniform(0, 10, (N, 2))]
+    Xs3 = np.c_[rng.uniform(0, 4, M), rng.uniform(0, 10, (M, 2))]
+    y = np.concatenate([np.sin(X3[:, 1] / 2), np.cos(X3[:, 2] / 2)]) + 0.01 * rng.normal(size=2 * N)
+    ty, pr = [0, 1], [[0.6, 1.5, 1.3, 2.0], [1.4, 0.7, 3.1, 2.2]]
+    # ill-conditioned case: the data carry 1e-2 of noise against a modelled 1e-9, so |alpha| ~ 1e7 and even a
+    # backward-stable solve is only good to eps n |K| |alpha| ~ 5e-7: that floor is the tolerance there
+    for noise, tol_fused, tol_mean, tol_var in ((0.05, 1e-9, 2e-8, (1e-6, 1e-10)), (1e-9, None, 5e-6, (1e-3, 1e-9))):
+        cases = [
+            (gp.HelmholtzGP(X3[:, 1:], y, 1.3, 3.1, 0.2, noise), Xs3[:, 1:],
+             lambda: orc.predict(X3[:, 1:], orc.fit(X3[:, 1:], y, 1.3, 3.1, 0.2, noise), 1.3, 3.1, 0.2, Xs3[:, 1:])),
+            (gp.SpaceTimeGP(X3, y, 1.3, 3.1, 0.2, 1.5, 0.8, noise), Xs3,
+             lambda: orc.st_predict(X3, orc.st_fit(X3, y, 1.3, 3.1, 0.2, 1.5, 0.8, noise), 1.3, 3.1, 0.2, 1.5, 0.8, Xs3)),
+            (gp.HelmholtzSumGP(X3, y, ty, pr, noise), Xs3,
+             lambda: orc.hsum_predict(X3, orc.hsum_fit(X3, y, ty, pr, noise), ty, pr, Xs3)),
+            (gp.ScalarGP(X3, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], noise), Xs3,
+             lambda: orc.rbf_predict(X3, orc.rbf_fit(X3, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], noise), [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], Xs3)),
+        ]
+        for g, P, oracle in cases:
+            mo, vo = oracle()
+            mr, vr = g.predict_refined(P, chunk_elems=60000)          # several chunks
+            scale = max(np.abs(mo).max(), 1e-3)
+            np.testing.assert_allclose(mr.cpu().numpy(), mo, rtol=0, atol=tol_mean * scale)
+            np.testing.assert_allclose(vr.cpu().numpy(), vo, rtol=tol_var[0], atol=tol_var[1])
+            assert (g.cond_bound() > 1e7) == (noise < 1e-6)
+            if tol_fused is not None:
+                mf, vf = g.predict(P)
+                np.testing.assert_allclose(mf.cpu().numpy(), mr.cpu().numpy(), rtol=0, atol=tol_fused * scale)
+                np.testing.assert_allclose(vf.cpu().numpy(), vr.cpu().numpy(), rtol=1e-8, atol=1e-11)
