@@ -373,6 +373,17 @@ class GPRegression:
         return "GPRegression  log-likelihood %s\n%s" % (self._ll, "\n".join(rows))
 
 
+def _restore(m, st):
+    """Constraints and optimisation history of a pickled model onto the rebuilt one."""
+    for prm, c in zip(m.parameters, st["constraints"]):
+        prm.constraint = c
+    for d in st["runs"]:
+        r = _Run(None, None, None, None)
+        r.__dict__.update(d)
+        m.optimization_runs.append(r)
+    return m
+
+
 def load(path, device=None):
     """Counterpart of GPy.load (krig.py:438,478-482)."""
     with open(path, "rb") as f:
@@ -388,25 +399,13 @@ def load(path, device=None):
             terms.append((curlFreeK if ty else divFreeK)(input_dim=D, **kw))
         k = terms[0] if name != "HelmholtzSum" else HelmholtzSum(terms)
         m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
-        for prm, c in zip(m.parameters, st["constraints"]):
-            prm.constraint = c
-        for d in st["runs"]:
-            r = _Run(None, None, None, None)
-            r.__dict__.update(d)
-            m.optimization_runs.append(r)
-        return m
+        return _restore(m, st)
     if "space" in st:
         kxy = {"myKernel": lambda: myKernel(2, [1, 2], p[2], p[3], p[4]), "nonDivK": lambda: nonDivK(2, [1, 2], p[2]),
                "nonRotK": lambda: nonRotK(2, [1, 2], p[2])}[st["space"]]()
         k = Kt(1, [0], p[0], p[1]) * kxy
         m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
-        for prm, c in zip(m.parameters, st["constraints"]):
-            prm.constraint = c
-        for d in st["runs"]:
-            r = _Run(None, None, None, None)
-            r.__dict__.update(d)
-            m.optimization_runs.append(r)
-        return m
+        return _restore(m, st)
     if "factors" in st:
         fs, o = [], 0
         for d in st["factors"]:
@@ -414,13 +413,7 @@ def load(path, device=None):
             fs.append(RBF(d["input_dim"], p[o], p[o + 1:o + 1 + nl], ARD=d["ARD"], active_dims=d["dims"], name=d["name"]))
             o += 1 + nl
         m = GPRegression(st["X"], st["Y"], Prod(fs), noise_var=p[-1], jitter=st["jitter"], device=device)
-        for prm, c in zip(m.parameters, st["constraints"]):
-            prm.constraint = c
-        for d in st["runs"]:
-            r = _Run(None, None, None, None)
-            r.__dict__.update(d)
-            m.optimization_runs.append(r)
-        return m
+        return _restore(m, st)
     if "parts" in st:
         parts, o = [], 0
         for d in st["parts"]:
@@ -430,13 +423,7 @@ def load(path, device=None):
             o += 1 + nl
         k = parts[0] if len(parts) == 1 else Add(parts)
         m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
-        for prm, c in zip(m.parameters, st["constraints"]):
-            prm.constraint = c
-        for d in st["runs"]:
-            r = _Run(None, None, None, None)
-            r.__dict__.update(d)
-            m.optimization_runs.append(r)
-        return m
+        return _restore(m, st)
     if name == "myKernel":
         k = myKernel(2, st["active_dims"], p[0], p[1], p[2])
     elif name == "nonDivK":
@@ -445,10 +432,4 @@ def load(path, device=None):
         k = nonRotK(2, st["active_dims"], p[0])
     k.reference_compat = st.get("reference_compat", False)
     m = GPRegression(st["X"], st["Y"], k, noise_var=p[-1], jitter=st["jitter"], device=device)
-    for prm, c in zip(m.parameters, st["constraints"]):
-        prm.constraint = c
-    for d in st["runs"]:
-        r = _Run(None, None, None, None)
-        r.__dict__.update(d)
-        m.optimization_runs.append(r)
-    return m
+    return _restore(m, st)
