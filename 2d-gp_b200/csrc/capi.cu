@@ -77,10 +77,10 @@ bool theta_ok(double l_df, double l_cf, double ratio) {
 // known from the arguments alone.  Past 1e7 (parity at 1e-8 is no longer safe) the panels are refined
 // against the factor (potri_lower, t_refine): +2 GEMMs per panel, no side-stream overlap.  The GP
 // configurations of BASELINE.json sit at 1e4-1e5; the per-drifter track models at 1e12-1e13.
-constexpr double ROBUST_COND = 1e7;
+double g_robust_cond = 1e7;          // bring-up hook: gp2d_dbg_set_robust_cond
 int refine_steps_for(double kss, long n_scalar, double diag_add) {
     if (!(diag_add > 0.0)) return 1;
-    return (kss * (double)n_scalar / diag_add > ROBUST_COND) ? 1 : 0;
+    return (kss * (double)n_scalar / diag_add > g_robust_cond) ? 1 : 0;
 }
 
 // factor + inverse of the padded covariance in ws (A destroyed or replaced by L), robust when asked
@@ -962,6 +962,8 @@ int gp2d_dbg_fp64_mode(int mode, int iters, int ctas, double* out, void* stream)
 }
 
 int gp2d_dbg_set_small_tile_threshold(int t) { set_small_tile_threshold(t); return t; }
+
+int gp2d_dbg_set_robust_cond(double c) { g_robust_cond = c; return 0; }
 
 int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; }
 
