@@ -133,7 +133,7 @@ constexpr int LEAF_LD = TILE + 1;
 constexpr int LEAF_SMEM_BYTES = TILE * LEAF_LD * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0) {
+potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0, int keep_L) {
     extern __shared__ double S[];                 // [128][129] staging: A in, q/L out, Z out
     __shared__ double colbuf[2][TILE];
     __shared__ double dsave[TILE];                // pivots d_j, then 1/sqrt(d_j)
@@ -208,8 +208,9 @@ potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int
     // L = q * diag(1/sqrt(d)) back to A (lower), Z = diag(1/sqrt(d)) * Y
     for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
         const int r = idx >> 7, c = idx & 127;
-        // the strict upper triangle is cleared: with keep_L the refinement GEMMs read whole diagonal tiles of L
-        A[(long)r * lda + c] = (c <= r) ? S[r * LEAF_LD + c] * dsave[c] : 0.0;
+        // with keep_L the strict upper triangle is cleared too: the refinement GEMMs read whole diagonal tiles of L
+        if (c <= r) A[(long)r * lda + c] = S[r * LEAF_LD + c] * dsave[c];
+        else if (keep_L) A[(long)r * lda + c] = 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -301,7 +302,7 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
     if (n == TILE) {
         potri_leaf_kernel<<<1, NTHREADS, LEAF_SMEM_BYTES, c.st>>>(
             c.A + (long)off * (c.lda + 1), c.lda, c.Z + (long)off * (c.ldz + 1), c.ldz,
-            c.logdiag + off, c.info, off);
+            c.logdiag + off, c.info, off, c.keep_L ? 1 : 0);
         c.err = cudaGetLastError();
         return;
     }
