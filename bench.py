@@ -34,7 +34,7 @@ GRID = (320, 320)
 THETA = (1.3, 3.1, 0.2)
 NOISE = 0.05
 CPU_GRID_SAMPLE = 1024
-NCU_PREDICT_DRAM_BYTES = 109.308913e9 + 6.736914e9
+NCU_PREDICT_DRAM_BYTES = 108.822557e9 + 6.737815e9
 METRIC = "fit_predict_seconds_per_snapshot"
 WORKLOAD = ("configs[1]: single LASER-style snapshot, N=2000 obs (4000x4000 fp64 covariance), "
             "320x320=102400-point grid, curl-free+div-free SE kernel theta=(1.3,3.1,0.2), noise 0.05")
@@ -343,7 +343,7 @@ def run_ours(args):
                 "kernel": "predict_kernel (fused K* generation + Z K*^T DMMA + mean/variance)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
-                # profiles/r01e_predict_kernel.md (re-reads of the per-CTA K* panel; 14.6 % of DRAM peak)
+                # profiles/r01h_predict_kernel.md (re-reads of the per-CTA K* panel; 14.6 % of DRAM peak)
                 "traffic": NCU_PREDICT_DRAM_BYTES, "traffic_unit": "bytes",
                 "peak_source": "FP64 DMMA.8x8x4 register-resident loop measured live in this run "
                                "(MEASURED_PEAKS.json has no fp64 figure; HGX B200 datasheet: 37 TFLOP/s)",
