@@ -25,6 +25,7 @@ __all__ = [
     "haversine_km", "simlaser_inputs", "rbf_ard_K", "LOG_2PI",
     "kt_K", "st_K", "st_dK", "st_fit", "st_predict", "st_lml_and_grad",
     "rbf_sum_K", "rbf_sum_dK", "rbf_kernel_grad_sums", "rbf_fit", "rbf_predict", "rbf_lml_and_grad",
+    "hsum_K", "hsum_Kdiag", "hsum_dK", "hsum_kernel_grad_sums", "hsum_fit", "hsum_predict", "hsum_lml_and_grad",
 ]
 
 LOG_2PI = math.log(2.0 * math.pi)
