@@ -207,3 +207,41 @@ def test_mykernel2_two_dimensional_and_column_selection():
         myKernel2.divFreeK(input_dim=3) + myKernel2.divFreeK(input_dim=2)
     with pytest.raises(ValueError):
         myKernel2.HelmholtzSum([myKernel2.divFreeK()] * 9)
+
+
+def test_hsum_large_size_properties():
+    """N = 8192 observations (16384 x 16384 covariance), four space-time terms: the oracle cannot
+    factorise this in test time, so parity rests on size-independent properties -- the GP identity
+    K alpha = y - noise alpha at observation sites (ties build, Cholesky, inverse, alpha and the
+    fused predictive mean together), variance bounds, the far-field prior variances per component,
+    grid-partition invariance and agreement of the two likelihood entry points."""
+    from gp2d_b200 import synthetic
+    N = 8192
+    X2, y = synthetic.drifter_snapshot(N, config_id=5)
+    rng = np.random.default_rng(1)
+    X = np.ascontiguousarray(np.c_[rng.uniform(0, 2, N), X2])
+    types, params = CASES[3]
+    noise = 0.05
+    g = gp.HelmholtzSumGP(X, y, types, params, noise)
+    lml = g.fit()
+    assert np.isfinite(lml)
+    sel = rng.choice(N, 400, replace=False)
+    pm, pv = g.predict(X[sel])
+    al = g.alpha()
+    idx = torch.as_tensor(sel, device=al.device)
+    rhs = torch.cat([g.y[idx], g.y[N + idx]]) - noise * torch.cat([al[idx], al[N + idx]])
+    torch.testing.assert_close(pm, rhs, rtol=1e-9, atol=1e-11)
+    assert float(pv.min()) > 0.0 and float(pv.max()) < noise
+    far = np.array([[1.0, 1e4, 1e4], [0.5, -1e4, 3e4]])
+    fm, fv = g.predict(far)
+    kd = orc.hsum_Kdiag(2, types, params)
+    np.testing.assert_allclose(fv.cpu().numpy(), kd, rtol=1e-12)
+    assert float(fm.abs().max()) < 1e-12
+    G = np.ascontiguousarray(np.c_[np.full(600, 1.0), synthetic.prediction_grid(X2, 30, 20)])
+    ma, va = g.predict(G)
+    m1, v1 = g.predict(G[:217])
+    m2, v2 = g.predict(G[217:])
+    assert torch.equal(torch.cat([m1[:217], m2[:383], m1[217:], m2[383:]]), ma)
+    assert torch.equal(torch.cat([v1[:217], v2[:383], v1[217:], v2[383:]]), va)
+    lml2, grad = g.lml_and_grad()
+    assert lml2 == lml and np.all(np.isfinite(grad)) and grad.shape == (17,)
