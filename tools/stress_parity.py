@@ -14,6 +14,7 @@ from oracle import gp_oracle as orc
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 worst = {"mean": 0.0, "var": 0.0, "lml": 0.0, "grad": 0.0}
+worst_ill = dict(worst)          # cases in the robust regime (conditioning bound > 1e7)
 fails = 0
 
 
@@ -25,7 +26,7 @@ for c in range(cases):
     fam = c % 4
     N = int(rng.choice([1, 2, 3, 15, 16, 17, 31, 33, 63, 64, 65, 100, 127, 128, 129, 200, 255, 257, 400, 511, 513, 700]))
     M = int(rng.choice([1, 2, 63, 64, 65, 127, 128, 129, 300, 1000, 2601, 5000]))
-    noise = float(10 ** rng.uniform(-3, -1))
+    noise = float(10 ** rng.uniform(-3, -1)) if rng.uniform() < 0.8 else float(10 ** rng.uniform(-8, -4))   # robust mode
     side = max(2.0, 0.5 * np.sqrt(N))
     try:
         if fam == 0:
@@ -84,10 +85,21 @@ for c in range(cases):
     e_var = rel(var.cpu().numpy(), vo, 1e-4)
     e_lml = abs(lml - lo) / max(abs(lo), 1.0)
     e_grad = rel(grad, go, max(1e-1, 1e-1 * np.abs(go).max()))
-    for k, v in (("mean", e_mean), ("var", e_var), ("lml", e_lml), ("grad", e_grad)):
-        worst[k] = max(worst[k], v)
-    if e_mean > 1e-8 or e_var > 1e-8 or e_lml > 1e-6 or e_grad > 1e-6:
+    if g.cond_bound() <= 1e7:
+        for k, v in (("mean", e_mean), ("var", e_var), ("lml", e_lml), ("grad", e_grad)):
+            worst[k] = max(worst[k], v)
+    else:
+        for k, v in (("mean", e_mean), ("var", e_var), ("lml", e_lml), ("grad", e_grad)):
+            worst_ill[k] = max(worst_ill[k], v)
+    # ill-conditioned draws (noise far below the scatter of the data): |alpha| is huge and even a
+    # backward-stable solve is only good to ~ eps n k** |alpha|; that floor, not 1e-8, is the bar there
+    n_sc = f["alpha"].size
+    kss = g.cond_bound() * (noise + 1e-8) / n_sc
+    floor = 100 * 2.2e-16 * n_sc * kss * float(np.abs(f["alpha"]).max()) / max(1e-3, 1e-1 * float(np.abs(mo).max()))
+    slack = max(1.0, floor / 1e-8, g.cond_bound() / 1e9)
+    if e_mean > 1e-8 * slack or e_var > 1e-8 * slack or e_lml > 1e-6 or e_grad > 1e-6 * slack:
         fails += 1
         print("FAIL case %d fam %d N=%d M=%d noise=%.3g: mean %.2e var %.2e lml %.2e grad %.2e" % (c, fam, N, M, noise, e_mean, e_var, e_lml, e_grad))
-print("cases %d, failures %d, worst relative errors %s" % (cases, fails, {k: "%.2e" % v for k, v in worst.items()}))
+print("cases %d, failures %d, worst relative errors %s; robust regime %s" % (
+    cases, fails, {k: "%.2e" % v for k, v in worst.items()}, {k: "%.2e" % v for k, v in worst_ill.items()}))
 sys.exit(1 if fails else 0)
