@@ -192,7 +192,11 @@ def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3,
         KsT = Ks.t().contiguous()
         W = matmul(P, KsT)
         for _ in range(int(steps)):
-            W = W + matmul(P, KsT - matmul(Kh, W))
+            dW = matmul(P, KsT - matmul(Kh, W))
+            W = W + dW
+            # converged to rounding: a further step would not change the variance (one host read per step)
+            if float(dW.abs().max()) <= 1e-13 * float(W.abs().max()):
+                break
         mc = matmul(Ks, a)
         vc = torch.clamp(kdiag_fn(hi - lo) - (KsT * W).sum(0), min=0.0) + var_add
         for c in range(ncomp):
