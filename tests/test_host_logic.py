@@ -263,9 +263,26 @@ def _worker(rank, world, port, out_dir):
         # one factorisation, shipped to the other rank in pieces
         fitst = _FakeFit(rank, 1000)
         gdist.broadcast_fit(fitst, src=0, chunk_bytes=384)
+        # drifters sharded over ranks (laser_io_methods.interp_kriging): the per-drifter solver is stubbed,
+        # the sharding, the object gather and the assembly are the real ones
+        from gp2d_b200 import laser_io_methods as lio
+        calls = []
+
+        def fake_kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
+            calls.append(dr.id)
+            nT = time.size
+            base = float(dr.id[2:])
+            return {"lon": np.full(nT, base), "lat": np.full(nT, -base), "varLon": np.full(nT, 0.1), "varLat": np.full(nT, 0.2),
+                    "u": np.full(nT - 1, base), "v": np.full(nT - 1, base), "n_samples": np.zeros(nT - 1), "data_freq": np.zeros(nT - 1),
+                    "drog_stat": np.ones(nT), "lastDrogTime": -1, "lenLon": base, "lenLat": base, "varianceLon": 1.0,
+                    "varianceLat": 1.0, "noiseLon": 1e-7, "noiseLat": 1e-7}
+        lio.kriging = fake_kriging
+        fleet = [lio.drifter("L_%d" % i, None, np.arange(0.0, 7200.0, 300.0) + 1000.0, np.zeros(24), np.zeros(24)) for i in range(5)]
+        tr = lio.interp_kriging(fleet, dt=900, period=0.05, optimize=False, parallel=1)
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), got=got.numpy(), mean=mean.numpy(), var=var.numpy(),
                  best=best, loaded=model.loaded, shard=np.array(gdist.shard_range(200, rank, world)),
-                 state=fitst.buf.numpy(), fitted=fitst.fitted)
+                 state=fitst.buf.numpy(), fitted=fitst.fitted, track_lon=tr.lon, track_len=tr.lenLon,
+                 track_calls=np.array([int(c[2:]) for c in calls]))
     finally:
         dist.destroy_process_group()
 
@@ -286,3 +303,9 @@ def test_gloo_world2_gathers(tmp_path):
     assert r[0]["state"][0] == 1 and r[0]["state"][1] == 7 and bool(r[1]["fitted"])
     np.testing.assert_array_equal(r[0]["shard"], [0, 128])
     np.testing.assert_array_equal(r[1]["shard"], [128, 200])
+    # drifter n ran on rank n % 2 only, and both ranks hold the assembled fleet
+    np.testing.assert_array_equal(r[0]["track_calls"], [0, 2, 4])
+    np.testing.assert_array_equal(r[1]["track_calls"], [1, 3])
+    for k in range(2):
+        np.testing.assert_array_equal(r[k]["track_len"], np.arange(5.0))
+        np.testing.assert_array_equal(r[k]["track_lon"][:, 0], np.arange(5.0))
