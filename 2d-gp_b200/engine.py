@@ -287,11 +287,14 @@ class HelmholtzGP:
                                        _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_predict")
         return mean, var
 
+    def kss(self):
+        """Largest prior variance k(x, x) of a component."""
+        return self.ratio / self.l_df ** 2 + (1.0 - self.ratio) / self.l_cf ** 2
+
     def cond_bound(self):
         """n k** / (noise + jitter) >= cond(K + (noise + jitter) I), from the arguments alone."""
         d = self.noise + self.jitter
-        kss = self.ratio / self.l_df ** 2 + (1.0 - self.ratio) / self.l_cf ** 2
-        return float("inf") if d <= 0 else 2 * self.N * kss / d
+        return float("inf") if d <= 0 else 2 * self.N * self.kss() / d
 
     def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
         """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
@@ -429,10 +432,13 @@ class SpaceTimeGP:
                                           self._pws.numel(), _stream()), "gp2d_st_predict")
         return mean, var
 
-    def cond_bound(self):
+    def kss(self):
         l_df, l_cf, ratio, tvar, _ = self.theta
+        return tvar * (ratio / l_df ** 2 + (1.0 - ratio) / l_cf ** 2)
+
+    def cond_bound(self):
         d = self.noise + self.jitter
-        return float("inf") if d <= 0 else 2 * self.N * tvar * (ratio / l_df ** 2 + (1.0 - ratio) / l_cf ** 2) / d
+        return float("inf") if d <= 0 else 2 * self.N * self.kss() / d
 
     def predict_refined(self, Xs3, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
         """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
@@ -595,9 +601,12 @@ class ScalarGP:
                       "gp2d_rbf_predict")
         return mean, var
 
+    def kss(self):
+        return float(np.sum(self.var))
+
     def cond_bound(self):
         d = self.noise + self.jitter
-        return float("inf") if d <= 0 else self.N * float(np.sum(self.var)) / d
+        return float("inf") if d <= 0 else self.N * self.kss() / d
 
     def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
         """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""
@@ -780,10 +789,14 @@ class HelmholtzSumGP:
                                             _ptr(self._pws), self._pws.numel(), _stream()), "gp2d_hsum_predict")
         return mean, var
 
+    def kss(self):
+        v0 = sum(p[0] / (p[2] ** 2 if t else p[3] ** 2) for t, p in zip(self.types, self.params))
+        v1 = sum(p[0] / (p[3] ** 2 if t else p[2] ** 2) for t, p in zip(self.types, self.params))
+        return float(max(v0, v1))
+
     def cond_bound(self):
         d = self.noise + self.jitter
-        kss = float(hsum_Kdiag(1, self.ldx, self.types, self.params, device=self.device).max().item())
-        return float("inf") if d <= 0 else 2 * self.N * kss / d
+        return float("inf") if d <= 0 else 2 * self.N * self.kss() / d
 
     def predict_refined(self, Xs, include_noise=False, steps=3, chunk_elems=REFINE_CHUNK):
         """Iterated-solve prediction for ill-conditioned covariances, see refined_predict()."""

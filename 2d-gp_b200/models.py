@@ -145,7 +145,7 @@ class GPRegression:
         self._sync()
         if self.scalar:
             try:
-                self._ll, g = self._gp.lml_and_grad()
+                self._ll, g = self._jitchol(self._gp.lml_and_grad)
                 self.kern._scatter_gradient(g[:-1])
                 self.Gaussian_noise.gradient = float(g[-1])
             except LinAlgError:
@@ -155,7 +155,7 @@ class GPRegression:
             return self._ll
         if self.hsum:
             try:
-                self._ll, g = self._gp.lml_and_grad()
+                self._ll, g = self._jitchol(self._gp.lml_and_grad)
                 self.kern.scatter_gradient(g[:-1])
                 self.Gaussian_noise.gradient = float(g[-1])
             except LinAlgError:
@@ -165,7 +165,7 @@ class GPRegression:
             return self._ll
         if self.spacetime:
             try:
-                self._ll, g = self._gp.lml_and_grad()
+                self._ll, g = self._jitchol(self._gp.lml_and_grad)
                 self.kern.scatter_gradient(g[:5])
                 self.Gaussian_noise.gradient = float(g[5])
             except LinAlgError:
@@ -174,12 +174,36 @@ class GPRegression:
                     p.gradient = 0.0
             return self._ll
         try:
-            self._ll, g = self._gp.lml_and_grad(reference_compat=self.kern.reference_compat)
+            self._ll, g = self._jitchol(lambda: self._gp.lml_and_grad(reference_compat=self.kern.reference_compat))
         except LinAlgError:
             self._ll, g = -np.inf, np.zeros(4)
         for p, gi in zip(self.parameters, self._grad_natural(g)):
             p.gradient = float(gi)
         return self._ll
+
+    def _jitchol(self, fn):
+        """GPy's jitchol (GPy/util/linalg.py): when the factorisation finds a non-positive pivot,
+        retry with a diagonal jitter of 1e-6 mean(diag K) 10^k, k = 0..4, warn, and give up after
+        that (the caller then reports -inf, as the optimiser expects)."""
+        try:
+            return fn()
+        except LinAlgError:
+            pass
+        base = self._gp.jitter
+        scale = 1e-6 * (self._gp.kss() + float(self.Gaussian_noise))
+        try:
+            for k in range(5):
+                self._gp.jitter = base + scale * 10 ** k
+                try:
+                    out = fn()
+                except LinAlgError:
+                    continue
+                import warnings
+                warnings.warn("Added jitter of %.3e" % (scale * 10 ** k), RuntimeWarning)
+                return out
+            raise LinAlgError("not positive definite, even with jitter")
+        finally:
+            self._gp.jitter = base
 
     def log_likelihood(self):
         return float(self._ll)

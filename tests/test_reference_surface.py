@@ -353,3 +353,18 @@ def test_laser_workflow_on_synthetic_tracks():
     mt, _ = orc.fit_predict_inverse_form(X, np.concatenate([uo, vo]), 5, 4, 0.4, 0.0025, np.stack([xt, yt], axis=1), want_var=False)
     np.testing.assert_allclose(np.concatenate([uft, vft]), mt, rtol=1e-7, atol=1e-8 * scale)
     assert GP_laser.laser2 is GP_laser.laser
+
+
+def test_model_retries_with_jitter_like_gpys_jitchol():
+    """Duplicate observation sites and no noise: K + 1e-8 I is numerically singular.  GPy's jitchol
+    (GPy/util/linalg.py) then adds 1e-6 mean(diag K) 10^k to the diagonal and warns; so does the model
+    here, instead of reporting -inf."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 5, (40, 2))
+    X = np.concatenate([X, X, X])                                  # every site three times
+    y = rng.normal(size=2 * X.shape[0])
+    with pytest.warns(RuntimeWarning, match="Added jitter"):
+        m = models.GPRegression(X, y[:, None], myKernel.myKernel(2, [0, 1], 8.0, 8.0, 0.5), noise_var=1e-300, jitter=0.0)
+    assert np.isfinite(m.log_likelihood())
+    mean, var = m.predict(X[:5], refined=False)
+    assert np.all(np.isfinite(mean)) and np.all(var >= 0)
