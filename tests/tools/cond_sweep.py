@@ -1,12 +1,12 @@
 """Accuracy of the fused path against the oracle as the conditioning bound n k**/noise grows, with the
-plain and the robust (refined-panel) factorisation.  Usage: python tools/cond_sweep.py"""
+plain and the robust (refined-panel) factorisation.  Usage: python tests/tools/cond_sweep.py"""
 import ctypes as C
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gp2d_b200 as gp
 from gp2d_b200._lib import lib
 from oracle import gp_oracle as orc

@@ -1,13 +1,13 @@
 """Randomised parity sweep (not part of the test suite): many random sizes / hyper-parameters for the
 four kernel families, CUDA path against the CPU oracle at the BASELINE.json tolerances.
-Usage: python tools/stress_parity.py [cases] [seed]"""
+Usage: python tests/tools/stress_parity.py [cases] [seed]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gp2d_b200 as gp
 from oracle import gp_oracle as orc
 

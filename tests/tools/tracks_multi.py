@@ -1,5 +1,5 @@
 """Per-drifter track interpolation sharded over ranks (drifter n on rank n % world): every rank must
-end with the same result as a single process.  Usage: torchrun --nproc-per-node 2 tools/tracks_multi.py"""
+end with the same result as a single process.  Usage: torchrun --nproc-per-node 2 tests/tools/tracks_multi.py"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_track_interpolation import _drifters          # noqa: E402
