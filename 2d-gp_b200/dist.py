@@ -9,6 +9,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .engine import ROBUST_COND
+
 
 def world():
     if dist.is_available() and dist.is_initialized():
@@ -61,15 +63,20 @@ def broadcast_fit(gp, src=0, chunk_bytes=1 << 30):
     gp.fitted = True
 
 
-def predict_sharded(gp, Xs, include_noise=False):
+def predict_sharded(gp, Xs, include_noise=False, refined=None):
     """Grid-sharded prediction: rank r predicts its contiguous tile-aligned slice with the
     fit state it holds (every rank fits the same snapshot, or receives it by broadcast), then
-    mean/var shards are all-gathered.  Returns (mean[2M], var[2M]) on every rank."""
+    mean/var shards are all-gathered.  Returns (mean[2M], var[2M]) on every rank.  ``refined``:
+    None takes the iterated solve for ill-conditioned covariances (engine.refined_predict), like
+    GPRegression.predict; True / False force it."""
     rank, ws = world()
     Xs = np.asarray(Xs, dtype=np.float64) if not isinstance(Xs, torch.Tensor) else Xs
     M = Xs.shape[0]
     lo, hi = shard_range(M, rank, ws)
-    mean, var = gp.predict(Xs[lo:hi], include_noise=include_noise)
+    if refined is None:
+        refined = hasattr(gp, "cond_bound") and gp.cond_bound() > ROBUST_COND
+    fn = gp.predict_refined if refined else gp.predict
+    mean, var = fn(Xs[lo:hi], include_noise=include_noise)
     m = hi - lo
     if ws == 1:
         return mean, var
