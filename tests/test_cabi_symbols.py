@@ -77,3 +77,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "2d-gp_b200")
+    exe = str(tmp_path / "host_example")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "host_example.c"), "-L" + libdir, "-lgp2d",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/gp2d.h must be usable from C (the boundary is a C ABI): the plain-C example of
+    INTEGRATION.md route C compiles with -std=c99 -Wall -Werror and links against libgp2d.so."""
+    assert os.path.isfile(_build_c_example(tmp_path))
+
+
+@pytest.mark.gpu
+def test_c_example_runs(tmp_path):
+    import subprocess
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "LML" in out.stdout
