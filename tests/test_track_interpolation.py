@@ -168,3 +168,35 @@ def test_ill_conditioned_likelihood_uses_the_robust_factorisation():
     K = orc.rbf_sum_K(X, None, V, L) + (NZ + 1e-8) * np.eye(X.shape[0])
     P = gp.spd_inverse(K).cpu().numpy()
     assert np.abs(np.eye(K.shape[0]) - P @ K).max() < 10 * np.abs(np.eye(K.shape[0]) - np.linalg.inv(K) @ K).max()
+
+
+@pytest.mark.gpu
+@needs_gpu
+def test_tracks_feed_the_laser_kriging_workflow():
+    """Both sides of the path together, as upstream: raw fixes -> interp_kriging (laser_io_methods.py:410-570)
+    -> the interpolated_tracks object GP_laser.laser reads (GP_laser.py:26-60) -> velocity field on a grid."""
+    from gp2d_b200 import GP_laser
+    from gp2d_b200 import laser_io_methods as lio
+    rng = np.random.default_rng(7)
+    t_base, n, step = 2.0e6, 40, 300.0
+    t = np.arange(t_base, t_base + 8 * 3600.0, step)
+    fleet = []
+    for i in range(n):
+        lon0, lat0 = -88.0 + 0.15 * rng.uniform(), 28.7 + 0.15 * rng.uniform()
+        # solid-body rotation about (-87.925, 28.775): a divergence-free flow of ~0.2 m/s
+        ang = 2e-5 * (t - t_base)
+        dx, dy = lon0 + 87.925, lat0 - 28.775
+        lon = -87.925 + dx * np.cos(ang) - dy * np.sin(ang) + 2e-5 * rng.normal(size=t.size)
+        lat = 28.775 + dx * np.sin(ang) + dy * np.cos(ang) + 2e-5 * rng.normal(size=t.size)
+        fleet.append(lio.drifter("L_%04d" % i, [datetime(2016, 2, 7) + timedelta(seconds=float(s - t_base)) for s in t],
+                                 t, lat, lon, datetime(2017, 1, 1), 1, 1))
+    tr = lio.interp_kriging(fleet, dt=900, period=0.3, optimize=False, parallel=4)
+    assert np.isfinite(tr.u[:, 2:20]).all()
+    out = GP_laser.laser(ts=4, nsteps=3, l_df=5, l_cf=5, rate=0.9, noise=0.0025, nsamples=1, tracks=tr)
+    x, y, uf, vf, xo, yo, uo, vo, uvar, vvar, xt, yt, ut, vt, uft, vft = out
+    assert uf.shape == vf.shape == uvar.shape == (y.size, x.size) and np.isfinite(uf).all() and (uvar > 0).all()
+    assert xo.size + xt.size == 3 * n
+    # the kriged field reproduces the held-out velocities far better than their own spread
+    err = np.sqrt(np.mean((uft - ut) ** 2 + (vft - vt) ** 2))
+    spread = np.sqrt(np.mean((ut - ut.mean()) ** 2 + (vt - vt.mean()) ** 2))
+    assert err < 0.25 * spread, (err, spread)
