@@ -29,10 +29,20 @@ class Param:
     def constrain_fixed(self, value=None):
         if value is not None:
             self.value = float(value)
+        if self.constraint != "fixed":
+            self._before_fix = self.constraint
         self.constraint = "fixed"
         return self
 
     fix = constrain_fixed
+
+    def unconstrain_fixed(self):
+        """GPy's unfix(): back to the constraint the parameter had before it was fixed."""
+        if self.constraint == "fixed":
+            self.constraint = getattr(self, "_before_fix", None)
+        return self
+
+    unfix = unconstrain_fixed
 
     # --- numeric behaviour ------------------------------------------------------------------
     def __float__(self):

@@ -309,3 +309,14 @@ def test_gloo_world2_gathers(tmp_path):
     for k in range(2):
         np.testing.assert_array_equal(r[k]["track_len"], np.arange(5.0))
         np.testing.assert_array_equal(r[k]["track_lon"][:, 0], np.arange(5.0))
+
+
+def test_param_fix_and_unfix_restore_the_constraint():
+    p = Param("ratio", 0.3).constrain_bounded(0, 1)
+    p.fix(0.5)
+    assert p.constraint == "fixed" and float(p) == 0.5
+    p.fix()                                  # fixing twice does not forget the original constraint
+    p.unfix()
+    assert p.constraint == ("bounded", 0.0, 1.0)
+    q = Param("l", 2.0).constrain_positive().constrain_fixed()
+    assert q.unconstrain_fixed().constraint == "positive"
