@@ -109,3 +109,49 @@ def test_c_example_runs(tmp_path):
     out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "LML" in out.stdout
+
+
+def test_argument_validation_of_every_family_returns_before_any_device_work():
+    """Each entry point checks its arguments first and answers -(index of the bad argument) without
+    touching the device: callable on a box without a GPU.  One probe per family and per kind of
+    mistake (null pointer, size out of range, bad hyper-parameter, undersized workspace)."""
+    import numpy as np
+    from gp2d_b200._lib import lib as L
+    dummy = np.zeros(16)
+    p = dummy.ctypes.data                      # a non-null host address: never dereferenced by these calls
+    ty = np.array([0, 1], dtype=np.int32)
+    pr = np.array([[1.0, 1.0, 1.0, 1.0], [1.0, 1.0, 2.0, 2.0]])
+    bad_pr = np.array([[1.0, 1.0, -1.0, 1.0], [1.0, 1.0, 2.0, 2.0]])
+    var, ls = np.array([1.0]), np.array([[1.0, 2.0, 3.0]])
+    # Helmholtz
+    assert L.gp2d_fit(None, 4, p, 1.0, 1.0, 0.5, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -1
+    assert L.gp2d_fit(p, 0, p, 1.0, 1.0, 0.5, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -2
+    assert L.gp2d_fit(p, 100000, p, 1.0, 1.0, 0.5, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -2     # 2N > 131072
+    assert L.gp2d_fit(p, 4, p, -1.0, 1.0, 0.5, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -4
+    assert L.gp2d_fit(p, 4, p, 1.0, 1.0, 1.5, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -4
+    assert L.gp2d_fit(p, 4, p, 1.0, 1.0, 0.5, -0.1, 0.0, p, 1 << 30, None, None, None, None) == -7
+    assert L.gp2d_fit(p, 4, p, 1.0, 1.0, 0.5, 0.1, 0.0, p, 16, None, None, None, None) == -10               # workspace too small
+    assert L.gp2d_lml_grad(p, 4, p, 1.0, 1.0, 0.5, 0.1, 0.0, 0, p, 1 << 30, None, None, None) == -12
+    assert L.gp2d_kernel_grad(p, 4, None, 5, 1.0, 1.0, 0.5, 0, p, 10, p, 1 << 20, p, None) == -4            # X2 == NULL needs M == N
+    assert L.gp2d_potrf(p, 4, 3, p, 1 << 30, p, None) == -3                                                 # lda < n
+    assert L.gp2d_dgemm(0, 0, 100, 128, 16, 1.0, p, 16, p, 128, 0.0, p, 128, None) == -3                     # M not a multiple of 128
+    # space-time product
+    assert L.gp2d_st_fit(p, 4, p, 1.0, 1.0, 0.5, 0.0, 1.0, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -7   # tvar must be > 0
+    assert L.gp2d_st_predict(p, 4, 1.0, 1.0, 0.5, 1.0, 1.0, None, 3, 3, 0.0, p, p, p, 1 << 30, None) == -8
+    # sum of terms
+    assert L.gp2d_hsum_fit(p, 4, 3, p, 2, ty.ctypes.data, bad_pr.ctypes.data, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -5
+    assert L.gp2d_hsum_fit(p, 4, 4, p, 2, ty.ctypes.data, pr.ctypes.data, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -5    # ldx is 2 or 3
+    assert L.gp2d_hsum_fit(p, 4, 3, p, 9, ty.ctypes.data, pr.ctypes.data, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -5    # at most 8 terms
+    assert L.gp2d_hsum_fit(p, 4, 3, p, 2, ty.ctypes.data, pr.ctypes.data, 0.1, 0.0, p, 16, None, None, None, None) == -11
+    assert L.gp2d_hsum_predict(p, 4, 3, 2, ty.ctypes.data, pr.ctypes.data, p, 5, 4, 0.0, p, p, p, 1 << 30, None) == -9           # out_stride < M
+    assert L.gp2d_hsum_fit_workspace_bytes(4, 3, 0) == 0 and L.gp2d_hsum_fit_workspace_bytes(4, 3, 2) > 0
+    assert L.gp2d_hsum_kernel_grad_workspace_bytes(100, 100, 8) == 8 * L.gp2d_hsum_kernel_grad_workspace_bytes(100, 100, 1)
+    # scalar RBF sums
+    assert L.gp2d_rbf_fit(p, 4, 5, p, 1, var.ctypes.data, ls.ctypes.data, 0.1, 0.0, p, 1 << 30, None, None, None, None) == -5  # D <= 4
+    assert L.gp2d_rbf_fit(p, 4, 3, p, 1, var.ctypes.data, ls.ctypes.data, 0.1, -1.0, p, 1 << 30, None, None, None, None) == -9
+    assert L.gp2d_rbf_predict(p, 4, 3, 1, var.ctypes.data, ls.ctypes.data, p, 3, 0.0, None, p, p, 1 << 30, None) == -10
+    assert L.gp2d_rbf_fit_workspace_bytes(200000, 3) == 0
+    # M == 0 is a valid no-op everywhere
+    assert L.gp2d_predict(p, 4, 1.0, 1.0, 0.5, None, 0, 0, 0.0, None, None, None, 0, None) == 0
+    assert L.gp2d_hsum_predict(p, 4, 3, 2, ty.ctypes.data, pr.ctypes.data, None, 0, 0, 0.0, None, None, None, 0, None) == 0
+    assert L.gp2d_error_string(-1005).decode().startswith("CUDA error")
