@@ -18,7 +18,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // Private layout of the fit workspace: a pure function of N.
 struct FitLayout {
     int npad;
-    size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_alpha, off_partial, off_X, off_scal, off_info, total;
+    size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_r, off_alpha, off_partial, off_X, off_scal, off_info, total;
 };
 
 // n: scalar observations; x_doubles: size of the copy of the observation points;
@@ -34,6 +34,7 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
     L.off_logdiag = o; o = align256(o + n * d);
     L.off_yint = o; o = align256(o + n * d);
     L.off_w = o; o = align256(o + n * d);
+    L.off_r = o; o = align256(o + n * d);
     size_t nchunks = (n + 255) / 256;
     size_t part = nchunks * n;
     if (grad_doubles > part) part = grad_doubles;
@@ -91,6 +92,13 @@ cudaError_t factor_ws(void* ws, const FitLayout& L, int refine, cudaStream_t st)
     // npad (npad + 128) / 2 doubles >= (npad / 2)^2) as panel scratch
     return potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws, L.off_logdiag), at<int>(ws, L.off_info),
                        /*need_inv=*/true, /*keep_L=*/refine > 0, refine > 0 ? at<double>(ws, L.off_Zt) : nullptr, st, refine);
+}
+
+// robust mode, after the covariance has been rebuilt into A: two refinement steps of alpha (linalg.h)
+cudaError_t refine_alpha_ws(void* ws, const FitLayout& L, cudaStream_t st) {
+    return refine_alpha(at<double>(ws, L.off_A), L.npad, at<double>(ws, L.off_Z), L.npad, L.npad, at<double>(ws, L.off_yint),
+                        at<double>(ws, L.off_w), at<double>(ws, L.off_r), at<double>(ws, L.off_alpha),
+                        at<double>(ws, L.off_partial), 2, st);
 }
 
 __global__ void fill_kernel(double* out, int n, double v) {
@@ -171,13 +179,18 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     if (e != cudaSuccess) return e;
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = factor_ws(ws, L, refine_steps_for(hp.tvar * (hp.w_df + hp.w_cf), 2L * N, diag_add), st);
+    const int refine = refine_steps_for(hp.tvar * (hp.w_df + hp.w_cf), 2L * N, diag_add);
+    e = factor_ws(ws, L, refine, st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
-    return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
-                           at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
-                           at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    e = solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+                        at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
+                        at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    if (e != cudaSuccess || !refine) return e;
+    e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);      // A held the factor: the matrix again
+    if (e != cudaSuccess) return e;
+    return refine_alpha_ws(ws, L, st);
 }
 
 }  // namespace
@@ -574,13 +587,18 @@ cudaError_t rbf_fit_core(const double* X, int N, const double* y, const RbfParam
     if (e != cudaSuccess) return e;
     e = rbf_build_padded_lower(X, N, rp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = factor_ws(ws, L, refine_steps_for(rp.kss, (long)N, diag_add), st);
+    const int refine = refine_steps_for(rp.kss, (long)N, diag_add);
+    e = factor_ws(ws, L, refine, st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
-    return solve_alpha_lml(Z, L.npad, L.npad, N, 1, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
-                           at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
-                           at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    e = solve_alpha_lml(Z, L.npad, L.npad, N, 1, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+                        at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
+                        at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    if (e != cudaSuccess || !refine) return e;
+    e = rbf_build_padded_lower(X, N, rp, diag_add, A, L.npad, L.npad, st);
+    if (e != cudaSuccess) return e;
+    return refine_alpha_ws(ws, L, st);
 }
 }  // namespace
 
@@ -738,13 +756,18 @@ cudaError_t hsum_fit_core(const double* X, int N, const double* y, const HsumPar
     if (e != cudaSuccess) return e;
     e = hsum_build_interleaved_lower(X, N, sp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
-    e = factor_ws(ws, L, refine_steps_for(sp.kss0 > sp.kss1 ? sp.kss0 : sp.kss1, 2L * N, diag_add), st);
+    const int refine = refine_steps_for(sp.kss0 > sp.kss1 ? sp.kss0 : sp.kss1, 2L * N, diag_add);
+    e = factor_ws(ws, L, refine, st);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
-    return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
-                           at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
-                           at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    e = solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
+                        at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
+                        at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+    if (e != cudaSuccess || !refine) return e;
+    e = hsum_build_interleaved_lower(X, N, sp, diag_add, A, L.npad, L.npad, st);
+    if (e != cudaSuccess) return e;
+    return refine_alpha_ws(ws, L, st);
 }
 }  // namespace
 

@@ -486,6 +486,41 @@ __global__ void lml_kernel(const double* __restrict__ w, const double* __restric
     }
 }
 
+// r = y - (t1 + t2 - diag(K) alpha): residual of the symmetric system from its two triangular products
+__global__ void sym_residual_kernel(const double* __restrict__ y, const double* __restrict__ t1, const double* t2,
+                                    const double* __restrict__ K, long ldk, const double* __restrict__ alpha,
+                                    double* r, int n) {      // r may alias t2
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = y[i] - (t1[i] + t2[i] - K[(long)i * (ldk + 1)] * alpha[i]);
+}
+__global__ void axpy1_kernel(const double* __restrict__ d, double* __restrict__ x, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += d[i];
+}
+
+// Iterative refinement of alpha against the matrix itself (robust mode): `steps` times
+//   alpha += Z^T Z (y - K alpha),   K = lower tiles of the padded covariance (identity padding).
+// With refined factor panels Z^T Z is a good preconditioner and two steps bring K alpha = y down to
+// the rounding level of the residual -- what a backward-stable triangular solve delivers -- while
+// the explicit-inverse product alone is off by ~cond(K) eps.  t1, t2: scratch vectors of npad.
+cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, int npad, const double* y_int,
+                         double* t1, double* t2, double* alpha_int, double* partial, int steps, cudaStream_t st) {
+    const int nchunks = (npad + TRMVT_ROWS - 1) / TRMVT_ROWS;
+    const dim3 gT(npad / 128, nchunks);
+    const int gv = (npad + 255) / 256, gr = (npad + 7) / 8;
+    for (int it = 0; it < steps; ++it) {
+        trmv_lower_kernel<<<gr, 256, 0, st>>>(K, ldk, alpha_int, t1, npad);                 // tril(K) alpha
+        trmvT_partial_kernel<<<gT, 128, 0, st>>>(K, ldk, alpha_int, partial, npad);         // tril(K)^T alpha
+        colsum_partials_kernel<<<gv, 256, 0, st>>>(partial, nchunks, npad, t2);
+        sym_residual_kernel<<<gv, 256, 0, st>>>(y_int, t1, t2, K, ldk, alpha_int, t2, npad);   // t2 = r
+        trmv_lower_kernel<<<gr, 256, 0, st>>>(Z, ldz, t2, t1, npad);                        // Z r
+        trmvT_partial_kernel<<<gT, 128, 0, st>>>(Z, ldz, t1, partial, npad);                // Z^T (Z r)
+        colsum_partials_kernel<<<gv, 256, 0, st>>>(partial, nchunks, npad, t2);
+        axpy1_kernel<<<gv, 256, 0, st>>>(t2, alpha_int, npad);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st) {

@@ -23,6 +23,10 @@ void set_potri_overlap(bool on);      // bring-up switch: side-stream overlap of
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st);
+// robust mode: alpha += Z^T Z (y - K alpha), `steps` times; K = lower tiles of the padded covariance,
+// t1 / t2 scratch vectors of npad doubles (t1 may be the w of solve_alpha_lml: it is not needed afterwards)
+cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, int npad, const double* y_int,
+                         double* t1, double* t2, double* alpha_int, double* partial, int steps, cudaStream_t st);
 cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st);
 // Tile-major, pre-swizzled copy of the lower triangle of Z (what predict_fused streams with
 // bulk copies): tile (row block li, k-tile kt) is number 8 li (li+1)/2 + kt, 2048 doubles each.

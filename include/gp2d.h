@@ -77,7 +77,8 @@ int gp2d_potrf(double* A, int n, int64_t lda, void* ws, size_t ws_bytes, int* in
  * twins): the factorisation forms panels of L with explicit block inverses, which is accurate to
  * the 1e-8 parity bar while n k(x,x) / (noise + jitter) stays below ~1e9; past 1e7 the fit switches
  * to the same refined panels by itself (same results to rounding for well-conditioned input, ~55 %
- * more time).  The fused prediction applies the explicit inverse factor: for covariances beyond
+ * more time) and iterates alpha against the matrix, so alpha and the predictive MEAN keep the accuracy
+ * of a backward-stable solve.  The fused predictive VARIANCE applies the explicit inverse factor: for covariances beyond
  * that bound use the iterated solve the Python engine builds from gp2d_*_kernel_build,
  * gp2d_spd_inverse and gp2d_dgemm (engine.refined_predict). */
 size_t gp2d_spd_inverse_workspace_bytes(int n);
