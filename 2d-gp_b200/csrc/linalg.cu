@@ -141,9 +141,20 @@ potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int
     const int tid = threadIdx.x, lane = tid & 31;
     const int tc = tid >> 4, tr = tid & 15;
     if (tid == 0) first_bad = TILE;
-    for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-        const int r = idx >> 7, c = idx & 127;
-        S[r * LEAF_LD + c] = (c <= r) ? A[(long)r * lda + c] : 0.0;
+    // stage the tile through shared memory, 8 independent loads in flight per thread (one load per
+    // iteration serialised the prologue on the global-memory latency: 11 % of the kernel in the profile)
+    for (int idx0 = tid; idx0 < TILE * TILE; idx0 += 8 * NTHREADS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * NTHREADS, r = idx >> 7, c = idx & 127;
+            v[u] = (c <= r) ? A[(long)r * lda + c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * NTHREADS, r = idx >> 7, c = idx & 127;
+            S[r * LEAF_LD + c] = v[u];
+        }
     }
     __syncthreads();
     double M[8][8];
