@@ -56,9 +56,15 @@ __global__ void __launch_bounds__(NT, (TS == 64 ? 3 : 1)) dgemm_kernel(GemmArgs 
         while ((long)tm * (tm + 1) / 2 > t) --tm;
         tn = t - tm * (tm + 1) / 2;
     } else {
-        int tiles_n = p.N / TS;
-        tm = blockIdx.x / tiles_n;
-        tn = blockIdx.x % tiles_n;
+        // grouped raster: bands of GR tile rows, walked column by column, so that the CTAs in flight
+        // form a near-square patch and share operand panels in L2 (plain row-major order streamed
+        // 61 GB from DRAM for an 8192^3 product whose operands are 1 GB)
+        constexpr int GR = TS == 64 ? 16 : 8;
+        const int tiles_m = p.M / TS, tiles_n = p.N / TS;
+        const int per = GR * tiles_n, band = blockIdx.x / per, first = band * GR;
+        const int h = min(GR, tiles_m - first), r = blockIdx.x - band * per;
+        tm = first + r % h;
+        tn = r / h;
     }
     int k0 = 0, k1 = p.K;
     if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TS);
@@ -150,9 +156,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dgemm_ws_kernel(GemmArgs p) {
         while ((long)tm * (tm + 1) / 2 > t) --tm;
         tn = t - tm * (tm + 1) / 2;
     } else {
-        int tiles_n = p.N / TS;
-        tm = blockIdx.x / tiles_n;
-        tn = blockIdx.x % tiles_n;
+        // grouped raster: bands of GR tile rows, walked column by column, so that the CTAs in flight
+        // form a near-square patch and share operand panels in L2 (plain row-major order streamed
+        // 61 GB from DRAM for an 8192^3 product whose operands are 1 GB)
+        constexpr int GR = TS == 64 ? 16 : 8;
+        const int tiles_m = p.M / TS, tiles_n = p.N / TS;
+        const int per = GR * tiles_n, band = blockIdx.x / per, first = band * GR;
+        const int h = min(GR, tiles_m - first), r = blockIdx.x - band * per;
+        tm = first + r % h;
+        tn = r / h;
     }
     int k0 = 0, k1 = p.K;
     if (p.krule & KR_LE_M) k1 = min(k1, (tm + 1) * TS);
