@@ -35,6 +35,33 @@ struct GemmArgs {
     int krule;
 };
 
+// Tile (tm, tn), tn <= tm, number t of the banded walk over the lower triangle of a tiles_m x tiles_m
+// grid.  Bands of GRL tile rows in row order (band starting at row r0 begins at t = r0 (r0+1)/2, as in
+// plain row-major numbering); inside a band the columns 0..r0, which every row of the band owns, are
+// walked column by column, then the small triangle on the diagonal row by row: the CTAs in flight share
+// operand panels in L2, like the grouped raster of the rectangular case.
+template <int GRL>
+__device__ __forceinline__ void lower_tile(int t, int tiles_m, int& tm, int& tn) {
+    int row = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(row + 1) * (row + 2) / 2 <= t) ++row;
+    while ((long)row * (row + 1) / 2 > t) --row;
+    const int r0 = (row / GRL) * GRL;
+    const int h = min(GRL, tiles_m - r0);
+    int q = t - (int)((long)r0 * (r0 + 1) / 2);
+    const int rect = (r0 + 1) * h;
+    if (q < rect) {
+        tn = q / h;
+        tm = r0 + q % h;
+        return;
+    }
+    q -= rect;                                   // rows r0+1 .. r0+h-1, columns r0+1 .. row
+    int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    while (i * (i + 1) / 2 > q) --i;
+    tm = r0 + 1 + i;
+    tn = r0 + 1 + (q - i * (i + 1) / 2);
+}
+
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);   // 128 KB (TS = 128)
 constexpr int gemm_smem_bytes(int ts) { return GEMM_STAGES * 2 * ts * BK * (int)sizeof(double); }
@@ -49,12 +76,8 @@ __global__ void __launch_bounds__(NT, (TS == 64 ? 3 : 1)) dgemm_kernel(GemmArgs 
 
     int tm, tn;
     if (p.lower_out) {
-        // linear index over the lower triangle of the tile grid, heaviest rows last
-        int t = blockIdx.x;
-        tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((long)(tm + 1) * (tm + 2) / 2 <= t) ++tm;
-        while ((long)tm * (tm + 1) / 2 > t) --tm;
-        tn = t - tm * (tm + 1) / 2;
+        // lower triangle of the tile grid in bands of tile rows, heaviest rows last (lower_tile)
+        lower_tile<TS == 64 ? 16 : 8>((int)blockIdx.x, p.M / TS, tm, tn);
     } else {
         // grouped raster: bands of GR tile rows, walked column by column, so that the CTAs in flight
         // form a near-square patch and share operand panels in L2 (plain row-major order streamed
@@ -150,11 +173,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dgemm_ws_kernel(GemmArgs p) {
 
     int tm, tn;
     if (p.lower_out) {
-        int t = blockIdx.x;
-        tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((long)(tm + 1) * (tm + 2) / 2 <= t) ++tm;
-        while ((long)tm * (tm + 1) / 2 > t) --tm;
-        tn = t - tm * (tm + 1) / 2;
+        // lower triangle of the tile grid in bands of tile rows, heaviest rows last (lower_tile)
+        lower_tile<TS == 64 ? 16 : 8>((int)blockIdx.x, p.M / TS, tm, tn);
     } else {
         // grouped raster: bands of GR tile rows, walked column by column, so that the CTAs in flight
         // form a near-square patch and share operand panels in L2 (plain row-major order streamed
