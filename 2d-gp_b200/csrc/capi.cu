@@ -35,7 +35,7 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
     L.off_yint = o; o = align256(o + n * d);
     L.off_w = o; o = align256(o + n * d);
     L.off_r = o; o = align256(o + n * d);
-    size_t nchunks = (n + 255) / 256;
+    size_t nchunks = (n + 63) / 64;           // TRMVT_ROWS of linalg.cu
     size_t part = nchunks * n;
     if (grad_doubles > part) part = grad_doubles;
     L.off_partial = o; o = align256(o + part * d);
