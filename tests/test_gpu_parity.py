@@ -647,13 +647,20 @@ def test_refined_prediction_all_families():
             (gp.ScalarGP(X3, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], noise), Xs3,
              lambda: orc.rbf_predict(X3, orc.rbf_fit(X3, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], noise), [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], Xs3)),
         ]
-        for g, P, oracle in cases:
+        lmls = [lambda: orc.fit(X3[:, 1:], y, 1.3, 3.1, 0.2, noise)["lml"],
+                lambda: orc.st_fit(X3, y, 1.3, 3.1, 0.2, 1.5, 0.8, noise)["lml"],
+                lambda: orc.hsum_fit(X3, y, ty, pr, noise)["lml"],
+                lambda: orc.rbf_fit(X3, y[:N], [1.0, 0.5], [[1, 2, 3], [3, 2, 1]], noise)["lml"]]
+        for (g, P, oracle), lml_oracle in zip(cases, lmls):
             mo, vo = oracle()
             mr, vr = g.predict_refined(P, chunk_elems=60000)          # several chunks
             scale = max(np.abs(mo).max(), 1e-3)
             np.testing.assert_allclose(mr.cpu().numpy(), mo, rtol=0, atol=tol_mean * scale)
             np.testing.assert_allclose(vr.cpu().numpy(), vo, rtol=tol_var[0], atol=tol_var[1])
             assert (g.cond_bound() > 1e7) == (noise < 1e-6)
+            # the likelihood keeps its 1e-6 bar in both regimes (robust factorisation in the second)
+            lo = lml_oracle()
+            assert abs(g.fit() - lo) <= 1e-6 * abs(lo), (type(g).__name__, noise)
             if tol_fused is not None:
                 mf, vf = g.predict(P)
                 np.testing.assert_allclose(mf.cpu().numpy(), mr.cpu().numpy(), rtol=0, atol=tol_fused * scale)
