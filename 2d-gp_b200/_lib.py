@@ -82,6 +82,7 @@ SIGNATURES = {
                                      C.c_void_p, C.c_size_t, c_dp, c_ip, c_st]),
     "gp2d_fit_predict_host": (C.c_int, [c_dp, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_double, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
+    "gp2d_host_release": (None, []),
 }
 
 

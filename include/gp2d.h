@@ -5,7 +5,8 @@
  * function name ends in _host, every data pointer is a CALLER-OWNED DEVICE pointer to
  * IEEE fp64, `stream` is a cudaStream_t passed as void*, calls are asynchronous on that
  * stream, allocate nothing (workspace is sized by the *_workspace_bytes queries), keep no
- * global state and are re-entrant across streams.
+ * global state and are re-entrant across streams (the _host entry points cache one device buffer per
+ * host thread, see the end of this file).
  *
  * Return value: 0 = launched OK; -k = argument k (1-based) is invalid;
  * <= -1000 = -(1000 + cudaError_t).  Numerical failure of the factorisation is reported
@@ -231,12 +232,18 @@ int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, 
 
 /* ---- host-buffer convenience (allocates, copies, synchronises) -------------------- */
 
-/* Whole fit + predict with HOST pointers on the current device; returns info (> 0) or an
- * error code (< 0).  lml may be NULL. */
+/* Whole fit + predict with HOST pointers (pageable is fine) on the current device, legacy default
+ * stream; returns info (> 0) or an error code (< 0).  lml may be NULL.  This is what the numpy route
+ * of the reference binds in one call: GP_laser.simLaser's K + noise I ; inv ; getMean ; diag(Cov)
+ * (GP_laser.py:177-185) and GPRegression(X,Y,k).predict(Xnew) (GP_plots.py:763-768).
+ * The device buffer (fit workspace, inputs, outputs, K* panels) is cached PER HOST THREAD between
+ * calls and grown on demand -- the only state the library keeps; it is freed when the thread exits
+ * or by gp2d_host_release() (current thread). */
 int gp2d_fit_predict_host(const double* X, int N, const double* y,
                           double l_df, double l_cf, double ratio, double noise, double jitter,
                           const double* Xs, int M, int include_noise,
                           double* mean, double* var, double* lml);
+void gp2d_host_release(void);
 
 #ifdef __cplusplus
 }
