@@ -437,6 +437,168 @@ int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l
     return 0;
 }
 
+/* ---- batches of independent problems of one size (survey kernel k6) ------------------------------- */
+
+namespace {
+
+// scal[16..29) of every problem's workspace holds its BatchPar (kernel parameters + diagonal term)
+constexpr size_t BATCH_PAR_OFF = 16 * sizeof(double);
+static_assert(BATCH_PAR_OFF + sizeof(BatchPar) <= 32 * sizeof(double), "BatchPar must fit the scalar block");
+
+// out[b][0..4] = (LML, d/dl_df, d/dl_cf, d/dratio, d/dnoise) (grad) or out[b] = LML; info[b]
+__global__ void gather_batch_out_kernel(const double* __restrict__ scal, const int* __restrict__ info_ws, long bstride,
+                                        int with_grad, double* __restrict__ out, int* __restrict__ info, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const double* s = scal + (long)b * bstride;
+    if (out) {
+        if (with_grad) {
+            out[5 * b + 0] = s[0]; out[5 * b + 1] = s[1]; out[5 * b + 2] = s[2]; out[5 * b + 3] = s[3]; out[5 * b + 4] = s[6];
+        } else {
+            out[b] = s[0];
+        }
+    }
+    if (info) info[b] = info_ws[(long)b * 2 * bstride];
+}
+
+struct BatchProblem { HelmParams hp; double noise, diag_add; int refine; };
+
+// validates theta4 = [B][4] rows (l_df, l_cf, ratio, noise) and fills the per-problem records
+int batch_problems(const double* theta4, int B, int N, double jitter, BatchProblem* out) {
+    for (int b = 0; b < B; ++b) {
+        const double* t = theta4 + 4 * b;
+        if (!theta_ok(t[0], t[1], t[2]) || !(t[3] >= 0.0)) return -1;
+        out[b].hp = make_helm(t[0], t[1], t[2]);
+        out[b].noise = t[3];
+        out[b].diag_add = t[3] + jitter;
+        out[b].refine = refine_steps_for(out[b].hp.w_df + out[b].hp.w_cf, 2L * N, out[b].diag_add);
+    }
+    return 0;
+}
+
+// plain-mode problems [b0, b0 + nb) in one chain of launches (every launch covers the whole run)
+cudaError_t fit_core_batched(const double* X, long x_stride, int N, const double* y, long y_stride, const BatchProblem* pr,
+                             int nb, void* ws0, const FitLayout& L, cudaStream_t st) {
+    const long bs = (long)(L.total / sizeof(double));
+    BatchPar host[64];
+    BatchPar* par = at<BatchPar>(ws0, L.off_scal + BATCH_PAR_OFF);
+    cudaError_t e = cudaSuccess;
+    for (int c0 = 0; c0 < nb && e == cudaSuccess; c0 += 64) {
+        const int nc = nb - c0 < 64 ? nb - c0 : 64;
+        for (int i = 0; i < nc; ++i) { host[i].hp = pr[c0 + i].hp; host[i].diag_add = pr[c0 + i].diag_add; }
+        e = scatter_batch_params(host, nc, reinterpret_cast<BatchPar*>(reinterpret_cast<double*>(par) + (long)c0 * bs), bs,
+                                 X + (long)c0 * x_stride, x_stride, 2 * N, at<double>(ws0, L.off_X) + (long)c0 * bs, st);
+    }
+    if (e != cudaSuccess) return e;
+    double* A = at<double>(ws0, L.off_A);
+    double* Z = at<double>(ws0, L.off_Z);
+    e = build_interleaved_lower_batched(X, x_stride, N, par, A, L.npad, L.npad, nb, bs, st);
+    if (e != cudaSuccess) return e;
+    e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws0, L.off_logdiag), at<int>(ws0, L.off_info),
+                    /*need_inv=*/true, /*keep_L=*/false, nullptr, st, 0, nb, bs);
+    if (e != cudaSuccess) return e;
+    e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws0, L.off_Zt), st, nb, bs);
+    if (e != cudaSuccess) return e;
+    return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws0, L.off_yint), at<double>(ws0, L.off_w),
+                           at<double>(ws0, L.off_alpha), at<double>(ws0, L.off_partial), at<double>(ws0, L.off_logdiag),
+                           at<double>(ws0, L.off_scal), st, nb, y_stride, bs);
+}
+
+// shared driver of gp2d_fit_batched / gp2d_lml_grad_batched: runs of consecutive plain-mode problems go
+// through the batched chain, robust-mode problems (ill-conditioned, rare) one by one through the
+// single-problem entry points, so every problem gets exactly the arithmetic of its unbatched call
+int run_batch(bool grad, const double* X, int64_t x_stride, int N, const double* y, int64_t y_stride, int B,
+              const double* theta4, double jitter, int compat, void* ws, double* alpha_out, double* out, int* info,
+              cudaStream_t st) {
+    const FitLayout L = fit_layout(N);
+    const long bs = (long)(L.total / sizeof(double));
+    BatchProblem* pr = new BatchProblem[B];
+    if (batch_problems(theta4, B, N, jitter, pr)) { delete[] pr; return -7; }
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    for (int b0 = 0; b0 < B && rc == 0 && e == cudaSuccess;) {
+        char* ws0 = reinterpret_cast<char*>(ws) + (size_t)b0 * L.total;
+        if (pr[b0].refine) {
+            const double* t = theta4 + 4 * b0;
+            if (grad) rc = gp2d_lml_grad(X + b0 * x_stride, N, y + b0 * y_stride, t[0], t[1], t[2], t[3], jitter, compat, ws0,
+                                         L.total, out + 5 * b0, info ? info + b0 : nullptr, st);
+            else rc = gp2d_fit(X + b0 * x_stride, N, y + b0 * y_stride, t[0], t[1], t[2], t[3], jitter, ws0, L.total,
+                               alpha_out ? alpha_out + (size_t)2 * N * b0 : nullptr, out ? out + b0 : nullptr,
+                               info ? info + b0 : nullptr, st);
+            ++b0;
+            continue;
+        }
+        int nb = 1;
+        while (b0 + nb < B && !pr[b0 + nb].refine) ++nb;
+        e = fit_core_batched(X + b0 * x_stride, (long)x_stride, N, y + b0 * y_stride, (long)y_stride, pr + b0, nb, ws0, L, st);
+        if (e != cudaSuccess) break;
+        if (grad) {
+            double* Z = at<double>(ws0, L.off_Z);
+            double* Kinv = at<double>(ws0, L.off_A);
+            GemmArgs g{Z, L.npad, Z, L.npad, Kinv, L.npad, L.npad, L.npad, L.npad, 1.0, 0.0, 1, KR_GE_M};
+            g.batch = nb; g.bsA = g.bsB = g.bsC = nb > 1 ? bs : 0;
+            e = launch_dgemm(true, true, g, st);
+            if (e != cudaSuccess) break;
+            e = lml_grad_reduce_batched(Kinv, L.npad, L.npad, at<double>(ws0, L.off_alpha), at<double>(ws0, L.off_X), N,
+                                        at<BatchPar>(ws0, L.off_scal + BATCH_PAR_OFF), compat, at<double>(ws0, L.off_partial),
+                                        at<double>(ws0, L.off_scal) + 1, nb, bs, st);
+            if (e != cudaSuccess) break;
+        } else if (alpha_out) {
+            e = deinterleave(at<double>(ws0, L.off_alpha), N, alpha_out + (size_t)2 * N * b0, st, nb, bs);
+            if (e != cudaSuccess) break;
+        }
+        gather_batch_out_kernel<<<(nb + 127) / 128, 128, 0, st>>>(at<double>(ws0, L.off_scal), at<int>(ws0, L.off_info), bs,
+                                                                  grad ? 1 : 0, out ? out + (grad ? 5 : 1) * b0 : nullptr,
+                                                                  info ? info + b0 : nullptr, nb);
+        e = cudaGetLastError();
+        b0 += nb;
+    }
+    delete[] pr;
+    if (rc) return rc;
+    return cuda_rc(e);
+}
+
+}  // namespace
+
+size_t gp2d_fit_batched_workspace_bytes(int N, int B) {
+    if (!size_ok(2L * N) || B < 1) return 0;
+    return fit_layout(N).total * (size_t)B;
+}
+
+int gp2d_fit_batched(const double* X, int64_t x_stride, int N, const double* y, int64_t y_stride, int B,
+                     const double* theta4, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
+                     double* lml_out, int* info, void* stream) {
+    if (!X) return -1;
+    if (x_stride != 0 && x_stride < 2 * (int64_t)N) return -2;
+    if (!size_ok(2L * N)) return -3;
+    if (!y) return -4;
+    if (y_stride != 0 && y_stride < 2 * (int64_t)N) return -5;
+    if (B < 1) return -6;
+    if (!theta4) return -7;
+    if (!(jitter >= 0.0)) return -8;
+    if (!ws) return -9;
+    if (ws_bytes < gp2d_fit_batched_workspace_bytes(N, B)) return -10;
+    return run_batch(false, X, x_stride, N, y, y_stride, B, theta4, jitter, 0, ws, alpha_out, lml_out, info, (cudaStream_t)stream);
+}
+
+int gp2d_lml_grad_batched(const double* X, int64_t x_stride, int N, const double* y, int64_t y_stride, int B,
+                          const double* theta4, double jitter, int reference_compat, void* ws, size_t ws_bytes,
+                          double* out5, int* info, void* stream) {
+    if (!X) return -1;
+    if (x_stride != 0 && x_stride < 2 * (int64_t)N) return -2;
+    if (!size_ok(2L * N)) return -3;
+    if (!y) return -4;
+    if (y_stride != 0 && y_stride < 2 * (int64_t)N) return -5;
+    if (B < 1) return -6;
+    if (!theta4) return -7;
+    if (!(jitter >= 0.0)) return -8;
+    if (!ws) return -10;
+    if (ws_bytes < gp2d_fit_batched_workspace_bytes(N, B)) return -11;
+    if (!out5) return -12;
+    return run_batch(true, X, x_stride, N, y, y_stride, B, theta4, jitter, reference_compat != 0, ws, nullptr, out5, info,
+                     (cudaStream_t)stream);
+}
+
 /* ---- space-time product kernel: tvar exp(-dt^2 / 2 lt^2) * Helmholtz(a, b) ------------------------ */
 
 namespace {

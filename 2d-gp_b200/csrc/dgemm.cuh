@@ -33,6 +33,10 @@ struct GemmArgs {
     double alpha, beta;
     int lower_out;
     int krule;
+    // batch of independent products of the same shape (gridDim.y): problem b works on A + b bsA,
+    // B + b bsB, C + b bsC (strides in doubles)
+    int batch = 1;
+    long bsA = 0, bsB = 0, bsC = 0;
 };
 
 // Tile (tm, tn), tn <= tm, number t of the banded walk over the lower triangle of a tiles_m x tiles_m
@@ -68,6 +72,9 @@ constexpr int gemm_smem_bytes(int ts) { return GEMM_STAGES * 2 * ts * BK * (int)
 
 template <bool A_MN, bool B_MN, int NT, int TS>
 __global__ void __launch_bounds__(NT, (TS == 64 ? 3 : 1)) dgemm_kernel(GemmArgs p) {
+    p.A += (long)blockIdx.y * p.bsA;
+    p.B += (long)blockIdx.y * p.bsB;
+    p.C += (long)blockIdx.y * p.bsC;
     using Cfg = TileCfg<TS, NT>;
     constexpr int MB = Cfg::MB, WM = Cfg::WM, SD = Cfg::STAGE_DOUBLES;
     extern __shared__ __align__(16) double smem[];
@@ -166,6 +173,9 @@ constexpr int GEMM_WS_SMEM_BYTES = WS_RING_BYTES + WS_BAR_BYTES;
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(WS_THREADS, 1) dgemm_ws_kernel(GemmArgs p) {
+    p.A += (long)blockIdx.y * p.bsA;
+    p.B += (long)blockIdx.y * p.bsB;
+    p.C += (long)blockIdx.y * p.bsC;
     constexpr int TS = TILE;
     extern __shared__ __align__(16) double smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);

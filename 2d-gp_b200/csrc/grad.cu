@@ -12,10 +12,9 @@
 
 namespace gp2d {
 
-__global__ void __launch_bounds__(256)
-lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
-                const double* __restrict__ X, int N, HelmParams hp, int compat,
-                double* __restrict__ partial) {
+__device__ __forceinline__ void lml_grad_tile(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                                              const double* __restrict__ X, int N, const HelmParams& hp, int compat,
+                                              double* __restrict__ partial) {
     __shared__ double sh[(HELM_NP + 1) * 32];
     int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
@@ -56,6 +55,23 @@ lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restri
     }
 }
 
+__global__ void __launch_bounds__(256)
+lml_grad_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                const double* __restrict__ X, int N, HelmParams hp, int compat,
+                double* __restrict__ partial) {
+    lml_grad_tile(Kinv, ld, alpha, X, N, hp, compat, partial);
+}
+
+// batch (gridDim.y problems bstride doubles apart), parameters from the problem's BatchPar
+__global__ void __launch_bounds__(256)
+lml_grad_batched_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                        const double* __restrict__ X, int N, const BatchPar* __restrict__ par, int compat,
+                        double* __restrict__ partial, long bstride) {
+    const long o = (long)blockIdx.y * bstride;
+    const HelmParams hp = reinterpret_cast<const BatchPar*>(reinterpret_cast<const double*>(par) + o)->hp;
+    lml_grad_tile(Kinv + o, ld, alpha + o, X + o, N, hp, compat, partial + o);
+}
+
 int lml_grad_partials(int npad) {
     int T = npad / TILE;
     return T * (T + 1) / 2;
@@ -68,6 +84,15 @@ cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double*
     int count = lml_grad_partials(npad);
     lml_grad_kernel<<<count, 256, 0, st>>>(Kinv, ld, alpha_int, X, N, hp, compat, partial);
     final_reduce_kernel<HELM_NP + 1><<<1, 1024, 0, st>>>(partial, count, out6);
+    return cudaGetLastError();
+}
+
+cudaError_t lml_grad_reduce_batched(const double* Kinv, long ld, int npad, const double* alpha_int, const double* X, int N,
+                                    const BatchPar* par, int compat, double* partial, double* out6, int batch, long bstride,
+                                    cudaStream_t st) {
+    int count = lml_grad_partials(npad);
+    lml_grad_batched_kernel<<<dim3(count, batch), 256, 0, st>>>(Kinv, ld, alpha_int, X, N, par, compat, partial, bstride);
+    final_reduce_kernel<HELM_NP + 1><<<batch, 1024, 0, st>>>(partial, count, out6, bstride);
     return cudaGetLastError();
 }
 

@@ -94,9 +94,8 @@ cudaError_t hsum_build_block_layout(const double* X, int N, const double* X2, in
 // (64x64 point pairs); a warp writes 512 contiguous bytes per matrix row.
 // ---------------------------------------------------------------------------------------
 template <class KP>
-__global__ void __launch_bounds__(256)
-build_interleaved_kernel(const double* __restrict__ X, int N, const __grid_constant__ KP hp, double diag_add,
-                         double* __restrict__ K, long ldk) {
+__device__ __forceinline__ void build_interleaved_tile(const double* __restrict__ X, int N, const KP& hp, double diag_add,
+                                                       double* __restrict__ K, long ldk) {
     int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
@@ -123,10 +122,63 @@ build_interleaved_kernel(const double* __restrict__ X, int N, const __grid_const
     }
 }
 
+template <class KP>
+__global__ void __launch_bounds__(256)
+build_interleaved_kernel(const double* __restrict__ X, int N, const __grid_constant__ KP hp, double diag_add,
+                         double* __restrict__ K, long ldk) {
+    build_interleaved_tile(X, N, hp, diag_add, K, ldk);
+}
+
+// batch (gridDim.y problems): the same tile code with the problem's own points, parameters and matrix
+__global__ void __launch_bounds__(256)
+build_interleaved_batched_kernel(const double* __restrict__ X, long x_bstride, int N, const BatchPar* __restrict__ par,
+                                 double* __restrict__ K, long ldk, long bstride) {
+    const BatchPar* bp = reinterpret_cast<const BatchPar*>(reinterpret_cast<const double*>(par) + (long)blockIdx.y * bstride);
+    const HelmParams hp = bp->hp;
+    build_interleaved_tile(X + (long)blockIdx.y * x_bstride, N, hp, bp->diag_add, K + (long)blockIdx.y * bstride, ldk);
+}
+
 cudaError_t build_interleaved_lower(const double* X, int N, const HelmParams& hp, double diag_add,
                                     double* K, long ldk, int npad, cudaStream_t st) {
     const int T = npad / TILE;
     build_interleaved_kernel<HelmParams><<<T * (T + 1) / 2, 256, 0, st>>>(X, N, hp, diag_add, K, ldk);
+    return cudaGetLastError();
+}
+cudaError_t build_interleaved_lower_batched(const double* X, long x_bstride, int N, const BatchPar* par, double* K, long ldk,
+                                            int npad, int batch, long bstride, cudaStream_t st) {
+    const int T = npad / TILE;
+    build_interleaved_batched_kernel<<<dim3(T * (T + 1) / 2, batch), 256, 0, st>>>(X, x_bstride, N, par, K, ldk, bstride);
+    return cudaGetLastError();
+}
+
+// Parameters of up to 16 problems travel as kernel arguments (no host staging buffer to keep alive, no
+// stream synchronisation as a pageable cudaMemcpyAsync would force) and are written to each problem's
+// workspace together with its copy of the observation points.
+constexpr int SCATTER_CHUNK = 16;
+struct BatchParChunk { BatchPar p[SCATTER_CHUNK]; };
+__global__ void __launch_bounds__(256)
+scatter_batch_params_kernel(const __grid_constant__ BatchParChunk chunk, BatchPar* __restrict__ par, long bstride,
+                            const double* __restrict__ X, long x_bstride, int x_doubles, double* __restrict__ Xws) {
+    const int b = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(BatchPar) / sizeof(double)))
+        (reinterpret_cast<double*>(par) + (long)b * bstride)[threadIdx.x] = reinterpret_cast<const double*>(&chunk.p[b])[threadIdx.x];
+    const double* src = X + (long)b * x_bstride;
+    double* dst = Xws + (long)b * bstride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < x_doubles; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static_assert(sizeof(BatchPar) % sizeof(double) == 0, "BatchPar is copied as doubles");
+
+cudaError_t scatter_batch_params(const BatchPar* host, int batch, BatchPar* par, long bstride, const double* X,
+                                 long x_bstride, int x_doubles, double* Xws, cudaStream_t st) {
+    for (int b0 = 0; b0 < batch; b0 += SCATTER_CHUNK) {
+        const int nb = batch - b0 < SCATTER_CHUNK ? batch - b0 : SCATTER_CHUNK;
+        BatchParChunk c;
+        for (int i = 0; i < nb; ++i) c.p[i] = host[b0 + i];
+        for (int i = nb; i < SCATTER_CHUNK; ++i) c.p[i] = host[b0];
+        scatter_batch_params_kernel<<<dim3(8, nb), 256, 0, st>>>(
+            c, reinterpret_cast<BatchPar*>(reinterpret_cast<double*>(par) + (long)b0 * bstride), bstride,
+            X + (long)b0 * x_bstride, x_bstride, x_doubles, Xws + (long)b0 * bstride);
+    }
     return cudaGetLastError();
 }
 cudaError_t hsum_build_interleaved_lower(const double* X, int N, const HsumParams& hp, double diag_add,

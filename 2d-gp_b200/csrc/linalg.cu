@@ -53,15 +53,17 @@ cudaError_t dgemm_init() {
     return cudaSuccess;
 }
 
-static void gemm_launch64(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
+static void gemm_launch64(bool a_mn, bool b_mn, unsigned tiles, const GemmArgs& a, cudaStream_t st) {
     constexpr int SM = gemm_smem_bytes(64);
+    const dim3 grid(tiles, (unsigned)a.batch);
     if (!a_mn && !b_mn) dgemm_kernel<false, false, 128, 64><<<grid, 128, SM, st>>>(a);
     else if (!a_mn && b_mn) dgemm_kernel<false, true, 128, 64><<<grid, 128, SM, st>>>(a);
     else if (a_mn && b_mn) dgemm_kernel<true, true, 128, 64><<<grid, 128, SM, st>>>(a);
     else dgemm_kernel<true, false, 128, 64><<<grid, 128, SM, st>>>(a);
 }
-static void gemm_launch_ws(bool a_mn, bool b_mn, unsigned grid, const GemmArgs& a, cudaStream_t st) {
+static void gemm_launch_ws(bool a_mn, bool b_mn, unsigned tiles, const GemmArgs& a, cudaStream_t st) {
     constexpr int SM = GEMM_WS_SMEM_BYTES;
+    const dim3 grid(tiles, (unsigned)a.batch);
     if (!a_mn && !b_mn) dgemm_ws_kernel<false, false><<<grid, WS_THREADS, SM, st>>>(a);
     else if (!a_mn && b_mn) dgemm_ws_kernel<false, true><<<grid, WS_THREADS, SM, st>>>(a);
     else if (a_mn && b_mn) dgemm_ws_kernel<true, true><<<grid, WS_THREADS, SM, st>>>(a);
@@ -105,9 +107,12 @@ cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t s
     if (e != cudaSuccess) return e;
     const long tm = a.M / TILE, tn = a.N / TILE;
     if (a.lower_out && tm != tn) return cudaErrorInvalidValue;
+    if (a.batch < 1 || a.batch > 65535) return cudaErrorInvalidValue;
     const long t128 = a.lower_out ? tm * (tm + 1) / 2 : tm * tn;
     const long t64 = a.lower_out ? (2 * tm) * (2 * tm + 1) / 2 : 4 * tm * tn;
-    if (use_tile64(t128, t64)) gemm_launch64(a_mn, b_mn, (unsigned)t64, a, st);
+    // the tile shape is chosen for the whole batch; both shapes accumulate every output element over k in
+    // the same order with the same DMMA shape, so the choice never changes a result bit
+    if (use_tile64(t128 * a.batch, t64 * a.batch)) gemm_launch64(a_mn, b_mn, (unsigned)t64, a, st);
     else gemm_launch_ws(a_mn, b_mn, (unsigned)t128, a, st);
     return cudaGetLastError();
 }
@@ -133,7 +138,13 @@ constexpr int LEAF_LD = TILE + 1;
 constexpr int LEAF_SMEM_BYTES = TILE * LEAF_LD * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0, int keep_L) {
+potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0, int keep_L,
+                  long bstride) {
+    // batch: problem blockIdx.x lives bstride doubles (2 bstride ints) further on in every array
+    A += (long)blockIdx.x * bstride;
+    Z += (long)blockIdx.x * bstride;
+    logdiag += (long)blockIdx.x * bstride;
+    info += (long)blockIdx.x * 2 * bstride;
     extern __shared__ double S[];                 // [128][129] staging: A in, q/L out, Z out
     __shared__ double colbuf[2][TILE];
     __shared__ double dsave[TILE];                // pivots d_j, then 1/sqrt(d_j)
@@ -298,10 +309,14 @@ struct PotriCtx {
     cudaError_t err;
     PotriSide* side;    // nullptr: everything on st
     int t_refine;       // refinement steps of every panel T (needs keep_L), see potri_lower
+    int batch;          // independent problems of the same size, bstride doubles apart in A, Z, logdiag (and info)
+    long bstride;
 };
 
-static void gemm_checked(PotriCtx& c, bool a_mn, bool b_mn, const GemmArgs& g, cudaStream_t st) {
+static void gemm_checked(PotriCtx& c, bool a_mn, bool b_mn, GemmArgs g, cudaStream_t st) {
     if (c.err != cudaSuccess) return;
+    g.batch = c.batch;
+    g.bsA = g.bsB = g.bsC = c.bstride;      // every operand of the recursion lives in the problem's own workspace
     c.err = launch_dgemm(a_mn, b_mn, g, st);
 }
 static void cuda_checked(PotriCtx& c, cudaError_t e) {
@@ -311,9 +326,9 @@ static void cuda_checked(PotriCtx& c, cudaError_t e) {
 static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
     if (c.err != cudaSuccess) return;
     if (n == TILE) {
-        potri_leaf_kernel<<<1, NTHREADS, LEAF_SMEM_BYTES, c.st>>>(
+        potri_leaf_kernel<<<c.batch, NTHREADS, LEAF_SMEM_BYTES, c.st>>>(
             c.A + (long)off * (c.lda + 1), c.lda, c.Z + (long)off * (c.ldz + 1), c.ldz,
-            c.logdiag + off, c.info, off, c.keep_L ? 1 : 0);
+            c.logdiag + off, c.info, off, c.keep_L ? 1 : 0, c.bstride);
         c.err = cudaGetLastError();
         return;
     }
@@ -369,8 +384,9 @@ static void potri_rec(PotriCtx& c, int off, int n, bool need_inv, int depth) {
 }
 
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
-                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine) {
-    if (n % TILE || n <= 0) return cudaErrorInvalidValue;
+                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine, int batch, long bstride) {
+    if (n % TILE || n <= 0 || batch < 1) return cudaErrorInvalidValue;
+    if (batch > 1 && (keep_L || t_refine > 0)) return cudaErrorInvalidValue;      // the robust mode shares one scratch W
     static PerDeviceOnce leaf_once;
     const int slot = leaf_once.pending();
     if (slot >= 0) {
@@ -378,11 +394,12 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
         if (e0 != cudaSuccess) return e0;
         leaf_once.done[slot] = true;
     }
-    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    cudaError_t e = batch == 1 ? cudaMemsetAsync(info, 0, sizeof(int), st)
+                               : cudaMemset2DAsync(info, (size_t)bstride * sizeof(double), 0, sizeof(int), (size_t)batch, st);
     if (e != cudaSuccess) return e;
     PotriSide* side = (g_potri_overlap && !keep_L && need_inv && n >= 4 * TILE && g_side.init()) ? &g_side : nullptr;
     if (t_refine > 0 && (!keep_L || !W)) return cudaErrorInvalidValue;
-    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess, side, t_refine};
+    PotriCtx c{A, lda, Z, ldz, logdiag, info, W, keep_L, st, cudaSuccess, side, t_refine, batch, batch > 1 ? bstride : 0};
     potri_rec(c, 0, n, need_inv, 0);
     return c.err;
 }
@@ -394,7 +411,9 @@ cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double*
 // shared-memory image (kmaj_off), so one 16 KB bulk copy brings a whole operand stage.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_lower_tiles_kernel(const double* __restrict__ Z, long ldz, double* __restrict__ Zt) {
+pack_lower_tiles_kernel(const double* __restrict__ Z, long ldz, double* __restrict__ Zt, long bstride) {
+    Z += (long)blockIdx.y * bstride;
+    Zt += (long)blockIdx.y * bstride;
     int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
@@ -415,9 +434,9 @@ size_t packed_tiles_doubles(int npad) {
     return 8 * (nb * (nb + 1) / 2) * (size_t)TILE_DOUBLES;
 }
 
-cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st) {
+cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st, int batch, long bstride) {
     const int nb = npad / TILE;
-    pack_lower_tiles_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(Z, ldz, Zt);
+    pack_lower_tiles_kernel<<<dim3(nb * (nb + 1) / 2, batch), 256, 0, st>>>(Z, ldz, Zt, batch > 1 ? bstride : 0);
     return cudaGetLastError();
 }
 
@@ -425,7 +444,10 @@ cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cu
 // vectors: y -> interleaved, w = Z y, alpha = Z^T w, LML
 // ------------------------------------------------------------------------------------
 // ncomp = 2: stacked [u; v] -> pair-interleaved; ncomp = 1: scalar observations, zero padded
-__global__ void interleave_kernel(const double* __restrict__ y, int N, int ncomp, double* __restrict__ yi, int npad) {
+__global__ void interleave_kernel(const double* __restrict__ y, int N, int ncomp, double* __restrict__ yi, int npad,
+                                  long y_bstride, long bstride) {
+    y += (long)blockIdx.y * y_bstride;
+    yi += (long)blockIdx.y * bstride;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npad) return;
     if (ncomp == 2) {
@@ -436,7 +458,9 @@ __global__ void interleave_kernel(const double* __restrict__ y, int N, int ncomp
     }
 }
 
-__global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double* __restrict__ x) {
+__global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double* __restrict__ x, long bstride) {
+    xi += (long)blockIdx.y * bstride;
+    x += (long)blockIdx.y * 2 * N;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 2 * N) return;
     int c = p / N, i = p - c * N;
@@ -445,7 +469,10 @@ __global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double
 
 // w[i] = sum_{k<=i} Z[i][k] y[k]; one warp per row
 __global__ void trmv_lower_kernel(const double* __restrict__ Z, long ldz, const double* __restrict__ y,
-                                  double* __restrict__ w, int n) {
+                                  double* __restrict__ w, int n, long bstride = 0) {
+    Z += (long)blockIdx.y * bstride;
+    y += (long)blockIdx.y * bstride;
+    w += (long)blockIdx.y * bstride;
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -462,7 +489,10 @@ __global__ void trmv_lower_kernel(const double* __restrict__ Z, long ldz, const 
 // 0.6 TB/s in the launch list)
 constexpr int TRMVT_ROWS = 64;
 __global__ void trmvT_partial_kernel(const double* __restrict__ Z, long ldz, const double* __restrict__ w,
-                                     double* __restrict__ partial, int n) {
+                                     double* __restrict__ partial, int n, long bstride = 0) {
+    Z += (long)blockIdx.z * bstride;
+    w += (long)blockIdx.z * bstride;
+    partial += (long)blockIdx.z * bstride;
     int j = blockIdx.x * 128 + threadIdx.x;
     int r0 = blockIdx.y * TRMVT_ROWS, r1 = min(n, r0 + TRMVT_ROWS);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -481,7 +511,9 @@ __global__ void trmvT_partial_kernel(const double* __restrict__ Z, long ldz, con
 }
 
 __global__ void colsum_partials_kernel(const double* __restrict__ partial, int nchunks, int n,
-                                       double* __restrict__ out) {
+                                       double* __restrict__ out, long bstride = 0) {
+    partial += (long)blockIdx.y * bstride;
+    out += (long)blockIdx.y * bstride;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double s = 0.0;
@@ -491,7 +523,10 @@ __global__ void colsum_partials_kernel(const double* __restrict__ partial, int n
 
 // out[0] = -0.5 w'w - sum logdiag - (n/2) log(2 pi)      (n scalar observations)
 __global__ void lml_kernel(const double* __restrict__ w, const double* __restrict__ logdiag, int npad,
-                           double half_n, double* __restrict__ out) {
+                           double half_n, double* __restrict__ out, long bstride) {
+    w += (long)blockIdx.x * bstride;
+    logdiag += (long)blockIdx.x * bstride;
+    out += (long)blockIdx.x * bstride;
     __shared__ double sh[2][32];
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < npad; i += blockDim.x) { a = fma(w[i], w[i], a); b += logdiag[i]; }
@@ -544,18 +579,20 @@ cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, i
 
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
-                            const double* logdiag, double* lml_out, cudaStream_t st) {
-    interleave_kernel<<<(npad + 255) / 256, 256, 0, st>>>(y_block, N, ncomp, y_int, npad);
-    trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, st>>>(Z, ldz, y_int, w, npad);
+                            const double* logdiag, double* lml_out, cudaStream_t st, int batch, long y_bstride,
+                            long bstride) {
+    if (batch == 1) bstride = y_bstride = 0;
+    interleave_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, st>>>(y_block, N, ncomp, y_int, npad, y_bstride, bstride);
+    trmv_lower_kernel<<<dim3((npad + 7) / 8, batch), 256, 0, st>>>(Z, ldz, y_int, w, npad, bstride);
     int nchunks = (npad + TRMVT_ROWS - 1) / TRMVT_ROWS;
-    trmvT_partial_kernel<<<dim3(npad / 128, nchunks), 128, 0, st>>>(Z, ldz, w, partial, npad);
-    colsum_partials_kernel<<<(npad + 255) / 256, 256, 0, st>>>(partial, nchunks, npad, alpha_int);
-    lml_kernel<<<1, 1024, 0, st>>>(w, logdiag, npad, 0.5 * ncomp * (double)N, lml_out);
+    trmvT_partial_kernel<<<dim3(npad / 128, nchunks, batch), 128, 0, st>>>(Z, ldz, w, partial, npad, bstride);
+    colsum_partials_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, st>>>(partial, nchunks, npad, alpha_int, bstride);
+    lml_kernel<<<batch, 1024, 0, st>>>(w, logdiag, npad, 0.5 * ncomp * (double)N, lml_out, bstride);
     return cudaGetLastError();
 }
 
-cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st) {
-    deinterleave_kernel<<<(2 * N + 255) / 256, 256, 0, st>>>(xi, N, x);
+cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch, long bstride) {
+    deinterleave_kernel<<<dim3((2 * N + 255) / 256, batch), 256, 0, st>>>(xi, N, x, batch > 1 ? bstride : 0);
     return cudaGetLastError();
 }
 

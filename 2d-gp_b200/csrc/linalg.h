@@ -14,24 +14,30 @@ namespace gp2d {
 // log(L_ii); *info the 1-based index of the first non-positive pivot, else 0.
 // t_refine > 0 (needs keep_L and W): every off-diagonal panel of L gets that many steps of iterative
 // refinement against the factor (robust mode for ill-conditioned matrices, see potri_rec).
+// batch > 1: that many independent problems of the same size, problem b at A + b bstride, Z + b bstride,
+// logdiag + b bstride (doubles) and info + 2 b bstride (ints) -- one launch per step of the recursion for
+// the whole batch (plain mode only: no keep_L, no refinement).
 cudaError_t potri_lower(double* A, long lda, double* Z, long ldz, int n, double* logdiag, int* info,
-                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine = 0);
+                        bool need_inv, bool keep_L, double* W, cudaStream_t st, int t_refine = 0, int batch = 1,
+                        long bstride = 0);
 void set_potri_overlap(bool on);      // bring-up switch: side-stream overlap of the inverse GEMMs
 // alpha = Z^T Z y and LML from Z, logdiag.  y_block is the caller's vector: stacked [u;v] of
 // length 2N (ncomp = 2) or N scalar observations (ncomp = 1); everything else is internal
 // (pair-interleaved for ncomp = 2, padded to npad).
+// batch > 1: problem b at every workspace pointer + b bstride doubles, its observations at y_block + b y_bstride.
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
-                            const double* logdiag, double* lml_out, cudaStream_t st);
+                            const double* logdiag, double* lml_out, cudaStream_t st, int batch = 1, long y_bstride = 0,
+                            long bstride = 0);
 // robust mode: alpha += Z^T Z (y - K alpha), `steps` times; K = lower tiles of the padded covariance,
 // t1 / t2 scratch vectors of npad doubles (t1 may be the w of solve_alpha_lml: it is not needed afterwards)
 cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, int npad, const double* y_int,
                          double* t1, double* t2, double* alpha_int, double* partial, int steps, cudaStream_t st);
-cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st);
+cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch = 1, long bstride = 0);
 // Tile-major, pre-swizzled copy of the lower triangle of Z (what predict_fused streams with
 // bulk copies): tile (row block li, k-tile kt) is number 8 li (li+1)/2 + kt, 2048 doubles each.
 size_t packed_tiles_doubles(int npad);
-cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st);
+cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cudaStream_t st, int batch = 1, long bstride = 0);
 
 // kernel_build.cu -------------------------------------------------------------------------
 // Reference (component-major block) layout, arbitrary N, M, ld: K[2N, 2M].  X2 == nullptr
@@ -42,6 +48,14 @@ cudaError_t build_block_layout(const double* X, int N, const double* X2, int M, 
 // 128x128 tiles only (diagonal tiles complete).
 cudaError_t build_interleaved_lower(const double* X, int N, const HelmParams& hp, double diag_add,
                                     double* K, long ldk, int npad, cudaStream_t st);
+// Per-problem parameters of a batch, kept in each problem's workspace (set by scatter_batch_params).
+struct BatchPar { HelmParams hp; double diag_add; };
+// batch of problems bstride doubles apart: problem b reads its points at X + b x_bstride, its BatchPar at
+// par + b bstride and writes K + b bstride
+cudaError_t build_interleaved_lower_batched(const double* X, long x_bstride, int N, const BatchPar* par, double* K, long ldk,
+                                            int npad, int batch, long bstride, cudaStream_t st);
+cudaError_t scatter_batch_params(const BatchPar* host, int batch, BatchPar* par, long bstride, const double* X,
+                                 long x_bstride, int x_doubles, double* Xws, cudaStream_t st);
 // sum(dK/dtheta * dL_dK) for theta = (l_df, l_cf, ratio); dL_dK in block layout [2N,2M].
 cudaError_t kernel_grad_sums_block(const double* X, int N, const double* X2, int M, const HelmParams& hp,
                                    int compat, const double* dL_dK, long ld, double* partial,
@@ -93,6 +107,10 @@ void set_predict_split(int s);          // bring-up override: 1, 2, 4, 8 (0 = he
 cudaError_t lml_grad_reduce(const double* Kinv, long ld, int npad, const double* alpha_int,
                             const double* X, int N, const HelmParams& hp, int compat,
                             double* partial, double* out6, cudaStream_t st);
+// batch: every pointer + b bstride doubles, parameters from par + b bstride
+cudaError_t lml_grad_reduce_batched(const double* Kinv, long ld, int npad, const double* alpha_int, const double* X, int N,
+                                    const BatchPar* par, int compat, double* partial, double* out6, int batch, long bstride,
+                                    cudaStream_t st);
 int lml_grad_partials(int npad);
 // scalar ARD-RBF sum: out[Q (1 + D) + 1] = d LML / d(var_q, l_{q,0..D-1})_q, then d LML / d noise
 int rbf_lml_grad_partial_doubles(int npad);

@@ -25,8 +25,11 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* sh /* [NV]
     }
 }
 
+// batch: CTA b reduces partial + b bstride into out + b bstride
 template <int NV>
-__global__ void final_reduce_kernel(const double* __restrict__ partial, int count, double* __restrict__ out) {
+__global__ void final_reduce_kernel(const double* __restrict__ partial, int count, double* __restrict__ out, long bstride = 0) {
+    partial += (long)blockIdx.x * bstride;
+    out += (long)blockIdx.x * bstride;
     __shared__ double sh[NV * 32];
     double acc[NV];
 #pragma unroll

@@ -12,8 +12,8 @@ import torch
 from ._lib import lib, check, Gp2dError
 
 __all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
-           "spd_inverse", "matmul", "HelmholtzGP", "fit_predict_host", "rbf_K", "rbf_grad_sums", "ScalarGP",
-           "st_K", "st_grad_sums", "SpaceTimeGP"]
+           "spd_inverse", "matmul", "HelmholtzGP", "HelmholtzBatch", "krig_snapshots", "fit_predict_host", "rbf_K",
+           "rbf_grad_sums", "ScalarGP", "st_K", "st_grad_sums", "SpaceTimeGP"]
 
 
 class LinAlgError(np.linalg.LinAlgError):
@@ -319,6 +319,157 @@ class HelmholtzGP:
             raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         self.lml = float(host[0])
         return self.lml, host[1:5].copy()
+
+
+# ------------------------------------------------------------------------------------------
+class HelmholtzBatch:
+    """B independent Helmholtz GPs of one size advanced together (gp2d_fit_batched /
+    gp2d_lml_grad_batched): every kernel launch of the fit covers the whole batch.
+
+    Two uses, both from the reference: the restarts of ``optimize_restarts`` (krig.py:450;
+    GP_plots.py:765) -- one data set, B hyper-parameter points: ``X [N,2]``, ``y [2N]`` -- and the time
+    slices / snapshots of the predict loop (krig.py:541-557) -- ``X [B,N,2]``, ``y [B,2N]``.
+    Results are bit-identical to B separate HelmholtzGP calls."""
+
+    def __init__(self, X, y, B=None, jitter=0.0, device=None):
+        Xd = as_dev(X, device)
+        if Xd.dim() == 2:
+            if Xd.shape[1] != 2:
+                raise ValueError("points must be [N,2] or [B,N,2]")
+            if B is None:
+                raise ValueError("B is required when the problems share one data set")
+            self.shared = True
+            self.N = int(Xd.shape[0])
+            self.B = int(B)
+        else:
+            if Xd.dim() != 3 or Xd.shape[2] != 2:
+                raise ValueError("points must be [N,2] or [B,N,2]")
+            self.shared = False
+            self.B, self.N = int(Xd.shape[0]), int(Xd.shape[1])
+            if B is not None and int(B) != self.B:
+                raise ValueError("B does not match X")
+        self.X = Xd
+        self.y = as_dev(y, Xd.device).reshape(-1) if self.shared else as_dev(y, Xd.device).reshape(self.B, -1)
+        if self.y.shape[-1] != 2 * self.N:
+            raise ValueError("y must stack both components: length 2N per problem")
+        self.jitter = float(jitter)
+        self.ws_stride = lib.gp2d_fit_workspace_bytes(self.N)
+        if not self.ws_stride:
+            raise ValueError("problem size out of range")
+        self.ws = torch.empty(self.ws_stride * self.B, dtype=torch.uint8, device=Xd.device)
+        self._out = torch.zeros((self.B, 5), dtype=torch.float64, device=Xd.device)
+        self._info = torch.zeros(self.B, dtype=torch.int32, device=Xd.device)
+        self._pws = None
+        self.theta4 = None
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def _theta(self, theta4, nb):
+        t = np.ascontiguousarray(np.asarray(theta4, dtype=np.float64).reshape(-1, 4))
+        if t.shape[0] != nb:
+            raise ValueError("theta4 must be [%d,4] rows (l_df, l_cf, ratio, noise)" % nb)
+        return t
+
+    def _strides(self):
+        return (0, 0) if self.shared else (2 * self.N, 2 * self.N)
+
+    def fit_async(self, theta4, nb=None, alpha_out=None):
+        """Fit the first ``nb`` problems (default all) at theta4[nb,4]; LML and info stay on the device
+        (``lml_device()``, ``info_device()``)."""
+        nb = self.B if nb is None else int(nb)
+        t = self._theta(theta4, nb)
+        xs, ys = self._strides()
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_fit_batched(_ptr(self.X), xs, self.N, _ptr(self.y), ys, nb, t.ctypes.data, self.jitter,
+                                       _ptr(self.ws), self.ws.numel(), _ptr(alpha_out), _ptr(self._out), _ptr(self._info),
+                                       _stream()), "gp2d_fit_batched")
+        self.theta4 = t
+        self._nb = nb
+
+    def fit(self, theta4, nb=None):
+        """Returns (lml[nb], info[nb]) as numpy arrays (info > 0: not positive definite, LAPACK-style)."""
+        self.fit_async(theta4, nb)
+        lml = self._out.reshape(-1)[:self._nb].cpu().numpy()
+        return lml, self._info[:self._nb].cpu().numpy()
+
+    def lml_and_grad(self, theta4, nb=None, reference_compat=False):
+        """(lml[nb], grad[nb,4] over (l_df, l_cf, ratio, noise), info[nb]) -- one batched objective evaluation."""
+        nb = self.B if nb is None else int(nb)
+        t = self._theta(theta4, nb)
+        xs, ys = self._strides()
+        with torch.cuda.device(self.device):
+            check(lib.gp2d_lml_grad_batched(_ptr(self.X), xs, self.N, _ptr(self.y), ys, nb, t.ctypes.data, self.jitter,
+                                            int(bool(reference_compat)), _ptr(self.ws), self.ws.numel(), _ptr(self._out),
+                                            _ptr(self._info), _stream()), "gp2d_lml_grad_batched")
+        self.theta4 = t
+        self._nb = nb
+        host = self._out[:nb].cpu().numpy()
+        return host[:, 0].copy(), host[:, 1:5].copy(), self._info[:nb].cpu().numpy()
+
+    def state(self, b):
+        """Fit workspace of problem b (a view): what gp2d_predict reads."""
+        return self.ws[b * self.ws_stride:(b + 1) * self.ws_stride]
+
+    def predict(self, b, Xs, include_noise=False, out_mean=None, out_var=None):
+        """Fused prediction from problem b's fit state: mean[2M], var[2M] device tensors."""
+        if self.theta4 is None or b >= self._nb:
+            raise Gp2dError("problem %d has not been fitted" % b)
+        Xsd = _points(Xs, self.device)
+        M = int(Xsd.shape[0])
+        mean = out_mean if out_mean is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        var = out_var if out_var is not None else torch.empty(2 * M, dtype=torch.float64, device=self.device)
+        l_df, l_cf, ratio, noise = (float(v) for v in self.theta4[b])
+        if M:
+            with torch.cuda.device(self.device):
+                nbytes = lib.gp2d_predict_workspace_bytes(self.N, M)
+                if self._pws is None or self._pws.numel() < nbytes:
+                    self._pws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                check(lib.gp2d_predict(_ptr(self.state(b)), self.N, l_df, l_cf, ratio, _ptr(Xsd), M, M,
+                                       noise if include_noise else 0.0, _ptr(mean), _ptr(var), _ptr(self._pws),
+                                       self._pws.numel(), _stream()), "gp2d_predict")
+        return mean, var
+
+
+def krig_snapshots(X, y, Xs, l_df, l_cf, ratio, noise, jitter=0.0, include_noise=False, batch=4, device=None):
+    """Independent snapshots kriged with one hyper-parameter set: X [S,N,2], y [S,2N], Xs [M,2] (one grid for
+    all) or [S,M,2].  The fits of ``batch`` snapshots share every kernel launch (gp2d_fit_batched); each
+    snapshot is then predicted by the fused kernel.  Returns (mean [S,2M], var [S,2M], lml [S]) as numpy
+    arrays; raises LinAlgError for a snapshot whose covariance is not positive definite.  This is the
+    per-time-slice loop of krig.predict (krig.py:539-557) for the Helmholtz kernel."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(X.shape[0], -1)
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    S, N = X.shape[0], X.shape[1]
+    per_grid = Xs.ndim == 3
+    M = Xs.shape[-2]
+    dev = _device(device)
+    batch = max(1, min(int(batch), S))
+    mean = np.empty((S, 2 * M))
+    var = np.empty((S, 2 * M))
+    lml = np.empty(S)
+    theta = np.tile(np.array([l_df, l_cf, ratio, noise], dtype=np.float64), (batch, 1))
+    hb = HelmholtzBatch(torch.zeros((batch, N, 2), dtype=torch.float64, device=dev),
+                        torch.zeros((batch, 2 * N), dtype=torch.float64, device=dev), jitter=jitter)
+    Xsd = None if per_grid else as_dev(Xs, dev)
+    dm = torch.empty((batch, 2 * M), dtype=torch.float64, device=dev)
+    dv = torch.empty((batch, 2 * M), dtype=torch.float64, device=dev)
+    for s0 in range(0, S, batch):
+        nb = min(batch, S - s0)
+        hb.X[:nb].copy_(torch.from_numpy(X[s0:s0 + nb]))
+        hb.y[:nb].copy_(torch.from_numpy(y[s0:s0 + nb]))
+        l, info = hb.fit(theta[:nb], nb)
+        if np.any(info > 0):
+            bad = int(np.argmax(info > 0))
+            raise LinAlgError("snapshot %d: covariance not positive definite (pivot %d)" % (s0 + bad, info[bad]))
+        for b in range(nb):
+            g = as_dev(Xs[s0 + b], dev) if per_grid else Xsd
+            hb.predict(b, g, include_noise=include_noise, out_mean=dm[b], out_var=dv[b])
+        mean[s0:s0 + nb] = dm[:nb].cpu().numpy()
+        var[s0:s0 + nb] = dv[:nb].cpu().numpy()
+        lml[s0:s0 + nb] = l
+    return mean, var, lml
 
 
 # ------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ import pickle
 import numpy as np
 import scipy.optimize as sopt
 
-from .engine import HelmholtzGP, HelmholtzSumGP, LinAlgError, ROBUST_COND, ScalarGP, SpaceTimeGP
+from .engine import HelmholtzBatch, HelmholtzGP, HelmholtzSumGP, LinAlgError, ROBUST_COND, ScalarGP, SpaceTimeGP
 from .kern import RBF, Add, Prod, _ScalarKern
 from .myKernel import myKernel, nonDivK, nonRotK, _HelmholtzBase, Kt, SpaceTimeKern
 from .myKernel2 import _HelmholtzSumKern, HelmholtzSum, divFreeK, curlFreeK
@@ -32,6 +32,17 @@ class _Run:
 
     def __init__(self, x_opt, f_opt, status, nfev):
         self.x_opt, self.f_opt, self.status, self.funct_eval = x_opt, f_opt, status, nfev
+
+
+def _grad_natural_for(k, grad4):
+    """d/d(l_df, l_cf, ratio, noise) -> gradients of the kernel's own parameters, then the noise."""
+    if isinstance(k, myKernel):
+        g = [grad4[0], grad4[1], grad4[2]]
+    elif isinstance(k, nonDivK):
+        g = [grad4[0]]
+    else:
+        g = [grad4[1]]
+    return g + [grad4[3]]
 
 
 class GPRegression:
@@ -132,14 +143,7 @@ class GPRegression:
     # ---- likelihood ------------------------------------------------------------------------
     def _grad_natural(self, grad4):
         """Map d/d(l_df, l_cf, ratio, noise) onto this kernel's own parameters."""
-        k = self.kern
-        if isinstance(k, myKernel):
-            g = [grad4[0], grad4[1], grad4[2]]
-        elif isinstance(k, nonDivK):
-            g = [grad4[0]]
-        else:
-            g = [grad4[1]]
-        return g + [grad4[3]]
+        return _grad_natural_for(self.kern, grad4)
 
     def parameters_changed(self):
         self._sync()
@@ -260,15 +264,121 @@ class GPRegression:
             self.randomize(np.random.default_rng(child))
         return self.optimize(max_iters=max_iters, messages=False)
 
+    # ---- restarts in lock step: one batched objective evaluation per round --------------------------
+    def _lockstep_ok(self):
+        return not (self.scalar or self.spacetime or self.hsum)
+
+    def _restarts_lockstep(self, todo, first, init, children, max_iters, nbatch, robust, report):
+        """Run the restarts ``todo`` with ``nbatch`` of them in flight.  Every restart is an ordinary
+        scipy L-BFGS-B run in its own host thread; its objective hands theta to the serving loop below and
+        sleeps.  When every live restart has asked, ONE gp2d_lml_grad_batched call evaluates them all (each
+        kernel launch of the factorisation covers the whole batch) and the answers are handed back.  A
+        restart sees exactly the values the single-problem path would give it (bit-identical entry points),
+        so the set of runs is the same as with ``parallel=1``; only the wall time changes."""
+        import copy
+        import queue
+        import threading
+        hb = HelmholtzBatch(self._gp.X, self._gp.y, B=nbatch, jitter=self.jitter, device=self._gp.device)
+        compat = bool(self.kern.reference_compat)
+        cv = threading.Condition()
+        pending, answers = {}, {}
+        live = [nbatch]
+        work = queue.SimpleQueue()
+        for r in todo:
+            work.put(r)
+        results, errors = {}, []
+        fallback_lock = threading.Lock()
+        stats = {"rounds": 0, "evaluations": 0}
+
+        def worker(slot):
+            kern = copy.deepcopy(self.kern)
+            noise = copy.deepcopy(self.Gaussian_noise)
+            params = list(kern.parameters) + [noise]
+            free = [p for p in params if p.constraint != "fixed"]
+
+            def objective(x):
+                for p, xi in zip(free, x):
+                    p.from_free(float(xi))
+                theta = tuple(kern._theta()) + (float(noise),)
+                with cv:
+                    pending[slot] = theta
+                    cv.notify_all()
+                    while slot not in answers:
+                        cv.wait()
+                    ll, g4, info = answers.pop(slot)
+                if info > 0:
+                    # not positive definite: GPy's jitchol retries on the single-problem path
+                    with fallback_lock:
+                        f, g = self._objective(x)
+                    return f, g
+                if not np.isfinite(ll):
+                    return 1e100, np.zeros(len(x))
+                for p, gi in zip(params, _grad_natural_for(kern, g4)):
+                    p.gradient = float(gi)
+                return -ll, np.array([-p.gradient * p.dvalue_dfree(float(xi)) for p, xi in zip(free, x)])
+
+            try:
+                while True:
+                    try:
+                        r = work.get_nowait()
+                    except queue.Empty:
+                        break
+                    try:
+                        rr = r if first else max(r, 1)       # only the very first restart starts from the current point
+                        x0 = init if rr == 0 else np.random.default_rng(children[r]).standard_normal(len(free))
+                        res = sopt.minimize(objective, x0, jac=True, method="L-BFGS-B", options={"maxiter": int(max_iters)})
+                        results[r] = _Run(res.x.copy(), float(res.fun), res.message, int(res.nfev))
+                        report(r, results[r])
+                    except Exception as e:                  # noqa: BLE001
+                        if not robust:
+                            errors.append(e)
+                            break
+            finally:
+                with cv:
+                    live[0] -= 1
+                    cv.notify_all()
+
+        threads = [threading.Thread(target=worker, args=(s,), daemon=True) for s in range(nbatch)]
+        for t in threads:
+            t.start()
+        while True:
+            with cv:
+                while live[0] > 0 and len(pending) < live[0]:
+                    cv.wait()
+                if live[0] == 0:
+                    break
+                batch = sorted(pending.items())
+                pending.clear()
+            try:
+                ll, g, info = hb.lml_and_grad([th for _, th in batch], nb=len(batch), reference_compat=compat)
+                out = {slot: (float(ll[i]), g[i], int(info[i])) for i, (slot, _) in enumerate(batch)}
+            except Exception as e:                          # noqa: BLE001  hand the failure to every waiting restart
+                errors.append(e)
+                out = {slot: (-np.inf, np.zeros(4), 0) for slot, _ in batch}
+            stats["rounds"] += 1
+            stats["evaluations"] += len(batch)
+            with cv:
+                answers.update(out)
+                cv.notify_all()
+        for t in threads:
+            t.join()
+        self.lockstep_stats = stats
+        if errors:
+            raise errors[0]
+        return results
+
     def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, messages=False, max_iters=1000,
-                          seed=None, rank=0, world=1, parallel=1, **kw):
+                          seed=None, rank=0, world=1, parallel=1, batched=None, **kw):
         """GPy semantics: optimise from the current point, then from random points; keep the
         best.  ``rank``/``world`` shard the restart indices (restart r runs on rank r % world);
         use gp2d_b200.dist.gather_best to pick the global winner.  ``parallel`` > 1 runs that many
         restarts of this rank concurrently, each on its own CUDA stream and workspace: one
         small-n factorisation is a latency-bound chain of kernels that leaves most SMs idle, so
-        independent restarts overlap almost for free.  Restart r always starts from the point
-        drawn from seed-sequence child r, so the set of runs does not depend on the sharding."""
+        independent restarts overlap almost for free.  ``batched`` (default: on for the Helmholtz kernels
+        when this rank has at least two restarts) advances up to ``batched`` restarts (True: all of this
+        rank's, at most 64) in lock step through gp2d_lml_grad_batched instead -- one chain of launches per
+        round for all of them, see _restarts_lockstep.  Restart r always starts from the point
+        drawn from seed-sequence child r, so the set of runs does not depend on the sharding or the mode."""
         import torch
         base = np.random.SeedSequence(seed)
         children = base.spawn(int(num_restarts))
@@ -288,8 +398,22 @@ class GPRegression:
                     if not robust:
                         raise
 
+        if batched is None:
+            batched = self._lockstep_ok() and len(mine) >= 2 and parallel == 1
+        if batched and not self._lockstep_ok():
+            raise ValueError("batched restarts are implemented for the Helmholtz kernels (myKernel, nonDivK, nonRotK)")
         parallel = max(1, min(int(parallel), len(mine)))
-        if parallel == 1:
+        if batched and mine:
+            nbatch = len(mine) if batched is True else int(batched)
+            nbatch = max(1, min(nbatch, len(mine), 64))
+            free_b, _ = torch.cuda.mem_get_info(self._gp.device)
+            nbatch = max(1, min(nbatch, int(0.8 * free_b) // max(1, self._gp.ws_bytes)))
+
+            def report(r, run):
+                if messages or verbose:
+                    print("Optimization restart %d/%d, f = %s" % (r + 1, num_restarts, run.f_opt))
+            results.update(self._restarts_lockstep(mine, first, init, children, max_iters, nbatch, robust, report))
+        elif parallel == 1:
             keep = len(self.optimization_runs)
             work(self, mine)
             del self.optimization_runs[keep:]

@@ -561,7 +561,7 @@ def run_ours(args):
         flops_pred = float(n) * n * m_cols + 2.0 * n * m_cols
         ach = flops_pred / (pred_ms * 1e-3) / 1e12
         sm_max_mhz = clocks.get("sm_max_mhz") or 1965.0
-        derived = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+        derived = 148 * 64 * 2 * sm_max_mhz * 1e6 / 1e12
         out = {
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_max / K * 1e3, "higher_is_better": False, "scaling": "weak",
@@ -578,7 +578,7 @@ def run_ours(args):
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": NCU_PREDICT_DRAM_BYTES, "traffic_unit": "bytes", "traffic_source": NCU_PREDICT_SOURCE,
                 "peak_source": "FP64 DMMA.8x8x4 register-resident loop measured live in this run "
-                               "(MEASURED_PEAKS.json has no fp64 figure); derived ceiling 148 SMs x 128 FMA/clk x 2 x "
+                               "(MEASURED_PEAKS.json has no fp64 figure); derived ceiling 148 SMs x 64 FP64 FMA/clk/SM x 2 flop x "
                                "%.0f MHz = %.2f TFLOP/s" % (sm_max_mhz, derived),
                 "peak_derived": derived,
                 "algorithmic_flops_per_launch": flops_pred, "ms_per_launch": pred_ms,

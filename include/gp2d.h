@@ -137,6 +137,26 @@ int gp2d_lml_grad(const double* X, int N, const double* y,
                   int reference_compat, void* ws, size_t ws_bytes, double* out5, int* info,
                   void* stream);
 
+/* ---- batches of independent problems of one size ----------------------------------------------
+ * B problems with the same N in ONE chain of launches (every kernel of the fit covers the whole batch:
+ * B diagonal blocks factorise side by side instead of one SM working while 147 idle).  This is what the
+ * reference's independent units map to: the restarts of optimize_restarts (krig.py:450; GP_plots.py:765 --
+ * same X, y, different theta: x_stride = y_stride = 0) and the time slices / snapshots of the predict loop
+ * (krig.py:541-557 -- different X, y: strides >= 2N doubles).
+ * Problem b reads X + b x_stride, y + b y_stride, theta4[4 b .. 4 b + 3] = (l_df, l_cf, ratio, noise) (HOST
+ * array, read before the call returns) and owns the workspace ws + b gp2d_fit_workspace_bytes(N); after the
+ * call that workspace is a fit state like gp2d_fit's (pass it to gp2d_predict / gp2d_fit_predict_state).
+ * alpha_out [B][2N] may be NULL; lml_out [B]; out5 [B][5] as gp2d_lml_grad; info [B] (device).
+ * Every problem gets the arithmetic of its single-problem call: results are bit-identical to gp2d_fit /
+ * gp2d_lml_grad (ill-conditioned problems, which need the refined factorisation, run one by one). */
+size_t gp2d_fit_batched_workspace_bytes(int N, int B);
+int gp2d_fit_batched(const double* X, int64_t x_stride, int N, const double* y, int64_t y_stride, int B,
+                     const double* theta4, double jitter, void* ws, size_t ws_bytes, double* alpha_out,
+                     double* lml_out, int* info, void* stream);
+int gp2d_lml_grad_batched(const double* X, int64_t x_stride, int N, const double* y, int64_t y_stride, int B,
+                          const double* theta4, double jitter, int reference_compat, void* ws, size_t ws_bytes,
+                          double* out5, int* info, void* stream);
+
 /* ---- space-time product kernel ---------------------------------------------------------------
  * K = tvar * exp(-dt^2 / (2 lt^2)) * Helmholtz(l_df, l_cf, ratio)(a - a', b - b'): the product
  * Kt(t) * nonDivK(y, x) of scratch.py:506-508 with Kt of myKernel.py:337-363 (an RBF in time tiled
