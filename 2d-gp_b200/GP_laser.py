@@ -24,13 +24,40 @@ def great_circle_km(lat1, lon1, lat2, lon2):
     return 2.0 * EARTH_RADIUS_KM * np.arcsin(np.sqrt(a))
 
 
+class _TracksUnpickler(pickle.Unpickler):
+    """Unpickler for the reference's track pickles that imports nothing from the data's directory: the
+    container classes of laser_class.py map onto this package's own (laser_io_methods), numpy arrays /
+    dtypes / scalars and datetimes are rebuilt, every other global is refused."""
+    _NUMPY = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"}
+
+    def find_class(self, module, name):
+        if module in ("laser_class", "laser_io_methods") and name in ("interpolated_tracks", "drifter"):
+            from . import laser_io_methods
+            return getattr(laser_io_methods, name)
+        if module.split(".")[0] == "numpy" and name in self._NUMPY:
+            import importlib
+            try:
+                return getattr(importlib.import_module(module), name)
+            except (ImportError, AttributeError):          # numpy.core -> numpy._core renames
+                import numpy._core.multiarray as ma
+                return getattr(ma, name) if hasattr(ma, name) else getattr(np, name)
+        if (module, name) in (("datetime", "datetime"), ("datetime", "timedelta"), ("datetime", "date")):
+            import datetime
+            return getattr(datetime, name)
+        if (module, name) in (("copy_reg", "_reconstructor"), ("copyreg", "_reconstructor")):
+            import copyreg
+            return copyreg._reconstructor
+        if (module, name) in (("__builtin__", "object"), ("builtins", "object")):
+            return object
+        raise pickle.UnpicklingError("refusing to load %s.%s from a track pickle" % (module, name))
+
+
 def load_tracks(path="simulTracks.pkl", class_dir=None):
-    """Unpickle an ``interpolated_tracks`` object written by the reference (Python 2 pickle).
-    ``class_dir`` is the directory holding the reference's laser_class.py."""
-    if class_dir and class_dir not in sys.path:
-        sys.path.insert(0, class_dir)
+    """Read an ``interpolated_tracks`` object written by the reference (Python 2 pickle) with a
+    restricted unpickler: no module is imported from the pickle's directory (``class_dir`` is accepted
+    for compatibility and ignored), only the track containers, numpy arrays and datetimes are rebuilt."""
     with open(path, "rb") as f:
-        return pickle.load(f, encoding="latin1")
+        return _TracksUnpickler(f, encoding="latin1").load()
 
 
 def laser(ts=20, nsteps=8, l_df=5, l_cf=5, tau=1, rate=0.5, noise=0.0025, nsamples=1, tracks=None,
@@ -94,11 +121,17 @@ laser2 = laser          # GP_laser.laser2 (GP_laser.py:195-321) is a verbatim co
 
 def simLaser(ts=0, l_df=2, l_cf=2, rate=0.5, noise=0.05, tracks=None, path="simulTracks.pkl",
              simlaser_compat=False, return_var=False):
-    """Returns X, Y, uf, vf, xob, yob, u, v like the reference (plus uvar, vvar on request).
+    """Returns X, Y, uf, vf, xob, yob, u, v with the reference's shapes and ordering (plus uvar, vvar on
+    request).
 
-    simlaser_compat=True reproduces the reference's K* weighting (1-rate)*rate on the
-    curl-free part (GP_laser.py:181); the default uses the weighting of GP_laser.py:122.
-    """
+    DEVIATION FROM UPSTREAM BY DEFAULT: the reference's simLaser weights the cross-covariance as
+    rate*K*_df + (1-rate)*rate*K*_cf (GP_laser.py:181, an extra ``rate`` on the curl-free part that its
+    own K, GP_laser.py:177-179, and laser(), GP_laser.py:122, do not have), so its (uf, vf) are not the
+    posterior mean of the model it fits.  The default here is the consistent weighting of GP_laser.py:122.
+    Pass ``simlaser_compat=True`` for a drop-in comparison with upstream output: it reproduces
+    GP_laser.py:181 exactly (golden-tested both ways in tests/test_reference_surface.py and
+    tests/test_gpu_parity.py::test_simlaser_fit_predict); the variance is then not returned, as the
+    reference's own variance uses yet another weighting."""
     dx = 0.5
     x = np.arange(0, 25 + dx, dx)
     y = np.arange(0, 25 + dx, dx)

@@ -78,7 +78,7 @@ bool theta_ok(double l_df, double l_cf, double ratio) {
 // known from the arguments alone.  Past 1e7 (parity at 1e-8 is no longer safe) the panels are refined
 // against the factor (potri_lower, t_refine): +2 GEMMs per panel, no side-stream overlap.  The GP
 // configurations of BASELINE.json sit at 1e4-1e5; the per-drifter track models at 1e12-1e13.
-double g_robust_cond = 1e7;          // bring-up hook: gp2d_dbg_set_robust_cond
+thread_local double g_robust_cond = 1e7;   // bring-up hook gp2d_dbg_set_robust_cond: per host thread
 int refine_steps_for(double kss, long n_scalar, double diag_add) {
     if (!(diag_add > 0.0)) return 1;
     return (kss * (double)n_scalar / diag_add > g_robust_cond) ? 1 : 0;

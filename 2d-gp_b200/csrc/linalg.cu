@@ -77,7 +77,7 @@ static void gemm_launch_ws(bool a_mn, bool b_mn, unsigned tiles, const GemmArgs&
 // The cheaper estimate wins: small problems and awkward wave counts (e.g. 300 tiles = 2.03 waves)
 // go to the 64-tile kernel, everything else to the 128-tile one.  A non-negative override forces
 // 128-tiles at or above that many 128-tiles (0: always, huge: never) -- tests use it.
-static int g_small_tile_threshold = -1;
+static thread_local int g_small_tile_threshold = -1;      // bring-up override, per host thread
 void set_small_tile_threshold(int t) { g_small_tile_threshold = t; }
 
 static int num_sms() {
@@ -296,7 +296,7 @@ struct PotriSide {
     }
 };
 static thread_local PotriSide g_side;
-static bool g_potri_overlap = true;
+static thread_local bool g_potri_overlap = true;           // bring-up switch, per host thread
 void set_potri_overlap(bool on) { g_potri_overlap = on; }
 
 struct PotriCtx {

@@ -514,7 +514,7 @@ int predict_max_ctas() {
 // (measured with tools/explore.py split at npad = 4096: 1.15 % for the Helmholtz block generator,
 // 3.4 % for the scalar family, which needs one exponential per entry; both scale as 1 / npad).  The smallest nsplit in
 // {1,2,4,8} within 3 % of the best estimate is taken.
-static int g_force_split = 0;
+static thread_local int g_force_split = 0;                 // bring-up override, per host thread
 void set_predict_split(int s) { g_force_split = (s == 1 || s == 2 || s == 4 || s == 8) ? s : 0; }
 
 int predict_choose_split(long ntiles, int npad, int fam) {

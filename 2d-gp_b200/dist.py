@@ -103,6 +103,11 @@ def gather_best(model):
         dist.all_gather(allr, t)
         recs = torch.stack(allr).cpu().numpy()
         rec = recs[np.argmin(recs[:, 0])]
+    if not np.isfinite(rec[0]):
+        # no rank has a successful run (robust=True swallows failing restarts): keep the model as it is
+        import warnings
+        warnings.warn("gather_best: no successful optimisation run on any rank; parameters left unchanged", RuntimeWarning)
+        return float("inf")
     model._set_free(rec[1:])
     model.parameters_changed()
     return float(rec[0])

@@ -164,7 +164,7 @@ REFINE_CHUNK = 1 << 25      # doubles in one K* chunk (256 MB)
 ROBUST_COND = 1e7           # same threshold as csrc/capi.cu refine_steps_for
 
 
-def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3, chunk_elems=REFINE_CHUNK):
+def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3, chunk_elems=REFINE_CHUNK, cache=None):
     """Prediction whose accuracy does not degrade with cond(K): the fused kernel applies the explicit
     inverse factor (error ~ cond(K) eps), here the refined inverse P is only a preconditioner and
     both solves are iterated against fp64 residuals,
@@ -173,15 +173,24 @@ def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3,
     from this library's kernel builds, gp2d_spd_inverse and gp2d_dgemm; K* and W are materialised
     chunk by chunk over the grid points, ~8x the flops of the fused pass.
     K_fn(A, B, diag) -> covariance block (reference layout); ncomp = 2 for the stacked vector
-    kernels; kdiag_fn(m) -> prior variances of an m-point chunk in the same stacking."""
+    kernels; kdiag_fn(m) -> prior variances of an m-point chunk in the same stacking.
+    ``cache``: a dict owned by the caller; the O(n^3) part (K, its inverse, the iterated alpha) is stored
+    there under ``key`` and reused by later calls with the same key (krig.predict calls once per time
+    slice): pass {"key": (hyper-parameters, diag_add, steps)} and invalidate by replacing the dict."""
     dev = X.device
     N = int(X.shape[0])
     n = ncomp * N
-    Kh = K_fn(X, None, diag_add)
-    P = spd_inverse(Kh)
-    a = matmul(P, y)
-    for _ in range(int(steps)):
-        a = a + matmul(P, y - matmul(Kh, a))
+    key = None if cache is None else cache.get("key")
+    if cache is not None and cache.get("have") == key and key is not None:
+        Kh, P, a = cache["Kh"], cache["P"], cache["a"]
+    else:
+        Kh = K_fn(X, None, diag_add)
+        P = spd_inverse(Kh)
+        a = matmul(P, y)
+        for _ in range(int(steps)):
+            a = a + matmul(P, y - matmul(Kh, a))
+        if cache is not None and key is not None:
+            cache.update(Kh=Kh, P=P, a=a, have=key)
     M = int(Xs.shape[0])
     mean = torch.empty(ncomp * M, dtype=torch.float64, device=dev)
     var = torch.empty(ncomp * M, dtype=torch.float64, device=dev)
@@ -203,6 +212,18 @@ def refined_predict(K_fn, X, y, Xs, ncomp, kdiag_fn, diag_add, var_add, steps=3,
             mean[c * M + lo:c * M + hi] = mc[c * (hi - lo):(c + 1) * (hi - lo)]
             var[c * M + lo:c * M + hi] = vc[c * (hi - lo):(c + 1) * (hi - lo)]
     return mean, var
+
+
+def _refine_cache(gp, key):
+    """Cache slot of the iterated-solve prediction on a GP object: keyed on the hyper-parameters, the
+    EFFECTIVE diagonal term (noise and the jitter the fit settled on, models._jitchol raises gp.jitter) and
+    the data pointers, so set_params / new data / a different jitter all miss and rebuild."""
+    key = key + (gp.X.data_ptr(), gp.y.data_ptr(), int(gp.X.shape[0]))
+    c = getattr(gp, "_refined", None)
+    if c is None or c.get("key") != key:
+        c = {"key": key}
+        gp._refined = c
+    return c
 
 
 # ------------------------------------------------------------------------------------------
@@ -267,6 +288,10 @@ class HelmholtzGP:
         """K^-1 y in the caller's stacked order."""
         out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
         self.fit_async(alpha_out=out)
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         return out
 
     def predict(self, Xs, include_noise=False, out_mean=None, out_var=None):
@@ -302,7 +327,8 @@ class HelmholtzGP:
         th = (self.l_df, self.l_cf, self.ratio)
         return refined_predict(lambda A, B, d=0.0: kernel_K(A, B, *th, diag_add=d), self.X, self.y, Xsd, 2,
                                lambda m: kernel_Kdiag(m, *th, device=self.device), self.noise + self.jitter,
-                               self.noise if include_noise else 0.0, steps, chunk_elems)
+                               self.noise if include_noise else 0.0, steps, chunk_elems,
+                               cache=_refine_cache(self, (th, self.noise, self.jitter, int(steps))))
 
     def lml_and_grad(self, reference_compat=False):
         """(LML, grad[4]) with grad over (l_df, l_cf, ratio, noise) as host floats."""
@@ -558,6 +584,10 @@ class SpaceTimeGP:
     def alpha(self) -> torch.Tensor:
         out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
         self.fit_async(alpha_out=out)
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         return out
 
     def predict_state(self) -> torch.Tensor:
@@ -597,7 +627,8 @@ class SpaceTimeGP:
         l_df, l_cf, ratio, tvar, _ = self.theta
         return refined_predict(lambda A, B, d=0.0: st_K(A, B, *self.theta, diag_add=d), self.X, self.y, Xsd, 2,
                                lambda m: tvar * kernel_Kdiag(m, l_df, l_cf, ratio, device=self.device),
-                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems,
+                               cache=_refine_cache(self, (self.theta, self.noise, self.jitter, int(steps))))
 
     def lml_and_grad(self):
         """(LML, grad[6]) over (l_df, l_cf, ratio, tvar, lt, noise)."""
@@ -722,6 +753,10 @@ class ScalarGP:
     def alpha(self) -> torch.Tensor:
         out = torch.empty(self.N, dtype=torch.float64, device=self.device)
         self.fit_async(alpha_out=out)
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         return out
 
     def predict_state(self) -> torch.Tensor:
@@ -767,7 +802,8 @@ class ScalarGP:
         kss = float(np.sum(self.var))
         return refined_predict(lambda A, B, d=0.0: rbf_K(A, B, self.var, self.ls, diag_add=d), self.X, self.y, Xsd, 1,
                                lambda m: torch.full((m,), kss, dtype=torch.float64, device=self.device),
-                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems,
+                               cache=_refine_cache(self, (self.var.tobytes(), self.ls.tobytes(), self.noise, self.jitter, int(steps))))
 
     def lml_and_grad(self):
         """(LML, grad) with grad over (variance_q, lengthscale_q[..])_q then the noise variance."""
@@ -911,6 +947,10 @@ class HelmholtzSumGP:
     def alpha(self) -> torch.Tensor:
         out = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
         self.fit_async(alpha_out=out)
+        info = int(self._info.item())
+        if info > 0:
+            self.fitted = False
+            raise LinAlgError("covariance not positive definite (pivot %d)" % info)
         return out
 
     def predict_state(self) -> torch.Tensor:
@@ -956,7 +996,9 @@ class HelmholtzSumGP:
             raise ValueError("prediction points must have %d columns" % self.ldx)
         return refined_predict(lambda A, B, d=0.0: hsum_K(A, B, self.types, self.params, diag_add=d), self.X, self.y, Xsd, 2,
                                lambda m: hsum_Kdiag(m, self.ldx, self.types, self.params, device=self.device),
-                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems)
+                               self.noise + self.jitter, self.noise if include_noise else 0.0, steps, chunk_elems,
+                               cache=_refine_cache(self, (self.types.tobytes(), self.params.tobytes(), self.noise, self.jitter,
+                                                          int(steps))))
 
     def lml_and_grad(self):
         """(LML, grad) with grad over (var, lt, la, lb)_q for every term, then the noise variance."""

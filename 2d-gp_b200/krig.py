@@ -190,8 +190,11 @@ def runRestarts(fname, nres=10, nKernels=2, seed=None, max_iters=1000):
     rank, world = gdist.world()
     model.optimize_restarts(messages=False, verbose=False, num_restarts=nres, seed=seed, max_iters=max_iters,
                             rank=rank, world=world, robust=True)
-    gdist.gather_best(model)
+    best = gdist.gather_best(model)
     hyp = model.param_array
+    if not np.isfinite(best):
+        print('runRestarts: every restart failed; %s left as it was' % path)
+        return model
     if rank == 0:
         model.pickle(path)
         print('Optimized Hyperparameters =================================================')
@@ -320,6 +323,12 @@ def predictTest(filename):
     return out
 
 
+def testModel1D(model, Xt, test_points):
+    """RMSE of a scalar model at the test points (krig.py:637-639)."""
+    f, fVar = model.predict(Xt)
+    return rmse(f, test_points)
+
+
 def rmse(ys, y):
     """Root-mean-square error (krig.py:641-645)."""
     error = np.reshape(np.asarray(ys) - np.asarray(y), [-1])
@@ -404,6 +413,49 @@ def scikit_prior(filename0, varname='v', dt=0, tlim=6, radar='', xlim=[0, 0], yl
     writeNC(fi, varname, U)
     writeNC(fi, varname + 'var', Ustd ** 2)
     writeNC(fi, 'hyperparam_' + varname, HP)
+    fi.close()
+    print('End of script, time : ' + str(datetime.now() - startTime))
+    return outFile, U, Ustd ** 2
+
+
+
+def scikitSnapshot(filename, var, dt, ylim=[0, 0], xlim=[0, 0]):
+    """One time slice of the grid in ``filename.nc`` predicted with the pickled scikit-learn-style model
+    ``filename_scikit_u.pkl`` (var == 1) or ``filename_scikit_v.pkl`` and written to
+    ``<filename>_<time>h_scikit.nc`` (krig.py:210-256).  Upstream the function cannot run: it uses the
+    undefined names ``varname`` / ``covarname`` / ``startTime`` (krig.py:253-256) and indexes
+    ``ylim[1>ylim[0]]`` (krig.py:218); here the variable is 'u' / 'v' by ``var``, its variance goes to
+    '<name>var' as in scikit_prior, and both limits are compared the way xlim is.  The slice is
+    ``tg.size // 2 + dt``.  Returns (outFile, U, Uvar)."""
+    import pickle
+    from scipy.io import netcdf_file
+    startTime = datetime.now()
+    f = netcdf_file(filename + '.nc', 'r', mmap=False)
+    HPV = np.array(f.variables['hyperparam_v'][:])
+    xg, yg, tg = np.array(f.variables['x'][:]), np.array(f.variables['y'][:]), np.array(f.variables['time'][:])
+    f.close()
+    if (xlim[1] > xlim[0]) and (ylim[1] > ylim[0]):
+        xg = xg[np.where((xg >= xlim[0]) & (xg <= xlim[1]))]
+        yg = yg[np.where((yg >= ylim[0]) & (yg <= ylim[1]))]
+    Yg, Tg, Xg = np.meshgrid(yg, tg, xg)
+    X = np.concatenate([np.reshape(Tg, [Tg.size, 1]), np.reshape(Yg, [Yg.size, 1]), np.reshape(Xg, [Xg.size, 1])], axis=1)
+    inc = yg.size * xg.size
+    it = tg.size // 2 + dt
+    i2 = inc * it
+    outFile = filename + '_' + str(tg[it]) + 'h_scikit.nc'
+    tg = np.array([tg[it]])
+    X2 = X[i2:i2 + inc, :]
+    varname = 'u' if var == 1 else 'v'
+    with open(filename + '_scikit_' + varname + '.pkl', 'rb') as inp:
+        model_u = pickle.load(inp)
+    U, Ustd = model_u.predict(X2, return_std=True)
+    U = np.reshape(U, [tg.size, yg.size, xg.size])
+    Ustd = np.reshape(Ustd, [tg.size, yg.size, xg.size])
+    if not os.path.isfile(outFile):
+        createNC(outFile, tg, yg, xg, HPV)
+    fi = openNC(outFile, 'a')
+    writeNC(fi, varname, U)
+    writeNC(fi, varname + 'var', Ustd ** 2)
     fi.close()
     print('End of script, time : ' + str(datetime.now() - startTime))
     return outFile, U, Ustd ** 2

@@ -112,22 +112,33 @@ def _window(dr, time):
     return it, np.arange(lo, hi + 1)
 
 
-def _track_model(X, Y, optimize, max_iters, device):
-    k = RBF(input_dim=1, variance=TRACK_VARIANCE, lengthscale=TRACK_LENGTHSCALE)
+def _track_model(X, Y, optimize, max_iters, device, start=None):
+    """One scalar track model.  ``start`` = (variance, lengthscale, noise) to begin the optimisation from;
+    None = the preset values.  Upstream builds ONE kernel object before the drifter loop and reuses it for
+    every drifter and both coordinates (laser_io_methods.py:464-503), so there each optimisation begins at
+    the previous model's optimum; the default here starts every model from the presets, which makes the
+    drifters independent (they run concurrently and on different ranks) but can end in a different
+    L-BFGS-B optimum than the upstream chain.  ``warm_start=True`` in kriging() / interp_kriging() passes
+    the previous optimum along and reproduces the upstream order of starts (sequential only)."""
+    var0, len0, noise0 = (TRACK_VARIANCE, TRACK_LENGTHSCALE, TRACK_NOISE) if start is None else start
+    k = RBF(input_dim=1, variance=var0, lengthscale=len0)
     m = models.GPRegression(X, Y, k, device=device)
-    m.Gaussian_noise = TRACK_NOISE
+    m.Gaussian_noise = noise0
     if optimize:
         m.optimize(max_iters=max_iters, messages=False)
     return m
 
 
-def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
+def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None, start=None):
     """One drifter (laser_io_methods.py:637-700): dict with the interpolated lon / lat and their
     posterior variances on ``time`` (NaN outside the drifter's life span), centred-difference
     velocities, the per-interval data counts and the hyper-parameters of both models.  Times are
     seconds; the GP input is hours since ``t_origin`` (default time[0]).  Mean and variance come from
     the final model (interp_kriging upstream keeps the variance from before the optimisation,
-    laser_io_methods.py:499,520; its joblib twin uses the optimised one, :666-668, as here)."""
+    laser_io_methods.py:499,520; its joblib twin uses the optimised one, :666-668, as here).
+    ``start``: (variance, lengthscale, noise) the first (longitude) model starts from; the latitude model
+    then starts from the longitude optimum and the last optimum is returned under "next_start" -- the
+    chain of starts of the upstream loop, which shares one kernel object (see _track_model)."""
     time = np.asarray(time, dtype=np.float64)
     t0 = time[0] if t_origin is None else float(t_origin)
     nT = time.size
@@ -142,7 +153,9 @@ def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
         Tg = ((time[it] - t0) / 3600.)[:, None]
         for name, raw in (("Lon", dr.lon), ("Lat", dr.lat)):
             Y = np.asarray(raw, dtype=np.float64)[sel][:, None]
-            m = _track_model(X, Y, optimize, max_iters, device)
+            m = _track_model(X, Y, optimize, max_iters, device, start=start)
+            if start is not None:
+                start = (m.rbf.variance[0], m.rbf.lengthscale[0], m.Gaussian_noise[0])
             # cond(K) ~ n variance / noise ~ 1e10-1e13 for these models: predict() takes the iterated
             # solve by itself, not the fused explicit-inverse path (engine.refined_predict)
             mean, var = m.predict(Tg)
@@ -161,6 +174,8 @@ def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
             out["n_samples"][it[1:] - 1] = M1
             out["data_freq"][it[1:] - 1] = M2
     # drogue status along the time axis (laser_io_methods.py:528-538)
+    if start is not None:
+        out["next_start"] = start
     loss, dates = getattr(dr, "drogueLoss", None), getattr(dr, "date_time", None)
     before = [] if loss is None or dates is None else [i for i, d in enumerate(dates) if d < loss]
     if before:
@@ -172,12 +187,16 @@ def kriging(dr, time, t_origin=None, optimize=True, max_iters=200, device=None):
     return out
 
 
-def interp_kriging(data, dt=900, period=10, optimize=True, max_iters=200, output=None, parallel=4, device=None):
+def interp_kriging(data, dt=900, period=10, optimize=True, max_iters=200, output=None, parallel=4, device=None,
+                   warm_start=False):
     """All drifters (laser_io_methods.py:410-570 and its joblib twin :576-633): ``data`` is the list
     of raw drifter objects, data[0] the first one released.  Returns an ``interpolated_tracks`` and
     pickles it to ``output`` when given.  ``parallel`` drifters are in flight at a time on separate
     CUDA streams; under torch.distributed drifter n runs on rank n % world and rank 0 assembles (and
-    writes) the result, which every rank returns."""
+    writes) the result, which every rank returns.  ``warm_start=True`` reproduces the upstream chain of
+    optimisation starts (one shared kernel object, laser_io_methods.py:464-503): every model begins at the
+    optimum of the one before it, which makes the drifters sequential (parallel and the rank sharding are
+    then switched off)."""
     import torch
     t_first = float(np.asarray(data[0].time)[0])
     time = np.arange(float(np.asarray(data[0].time)[1]), t_first + period * 86400., dt)
@@ -191,7 +210,14 @@ def interp_kriging(data, dt=900, period=10, optimize=True, max_iters=200, output
             results[n] = kriging(data[n], time, t_origin=t_first, optimize=optimize, max_iters=max_iters, device=device)
 
     parallel = max(1, min(int(parallel), len(mine)))
-    if parallel == 1:
+    if warm_start:
+        start = (TRACK_VARIANCE, TRACK_LENGTHSCALE, TRACK_NOISE)
+        for n in range(len(data)):                                  # every rank runs the whole chain
+            results[n] = kriging(data[n], time, t_origin=t_first, optimize=optimize, max_iters=max_iters, device=device,
+                                 start=start)
+            start = results[n].pop("next_start", start)
+        world = 1
+    elif parallel == 1:
         work(mine)
     else:
         import queue

@@ -325,7 +325,12 @@ class GPRegression:
                         break
                     try:
                         rr = r if first else max(r, 1)       # only the very first restart starts from the current point
-                        x0 = init if rr == 0 else np.random.default_rng(children[r]).standard_normal(len(free))
+                        # the start point takes the same round trip through the constrained values as in
+                        # _one_restart (set, then read back in optimize), so the runs are the same bit for bit
+                        z = init if rr == 0 else np.random.default_rng(children[r]).standard_normal(len(free))
+                        for p, zi in zip(free, z):
+                            p.from_free(float(zi))
+                        x0 = np.array([p.to_free() for p in free])
                         res = sopt.minimize(objective, x0, jac=True, method="L-BFGS-B", options={"maxiter": int(max_iters)})
                         results[r] = _Run(res.x.copy(), float(res.fun), res.message, int(res.nfev))
                         report(r, results[r])
@@ -532,10 +537,25 @@ def _restore(m, st):
     return m
 
 
+class _StateUnpickler(pickle.Unpickler):
+    """Model pickles written by GPRegression.pickle are dicts of numpy arrays, lists, strings and numbers:
+    only numpy's array / dtype / scalar reconstructors are allowed as globals."""
+
+    def find_class(self, module, name):
+        if module.split(".")[0] == "numpy" and name in ("_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"):
+            import importlib
+            try:
+                return getattr(importlib.import_module(module), name)
+            except (ImportError, AttributeError):
+                import numpy._core.multiarray as ma
+                return getattr(ma, name) if hasattr(ma, name) else getattr(np, name)
+        raise pickle.UnpicklingError("refusing to load %s.%s from a model pickle" % (module, name))
+
+
 def load(path, device=None):
     """Counterpart of GPy.load (krig.py:438,478-482)."""
     with open(path, "rb") as f:
-        st = pickle.load(f)
+        st = _StateUnpickler(f).load()
     p = st["params"]
     name = st["kernel"]
     if "terms" in st:

@@ -221,6 +221,21 @@ class GaussianProcessRegressor:
         self.X_train_, self.y_train_ = X, y
         return self
 
+    # pickling (krig.scikitSnapshot loads <name>_scikit_u.pkl, krig.py:237-242): the device state is not
+    # stored, only the fitted kernel and the training data; loading refits with fixed hyper-parameters
+    def __getstate__(self):
+        st = {k: v for k, v in self.__dict__.items() if k not in ("_gp", "_components")}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        if "kernel_" in st:
+            D = self.X_train_.shape[1]
+            var, ls, noise = _flatten(self.kernel_, D)
+            self._components = _components(self.kernel_)
+            self._gp = ScalarGP(self.X_train_, np.asarray(self.y_train_).reshape(-1), var, ls, noise, jitter=self.alpha)
+            self._gp.fit()
+
     @property
     def theta_(self):
         return self._theta_of(self.kernel_, self.X_train_.shape[1])

@@ -6,7 +6,9 @@
  * IEEE fp64, `stream` is a cudaStream_t passed as void*, calls are asynchronous on that
  * stream, allocate nothing (workspace is sized by the *_workspace_bytes queries), keep no
  * global state and are re-entrant across streams (the _host entry points cache one device buffer per
- * host thread, see the end of this file).
+ * host thread, see the end of this file).  The library also exports bring-up hooks gp2d_dbg_* that are not
+ * declared here (tests and bench.py use them: forced GEMM tile shape, forced predict split, FP64 peak probe);
+ * the overrides they set are per host thread and off by default, so they never couple two callers.
  *
  * Return value: 0 = launched OK; -k = argument k (1-based) is invalid;
  * <= -1000 = -(1000 + cudaError_t).  Numerical failure of the factorisation is reported

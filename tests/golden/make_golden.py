@@ -20,6 +20,7 @@ import scipy.linalg as sla
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
+os.environ["GP2D_EXEC_REFERENCE"] = "1"      # this tool exists to run the reference's own lines: explicit opt-in
 from oracle import ref_slices as rs          # noqa: E402
 from oracle import gp_oracle as orc          # noqa: E402  (only for haversine/host prep)
 
