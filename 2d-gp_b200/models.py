@@ -549,6 +549,9 @@ class _StateUnpickler(pickle.Unpickler):
             except (ImportError, AttributeError):
                 import numpy._core.multiarray as ma
                 return getattr(ma, name) if hasattr(ma, name) else getattr(np, name)
+        if (module, name) == ("_codecs", "encode"):          # how protocol 2 writes the bytes of an array under py3
+            import codecs
+            return codecs.encode
         raise pickle.UnpicklingError("refusing to load %s.%s from a model pickle" % (module, name))
 
 
