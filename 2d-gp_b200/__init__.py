@@ -8,6 +8,6 @@ from . import _lib                                           # noqa: F401  (load
 from .engine import (HelmholtzGP, LinAlgError, kernel_K, kernel_Kdiag, kernel_grad_sums,   # noqa: F401
                      potrf, spd_inverse, matmul, fit_predict_host, as_dev, rbf_K, rbf_grad_sums, ScalarGP,
                      st_K, st_grad_sums, SpaceTimeGP, hsum_K, hsum_Kdiag, hsum_grad_sums, HelmholtzSumGP,
-                     HelmholtzBatch, krig_snapshots)
+                     HelmholtzBatch, krig_snapshots, set_predict_i8)
 
 __version__ = "0.1.0"

@@ -83,12 +83,16 @@ SIGNATURES = {
     "gp2d_fit_predict_host": (C.c_int, [c_dp, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_double, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "gp2d_host_release": (None, []),
+    "gp2d_set_option": (C.c_int, [C.c_int, C.c_double]),
     "gp2d_fit_batched_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gp2d_fit_batched": (C.c_int, [c_dp, C.c_int64, C.c_int, c_dp, C.c_int64, C.c_int, c_dp, C.c_double, C.c_void_p,
                                    C.c_size_t, c_dp, c_dp, c_ip, c_st]),
     "gp2d_lml_grad_batched": (C.c_int, [c_dp, C.c_int64, C.c_int, c_dp, C.c_int64, C.c_int, c_dp, C.c_double, C.c_int,
                                         C.c_void_p, C.c_size_t, c_dp, c_ip, c_st]),
 }
+
+
+GP2D_OPT_PREDICT_I8 = 1
 
 
 class Gp2dError(RuntimeError):

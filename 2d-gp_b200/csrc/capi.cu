@@ -19,11 +19,14 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct FitLayout {
     int npad;
     size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_r, off_alpha, off_partial, off_X, off_scal, off_info, total;
+    size_t off_Zq, off_zunit;     // int8 digit slices of Z and their row units (Helmholtz layouts; 0 bytes otherwise)
+    int i8;                       // the layout carries them
 };
+constexpr size_t GATE_OFF = 2 * sizeof(int);     // int after info in the off_info block: slice count of the int8 path, 0 = fp64 only
 
 // n: scalar observations; x_doubles: size of the copy of the observation points;
 // grad_doubles: partial-sum doubles the likelihood-gradient reduction needs
-FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doubles) {
+FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doubles, bool i8 = false) {
     FitLayout L;
     L.npad = round_up((int)n_scalar, TILE);
     const size_t n = (size_t)L.npad, d = sizeof(double);
@@ -41,6 +44,9 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
     L.off_partial = o; o = align256(o + part * d);
     // what gp2d_predict reads, contiguous so that it can be shipped to another GPU in one piece
     L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
+    L.i8 = i8 && L.npad <= i8_max_npad();
+    L.off_Zq = o; o = align256(o + (L.i8 ? i8_zq_bytes(L.npad) : 0));
+    L.off_zunit = o; o = align256(o + (L.i8 ? n * d : 0));
     L.off_alpha = o; o = align256(o + n * d);
     L.off_X = o; o = align256(o + x_doubles * d);
     L.off_scal = o; o = align256(o + 32 * d);
@@ -52,7 +58,7 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
 // ldx = 2: points (a, b); ldx = 3: space-time points (t, a, b)
 FitLayout fit_layout(int N, int ldx = 2) {
     return fit_layout_general(2 * (size_t)N, (size_t)ldx * N,
-                              (HELM_NP + 1) * (size_t)lml_grad_partials(round_up(2 * N, TILE)));
+                              (HELM_NP + 1) * (size_t)lml_grad_partials(round_up(2 * N, TILE)), /*i8=*/true);
 }
 
 FitLayout rbf_layout(int N, int D) {
@@ -82,6 +88,22 @@ thread_local double g_robust_cond = 1e7;   // bring-up hook gp2d_dbg_set_robust_
 int refine_steps_for(double kss, long n_scalar, double diag_add) {
     if (!(diag_add > 0.0)) return 1;
     return (kss * (double)n_scalar / diag_add > g_robust_cond) ? 1 : 0;
+}
+
+// int8-sliced predictive kernel (predict_i8.cu).  Its error is that of dropping the digit products beyond
+// the S-th: relative to the fp64 path ~2e-10 (S = 6) / ~1e-12 (S = 7) on the variance at a conditioning bound
+// of 1e4 and growing in proportion to the bound (tools/ozaki_emulate.py), so the slice count follows the same
+// bound the robust switch uses, and past the robust threshold the fp64 kernel stays the only path.
+// Per host thread: 0 = automatic, 1 = off, 6 / 7 = that slice count whenever the layout carries the slices.
+thread_local int g_i8_mode = 0;
+constexpr double I8_BOUND_S6 = 5e4;
+int i8_slices_for(double kss, long n_scalar, double diag_add, const FitLayout& L) {
+    if (!L.i8 || g_i8_mode == 1) return 0;
+    if (g_i8_mode == 6 || g_i8_mode == 7) return g_i8_mode;
+    if (!(diag_add > 0.0)) return 0;
+    const double bound = kss * (double)n_scalar / diag_add;
+    if (bound <= I8_BOUND_S6) return 6;
+    return bound <= g_robust_cond ? 7 : 0;
 }
 
 // factor + inverse of the padded covariance in ws (A destroyed or replaced by L), robust when asked
@@ -184,6 +206,13 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws, L.off_Zt), st);
     if (e != cudaSuccess) return e;
+    {   // digit slices for the int8 predictive kernel (off_r is free until refine_alpha)
+        const int s8 = i8_slices_for(hp.tvar * (hp.w_df + hp.w_cf), 2L * N, diag_add, L);
+        if (s8) e = i8_quantize_lower(Z, L.npad, L.npad, at<double>(ws, L.off_zunit), at<double>(ws, L.off_r), at<int8_t>(ws, L.off_Zq), st);
+        if (e != cudaSuccess) return e;
+        e = i8_set_gate(at<int>(ws, L.off_info + GATE_OFF), s8, st);
+        if (e != cudaSuccess) return e;
+    }
     e = solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
                         at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
                         at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
@@ -191,6 +220,22 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);      // A held the factor: the matrix again
     if (e != cudaSuccess) return e;
     return refine_alpha_ws(ws, L, st);
+}
+
+// Helmholtz-family prediction from a fit workspace: the int8 kernels run when the fit chose a slice count for
+// them (a flag in the fit state, read on the device), the fp64 kernel when it did not.
+cudaError_t predict_helm(const void* fit_ws, const FitLayout& L, int N, const HelmParams& hp, const double* Xs, int M,
+                         long out_stride, double var_add, double* mean, double* var, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int* gate = nullptr;
+    if (L.i8 && g_i8_mode != 1 && ws_bytes >= predict_i8_scratch_bytes(L.npad) / predict_max_ctas()) {
+        gate = at<int>(fit_ws, L.off_info + GATE_OFF);
+        cudaError_t e = predict_fused_i8(at<int8_t>(fit_ws, L.off_Zq), at<double>(fit_ws, L.off_zunit), gate, L.npad,
+                                         at<double>(fit_ws, L.off_alpha), at<double>(fit_ws, L.off_X), N, hp, Xs, M, out_stride,
+                                         var_add, mean, var, ws, ws_bytes, st);
+        if (e != cudaSuccess) return e;
+    }
+    return predict_fused(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha), at<double>(fit_ws, L.off_X), N,
+                         hp, Xs, M, out_stride, var_add, mean, var, (double*)ws, ws_bytes, st, gate);
 }
 
 }  // namespace
@@ -375,7 +420,23 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
 
 size_t gp2d_predict_workspace_bytes(int N, int M) {
     if (N <= 0 || M <= 0) return 256;
-    return align256(predict_scratch_bytes(round_up(2 * N, TILE), M, 64));
+    const int npad = round_up(2 * N, TILE);
+    size_t b = predict_scratch_bytes(npad, M, 64);
+    if (npad <= i8_max_npad()) {
+        const size_t b8 = predict_i8_scratch_bytes(npad);
+        if (b8 > b) b = b8;
+    }
+    return align256(b);
+}
+
+int gp2d_set_option(int key, double value) {
+    if (key == GP2D_OPT_PREDICT_I8) {
+        const int v = (int)value;
+        if (v != 0 && v != 1 && v != 6 && v != 7) return -2;
+        g_i8_mode = v;
+        return 0;
+    }
+    return -1;
 }
 
 int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double ratio, const double* Xs,
@@ -393,10 +454,8 @@ int gp2d_predict(const void* fit_ws, int N, double l_df, double l_cf, double rat
     FitLayout L = fit_layout(N);
     if (!ws) return -12;
     if (ws_bytes < predict_panel_bytes(L.npad)) return -13;
-    return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
-                                 at<double>(fit_ws, L.off_X), N, make_helm(l_df, l_cf, ratio), Xs, M,
-                                 (long)out_stride, var_add, mean, var, (double*)ws, ws_bytes,
-                                 (cudaStream_t)stream));
+    return cuda_rc(predict_helm(fit_ws, L, N, make_helm(l_df, l_cf, ratio), Xs, M, (long)out_stride, var_add, mean, var, ws,
+                                ws_bytes, (cudaStream_t)stream));
 }
 
 int gp2d_lml_grad(const double* X, int N, const double* y, double l_df, double l_cf, double ratio,
@@ -498,6 +557,9 @@ cudaError_t fit_core_batched(const double* X, long x_stride, int N, const double
                     /*need_inv=*/true, /*keep_L=*/false, nullptr, st, 0, nb, bs);
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws0, L.off_Zt), st, nb, bs);
+    if (e != cudaSuccess) return e;
+    for (int b = 0; b < nb && e == cudaSuccess; ++b)      // batched fits keep the fp64 predictive path
+        e = i8_set_gate(at<int>(ws0, L.off_info + GATE_OFF) + 2 * (long)b * bs, 0, st);
     if (e != cudaSuccess) return e;
     return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws0, L.off_yint), at<double>(ws0, L.off_w),
                            at<double>(ws0, L.off_alpha), at<double>(ws0, L.off_partial), at<double>(ws0, L.off_logdiag),
@@ -697,9 +759,8 @@ int gp2d_st_predict(const void* fit_ws, int N, double l_df, double l_cf, double 
     FitLayout L = fit_layout(N, 3);
     if (!ws) return -14;
     if (ws_bytes < predict_panel_bytes(L.npad)) return -15;
-    return cuda_rc(predict_fused(at<double>(fit_ws, L.off_Zt), L.npad, at<double>(fit_ws, L.off_alpha),
-                                 at<double>(fit_ws, L.off_X), N, make_helm_st(l_df, l_cf, ratio, tvar, lt), Xs3, M,
-                                 (long)out_stride, var_add, mean, var, (double*)ws, ws_bytes, (cudaStream_t)stream));
+    return cuda_rc(predict_helm(fit_ws, L, N, make_helm_st(l_df, l_cf, ratio, tvar, lt), Xs3, M, (long)out_stride, var_add,
+                                mean, var, ws, ws_bytes, (cudaStream_t)stream));
 }
 
 int gp2d_st_lml_grad(const double* X3, int N, const double* y, double l_df, double l_cf, double ratio, double tvar,

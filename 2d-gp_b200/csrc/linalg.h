@@ -1,6 +1,7 @@
 // Internal host-side entry points shared between the translation units of libgp2d.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include "helmholtz.cuh"
 #include "rbf.cuh"
 #include "hsum.cuh"
@@ -88,7 +89,7 @@ cudaError_t hsum_grad_sums(const double* X, int N, const double* X2, int M, cons
 cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           const double* X, int N, const HelmParams& hp, const double* Xs, int M,
                           long out_stride, double var_add, double* mean, double* var,
-                          double* scratch, size_t scratch_bytes, cudaStream_t st);
+                          double* scratch, size_t scratch_bytes, cudaStream_t st, const int* gate = nullptr);
 size_t predict_panel_bytes(int npad);
 size_t predict_scratch_bytes(int npad, int M, int pts_per_tile);   // full parallelism on the current device
 // scalar ARD-RBF sum: alpha and the tiles are in plain observation order (npad = N rounded up to 128)
@@ -101,6 +102,21 @@ cudaError_t predict_fused_hsum(const double* Zt, int npad, const double* alpha_i
                                double* mean, double* var, double* scratch, size_t scratch_bytes, cudaStream_t st);
 int predict_max_ctas();
 void set_predict_split(int s);          // bring-up override: 1, 2, 4, 8 (0 = heuristic)
+
+// predict_i8.cu ---------------------------------------------------------------------------
+// int8-sliced (tcgen05, TMEM) variant of predict_fused for the Helmholtz family.  Fit side: digit slices of the
+// lower triangle of Z as shared-memory tile images (Zq, i8_zq_bytes) with one power-of-two unit per row (zunit);
+// zqs is npad doubles of scratch.  *gate holds the slice count chosen for this fit (6, 7, or 0 = fp64 path only).
+size_t i8_zq_bytes(int npad);
+int i8_max_npad();
+cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st);
+cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st);
+size_t predict_i8_scratch_bytes(int npad);
+// launches the kernel of every slice count (only_s = 0) or of one; a kernel whose count is not *gate returns at once
+cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* gate, int npad, const double* alpha_int,
+                             const double* X, int N, const HelmParams& hp, const double* Xs, int M, long out_stride,
+                             double var_add, double* mean, double* var, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                             int only_s = 0);
 
 // grad.cu ---------------------------------------------------------------------------------
 // From Kinv (lower, interleaved, padded) and alpha_int: out6 = d LML / d(l_df, l_cf, ratio, tvar, lt, noise).

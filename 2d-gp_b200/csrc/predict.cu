@@ -42,6 +42,7 @@ struct PredictArgs {
     double* scratch;              // gridDim.x panels of npad x 128 doubles
     double* partial;              // [ntiles][8 groups][128] column sums (nsplit > 1)
     int ntiles, nsplit;
+    const int* gate;              // non-null: run only when *gate == 0 (the int8 kernel of predict_i8.cu owns the other values)
 };
 
 // Row-block groups.  The column sums of V^2 are ALWAYS formed as sum_{g=0..7} (group g), where
@@ -300,6 +301,7 @@ template <int FAM>
 __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_constant__ PredictArgs p) {
     constexpr int PTS = FAM == FAM_HELM ? 64 : 128;      // grid points per column tile
     constexpr int WM = 2, OS = WS_CONSUMERS / 64;
+    if (p.gate && *p.gate != 0) return;
     extern __shared__ __align__(16) double smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
     WsBarriers wb{bars, bars + WS_STAGES};
@@ -481,6 +483,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) predict_kernel(const __grid_con
 // nsplit > 1: var = k** - sum_g partial[tile][g][col], same order as the in-kernel sum
 template <int FAM>
 __global__ void __launch_bounds__(TILE) predict_finish_kernel(PredictArgs p) {
+    if (p.gate && *p.gate != 0) return;
     const int ct = blockIdx.x, tid = threadIdx.x;
     const int c = tid & 1;
     const int j = FAM == FAM_HELM ? ct * 64 + (tid >> 1) : ct * 128 + tid;
@@ -579,9 +582,10 @@ static cudaError_t predict_launch(PredictArgs& a, double* scratch, size_t scratc
 cudaError_t predict_fused(const double* Zt, int npad, const double* alpha_int,
                           const double* X, int N, const HelmParams& hp, const double* Xs, int M,
                           long out_stride, double var_add, double* mean, double* var,
-                          double* scratch, size_t scratch_bytes, cudaStream_t st) {
+                          double* scratch, size_t scratch_bytes, cudaStream_t st, const int* gate) {
     if (M <= 0) return cudaSuccess;
     PredictArgs a{};
+    a.gate = gate;
     a.Zt = Zt; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
     a.kss = a.kss1 = hp.tvar * (hp.w_df + hp.w_cf);   // ratio/l_df^2 + (1-ratio)/l_cf^2 (myKernel.py:55-57), times the time variance

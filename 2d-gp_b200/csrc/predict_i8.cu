@@ -1,0 +1,520 @@
+// Fused predictive pass on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM): the product
+// V = Z K* of predict.cu (Z = L^-1) computed from balanced base-256 digit slices of both operands
+// (Ozaki splitting): Z ~ zu_r sum_i A_i 256^(S-1-i), K* ~ ku sum_j B_j 256^(S-1-j), and
+//     V ~ zu_r ku sum_{d < S} 256^(2S-2-d) sum_{i+j=d} A_i B_j^T
+// with every A_i B_j^T an exact int8 x int8 -> int32 product.  The S (S + 1) / 2 slice products of a k-step
+// are S (S + 1) / 2 tcgen05.mma instructions into S accumulators (one per d) of NC columns each; the fp64
+// recombination (Horner in 256), the squares and the column sums happen once per row block, out of TMEM.
+// Integer arithmetic is exact, so the result is deterministic and independent of how the grid is cut.
+// What is lost is the tail i + j >= S: with S = 6 (S = 7) the variance agrees with the fp64 path to
+// ~2e-10 (~1e-12) relative at the conditioning of the BASELINE configurations (tools/ozaki_emulate.py);
+// the slice count is chosen at fit time from the conditioning bound and the fp64 DMMA kernel of predict.cu
+// remains the path beyond it (gate, below).  Same role as predict.cu: replaces GPy model.predict
+// (krig.py:543-544), GP_scripts.getMean + the diagonal of GP_laser.py:129-131.
+//
+// Why it is faster: the FP64 pipe peaks at 37 TFLOP/s; kind::i8 at M = 128, N = 80 issues one
+// 128 x 80 x 32 product per ~55 clocks per SM (bound by the shared-memory read of its operands), i.e.
+// 21 instructions per k-step of the fp64-equivalent product: ~165 TFLOP/s fp64-equivalent at S = 6.
+//
+// CTA (one per SM, persistent over column tiles of NC / 2 grid points x 2 components):
+//   warps 0-3   epilogue: TMEM -> registers, Horner, (v zu ku)^2, sum over the 128 rows, running column sums
+//   warp  4     producer: one thread, two bulk copies (A slices of Zq, B slices of the panel) per k-step
+//   warp  5     MMA issuer: one thread
+//   warps 6..   generators: build the digit slices of the K* panel of the NEXT column tile into the other
+//               of two global scratch panels while the tensor core works on the current one, and the mean
+//               K*^T alpha in fp64 on the way
+#include "common.cuh"
+#include "linalg.h"
+#include "umma.cuh"
+
+namespace gp2d {
+
+constexpr int I8_SMAX = 7;                           // digits stored per entry of Zq
+constexpr int I8_OBS_BATCH = 128;                    // observations staged in shared memory at a time
+// worst-case |accumulator| of d = S - 1 over k rows: k (2 64 128 + (S - 2) 128 128) < 2^31
+constexpr int I8_MAX_NPAD = 21760;
+
+template <int S, int NC>
+struct I8Cfg {
+    static constexpr int NG = NC / 2;                 // grid points per column tile
+    static constexpr int GT = NG * 8;                 // generator threads: (grid point, k-step slot)
+    static constexpr int THREADS = 192 + GT;
+    static constexpr int BTILE = NC * I8_KSTEP;       // bytes of one B slice tile
+    static constexpr int STAGE_BYTES = S * (I8_ATILE_BYTES + BTILE);
+    static constexpr int STAGES = S == 6 ? 5 : 4;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 2 + 4;  // full, empty, acc_full, acc_empty, panel_full[2], panel_empty[2]
+    // doubles after the barriers: observation stage, mean partials [8][NG][2], column sums [4][NC], parameters
+    static constexpr int TAIL_DOUBLES = 5 * I8_OBS_BATCH + 8 * NG * 2 + 4 * NC + 64;
+    static constexpr int SMEM_BYTES = RING_BYTES + NBARS * 8 + 16 + TAIL_DOUBLES * 8;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(S * NC <= TMEM_COLS, "S accumulators of NC columns must fit TMEM");
+    static_assert(NC % 16 == 0, "tcgen05.mma M = 128 needs N % 16 == 0");
+    static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+struct PredictI8Args {
+    const int8_t* Zq;             // [k-step of the lower triangle][I8_SMAX][4096]: digit slices of Z, tile images
+    const double* zunit;          // [npad] value of one unit of digit I8_SMAX - 1 of row r
+    int npad;
+    const double* alpha;          // pair-interleaved, zero padded
+    const double* X; int N;
+    HelmParams hp;
+    const double* Xs; int M;
+    long out_stride;
+    double kss, kss1, var_add;
+    double kscale;                // K* entries are quantised as rint(k kscale), |k kscale| <= 2^(8 S - 2)
+    double cscale;                // ku 256^(S-1) 256^(I8_SMAX-S): v = Horner zunit[r] cscale
+    double* mean; double* var;
+    uint8_t* scratch;             // gridDim.x x 2 panels
+    size_t panel_bytes;
+    int ntiles;
+    const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
+};
+
+// ---------------------------------------------------------------------------------------------------
+// fit side: digit slices of Z = L^-1
+// ---------------------------------------------------------------------------------------------------
+// one warp per row: power-of-two scale from max |Z[r][0 .. (r / 128 + 1) 128)| (upper part of the diagonal
+// tile is exactly zero).  zunit[r] = 2^(e - 55), zqs[r] = 2^(55 - e) with max / 2^e in [1/4, 1/2).
+__global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restrict__ Z, long ldz, int npad,
+                                                          double* __restrict__ zunit, double* __restrict__ zqs) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= npad) return;
+    const int ncol = (row / TILE + 1) * TILE;
+    const double* zr = Z + (long)row * ldz;
+    double mx = 0.0;
+    for (int c = 2 * lane; c < ncol; c += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(zr + c);
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+        int ex = 0;
+        if (mx > 0.0 && isfinite(mx)) frexp(mx, &ex); else ex = 0;      // a non-finite factor is reported through info
+        const int e = ex + 1;
+        zunit[row] = scalbn(1.0, e - (8 * I8_SMAX - 1));
+        zqs[row] = scalbn(1.0, (8 * I8_SMAX - 1) - e);
+    }
+}
+
+// one CTA per lower 128 x 128 tile (I, J): 4 k-steps x 7 slices of 4 KB tile images.  Thread (r, h): row r,
+// k-steps 2h, 2h+1.
+__global__ void __launch_bounds__(256) i8_quantize_kernel(const double* __restrict__ Z, long ldz, const double* __restrict__ zqs,
+                                                          int8_t* __restrict__ Zq) {
+    const int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((long)I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const double* src = Z + ((long)I * TILE + r) * ldz + (long)J * TILE + h * 64;
+    const double qs = zqs[I * TILE + r];
+    constexpr long long BIAS = i8_digit_bias(I8_SMAX);
+    const size_t ks0 = (size_t)2 * I * (I + 1) + 4 * (size_t)J + 2 * h;
+#pragma unroll 1
+    for (int c16 = 0; c16 < 4; ++c16) {          // 16 consecutive k: one 16-byte row chunk of every slice image
+        long long q[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(src + c16 * 16 + j);
+            q[j] = __double2ll_rn(v.x * qs) + BIAS;
+            q[j + 1] = __double2ll_rn(v.y * qs) + BIAS;
+        }
+        int8_t* dst = Zq + (ks0 + (c16 >> 1)) * (size_t)(I8_SMAX * I8_ATILE_BYTES) + i8_tile_off(r, (c16 & 1) * 16);
+#define GP2D_I8_STORE(P)                                                                                          \
+        *reinterpret_cast<uint4*>(dst + (I8_SMAX - 1 - P) * I8_ATILE_BYTES) =                                     \
+            make_uint4(i8_digit_word<P>(q[0], q[1], q[2], q[3]), i8_digit_word<P>(q[4], q[5], q[6], q[7]),        \
+                       i8_digit_word<P>(q[8], q[9], q[10], q[11]), i8_digit_word<P>(q[12], q[13], q[14], q[15]));
+        GP2D_I8_STORE(0) GP2D_I8_STORE(1) GP2D_I8_STORE(2) GP2D_I8_STORE(3) GP2D_I8_STORE(4) GP2D_I8_STORE(5) GP2D_I8_STORE(6)
+#undef GP2D_I8_STORE
+    }
+}
+
+__global__ void i8_set_gate_kernel(int* gate, int s) { *gate = s; }
+
+size_t i8_zq_bytes(int npad) {
+    const size_t nb = (size_t)npad / TILE;
+    return 2 * nb * (nb + 1) * (size_t)(I8_SMAX * I8_ATILE_BYTES);
+}
+int i8_max_npad() { return I8_MAX_NPAD; }
+
+// zqs: npad doubles of scratch
+cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st) {
+    const int nb = npad / TILE;
+    i8_rowscale_kernel<<<(npad + 7) / 8, 256, 0, st>>>(Z, ldz, npad, zunit, zqs);
+    i8_quantize_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(Z, ldz, zqs, Zq);
+    return cudaGetLastError();
+}
+cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st) {
+    i8_set_gate_kernel<<<1, 1, 0, st>>>(gate, s);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// predict side
+// ---------------------------------------------------------------------------------------------------
+// Generator: thread (g, slot) owns grid point gp0 + g and the k-steps slot, slot + 8, ... (16 observations =
+// 32 rows of K* each).  Per k-step it forms 16 2x2 blocks, quantises the 48 distinct values and stores, for
+// each digit and each of its two columns, the two 16-byte row chunks of the slice image.
+template <int S, bool SAME_LEN, bool HAS_T>
+__device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const HelmPoint& gpt, double wg, int nvalid, int o0,
+                                                  const double* __restrict__ stage, double kscale, uint8_t* __restrict__ dst,
+                                                  int btile, double& m0, double& m1) {
+    constexpr long long BIAS = i8_digit_bias(S);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {                 // 8 observations = 16 consecutive k
+        unsigned wa[S][4], wb[S][4];               // column 2g / 2g+1, digit p, word w
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            long long qa[2], qb[2], qc[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ol = h * 8 + w * 2 + e;
+                const double* sp = stage + ol * 5;
+                const double d1 = sp[0] - gpt.a, d2 = sp[1] - gpt.b;
+                const double a = d1 * d1, b = d2 * d2, c = d1 * d2, r2 = a + b;
+                const double E = exp_neg(-0.5 * hp.s_df * r2);
+                const double F = SAME_LEN ? E : exp_neg(-0.5 * hp.s_cf * r2);
+                double wv = (o0 + ol) < nvalid ? wg : 0.0;
+                if (HAS_T) {
+                    const double dt = sp[2] - gpt.t;
+                    wv *= hp.tvar * exp_neg(-hp.thalf * dt * dt);
+                }
+                const double ee = hp.w_df * E, ff = hp.w_cf * F;
+                const double es = ee * hp.s_df, fs = ff * hp.s_cf;
+                double k11 = fma(-b, es, ee) + fma(-a, fs, ff);
+                double k22 = fma(-a, es, ee) + fma(-b, fs, ff);
+                double k12 = c * (es - fs);
+                k11 *= wv; k12 *= wv; k22 *= wv;
+                m0 = fma(k11, sp[3], fma(k12, sp[4], m0));
+                m1 = fma(k12, sp[3], fma(k22, sp[4], m1));
+                qa[e] = __double2ll_rn(k11 * kscale) + BIAS;
+                qb[e] = __double2ll_rn(k12 * kscale) + BIAS;
+                qc[e] = __double2ll_rn(k22 * kscale) + BIAS;
+            }
+            // rows k = 2o, 2o+1, 2o+2, 2o+3: column 2g holds (k11, k12) per observation, column 2g+1 (k12, k22)
+#define GP2D_I8_WORDS(P)                                                              \
+            if (P < S) {                                                              \
+                wa[P < S ? P : 0][w] = i8_digit_word<P>(qa[0], qb[0], qa[1], qb[1]);  \
+                wb[P < S ? P : 0][w] = i8_digit_word<P>(qb[0], qc[0], qb[1], qc[1]);  \
+            }
+            GP2D_I8_WORDS(0) GP2D_I8_WORDS(1) GP2D_I8_WORDS(2) GP2D_I8_WORDS(3) GP2D_I8_WORDS(4) GP2D_I8_WORDS(5) GP2D_I8_WORDS(6)
+#undef GP2D_I8_WORDS
+        }
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+            // slice index S - 1 - p (most significant first); columns 2g, 2g+1 are adjacent 16-byte rows of the image
+            uint4* d = reinterpret_cast<uint4*>(dst + (S - 1 - p) * btile + h * 128);
+            d[0] = make_uint4(wa[p][0], wa[p][1], wa[p][2], wa[p][3]);
+            d[1] = make_uint4(wb[p][0], wb[p][1], wb[p][2], wb[p][3]);
+        }
+    }
+}
+
+template <int S, int NC, bool SAME_LEN, bool HAS_T>
+__device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const HelmParams& hp, uint8_t* __restrict__ panel,
+                                                 double* __restrict__ stage, int gp0, int gtid, double& mu0, double& mu1) {
+    using C = I8Cfg<S, NC>;
+    const int g = gtid % C::NG, slot = gtid / C::NG;
+    const int gj = gp0 + g;
+    const double wg = gj < p.M ? 1.0 : 0.0;
+    const HelmPoint gpt = helm_point(hp, p.Xs, gj < p.M ? gj : 0);
+    const int nobs_pad = p.npad >> 1;
+    // the two image rows (columns 2g, 2g+1 of the tile) of this thread inside a slice tile
+    const int rowoff = ((2 * g) >> 3) * 256 + ((2 * g) & 7) * 16;
+    double m0 = 0.0, m1 = 0.0;
+    for (int ob = 0; ob < nobs_pad; ob += I8_OBS_BATCH) {
+        named_barrier(2, C::GT);                  // the previous batch has been read
+        if (gtid < I8_OBS_BATCH) {
+            const int o = ob + gtid;
+            const bool ov = o < p.N;
+            const HelmPoint q = helm_point(hp, p.X, ov ? o : 0);
+            stage[gtid * 5 + 0] = q.a;
+            stage[gtid * 5 + 1] = q.b;
+            stage[gtid * 5 + 2] = q.t;
+            stage[gtid * 5 + 3] = ov ? __ldg(p.alpha + 2 * o) : 0.0;
+            stage[gtid * 5 + 4] = ov ? __ldg(p.alpha + 2 * o + 1) : 0.0;
+        }
+        named_barrier(2, C::GT);
+        const int o0 = ob + slot * 16;
+        if (o0 < nobs_pad) {
+            const int ks = o0 >> 4;
+            i8_generate_kstep<S, SAME_LEN, HAS_T>(hp, gpt, wg, p.N, o0, stage + slot * 16 * 5, p.kscale,
+                                                  panel + (size_t)ks * (S * C::BTILE) + rowoff, C::BTILE, m0, m1);
+        }
+    }
+    mu0 = m0;
+    mu1 = m1;
+}
+
+template <int S, int NC>
+__global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(const __grid_constant__ PredictI8Args p) {
+    using C = I8Cfg<S, NC>;
+    if (*p.gate != S) return;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* ring = smem_raw;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + C::RING_BYTES);
+    unsigned long long* full = bars;
+    unsigned long long* empty = bars + C::STAGES;
+    unsigned long long* acc_full = bars + 2 * C::STAGES;
+    unsigned long long* acc_empty = acc_full + 1;
+    unsigned long long* panel_full = acc_full + 2;
+    unsigned long long* panel_empty = acc_full + 4;
+    unsigned* tslot = reinterpret_cast<unsigned*>(bars + C::NBARS);
+    double* sh_stage = reinterpret_cast<double*>(smem_raw + C::RING_BYTES + C::NBARS * 8 + 16);
+    double* sh_mu = sh_stage + 5 * I8_OBS_BATCH;          // [8][NG][2]
+    double* sh_red = sh_mu + 8 * C::NG * 2;               // [4][NC]
+    double* sh_par = sh_red + 4 * NC;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = p.npad / TILE;
+    uint8_t* panels = p.scratch + (size_t)blockIdx.x * 2 * p.panel_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(panel_full + b, 1); mbar_init(panel_empty + b, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < (int)(sizeof(HelmParams) / sizeof(double))) sh_par[tid] = reinterpret_cast<const double*>(&p.hp)[tid];
+    if (warp == 5) tmem_alloc(tslot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = *tslot;
+
+    if (warp < 4) {
+        // ------------------------------ epilogue ------------------------------------------------
+        unsigned ph = 0;
+        const double cs = p.cscale;
+        for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x) {
+            double colsum[NC / 16];
+#pragma unroll
+            for (int c = 0; c < NC / 16; ++c) colsum[c] = 0.0;
+            for (int rb = 0; rb < nb; ++rb) {
+                const double rs = __ldg(p.zunit + rb * TILE + tid) * cs;
+                mbar_wait(acc_full, ph);
+                ph ^= 1u;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < NC / 16; ++c) {
+                    double t[16];
+                    int r[16];
+                    const unsigned ta = tbase + ((unsigned)(warp * 32) << 16) + c * 16;
+                    tmem_ld16(ta, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) t[j] = (double)r[j];
+#pragma unroll
+                    for (int d = 1; d < S; ++d) {
+                        tmem_ld16(ta + d * NC, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) t[j] = fma(t[j], 256.0, (double)r[j]);
+                    }
+                    if (c == NC / 16 - 1) {       // the accumulators have been read: the next row block may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const double v = t[j] * rs; t[j] = v * v; }
+                    // sum over the 32 rows of the warp, 16 columns at once: halve the columns with each exchange
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1) {
+                        const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+                        for (int j = 0; j < w; ++j) {
+                            const double keep = up ? t[j + w] : t[j], send = up ? t[j] : t[j + w];
+                            t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                        }
+                    }
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+                    colsum[c] += t[0];            // column c 16 + (lane >> 1)
+                }
+            }
+            // columns of the item: sum of the four warps in fixed order
+            if (!(lane & 1)) {
+#pragma unroll
+                for (int c = 0; c < NC / 16; ++c) sh_red[warp * NC + c * 16 + (lane >> 1)] = colsum[c];
+            }
+            named_barrier(1, 128);
+            if (tid < NC) {
+                const int pj = tid >> 1, cc = tid & 1;
+                const int j = item * C::NG + pj;
+                if (j < p.M) {
+                    const double ss = ((sh_red[tid] + sh_red[NC + tid]) + sh_red[2 * NC + tid]) + sh_red[3 * NC + tid];
+                    double v = (cc ? p.kss1 : p.kss) - ss;
+                    v = v < 0.0 ? 0.0 : v;
+                    p.var[(long)cc * p.out_stride + j] = v + p.var_add;
+                }
+            }
+            named_barrier(1, 128);
+        }
+    } else if (warp == 4) {
+        // ------------------------------ producer --------------------------------------------------
+        if (lane == 0) {
+            int rs = 0, it = 0;
+            unsigned rph = 0;
+            long fills = 0;
+            for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
+                const int b = it & 1;
+                mbar_wait(panel_full + b, (unsigned)(it >> 1) & 1u);
+                fence_proxy_async();
+                const uint8_t* pb = panels + (size_t)b * p.panel_bytes;
+                for (int rb = 0; rb < nb; ++rb) {
+                    const int8_t* za = p.Zq + (size_t)2 * rb * (rb + 1) * (size_t)(I8_SMAX * I8_ATILE_BYTES);
+                    const int nks = 4 * (rb + 1);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        if (fills >= C::STAGES) mbar_wait(empty + rs, rph ^ 1u);
+                        uint8_t* st = ring + rs * C::STAGE_BYTES;
+                        mbar_arrive_expect_tx(full + rs, C::STAGE_BYTES);
+                        bulk_g2s(st, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES), S * I8_ATILE_BYTES, full + rs);
+                        bulk_g2s(st + S * I8_ATILE_BYTES, pb + (size_t)ks * (S * C::BTILE), S * C::BTILE, full + rs);
+                        ++fills;
+                        if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0) {
+            constexpr unsigned IDESC = i8_idesc(128, NC);
+            const unsigned ring_lo = i8_desc_lo(smem_u32(ring));
+            int rs = 0, it = 0;
+            unsigned rph = 0;
+            long blocks = 0;
+            for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
+                for (int rb = 0; rb < nb; ++rb, ++blocks) {
+                    if (blocks > 0) {
+                        mbar_wait(acc_empty, (unsigned)(blocks - 1) & 1u);
+                        tc_fence_after();
+                    }
+                    const int nks = 4 * (rb + 1);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        mbar_wait(full + rs, rph);
+                        tc_fence_after();
+                        const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
+                        const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
+                        const unsigned acc0 = ks > 0 ? 1u : 0u;
+#pragma unroll
+                        for (int d = 0; d < S; ++d)
+#pragma unroll
+                            for (int i = 0; i <= d; ++i)
+                                umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
+                                           i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
+                        umma_commit(empty + rs);
+                        if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+                    }
+                    umma_commit(acc_full);
+                }
+                mbar_arrive(panel_empty + (it & 1));      // every copy out of this item's panel has landed
+            }
+        }
+    } else {
+        // ------------------------------ generators ------------------------------------------------
+        const int gtid = tid - 192;
+        const HelmParams& hp = *reinterpret_cast<const HelmParams*>(sh_par);
+        int it = 0;
+        for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
+            const int b = it & 1;
+            if (it >= 2 && gtid == 0) mbar_wait(panel_empty + b, (unsigned)((it >> 1) - 1) & 1u);
+            uint8_t* panel = panels + (size_t)b * p.panel_bytes;
+            double mu0 = 0.0, mu1 = 0.0;
+            const int gp0 = item * C::NG;
+            if (hp.has_t) {
+                if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+            } else {
+                if (hp.same_len) i8_generate_item<S, NC, true, false>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, false>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+            }
+            fence_proxy_async();                  // the panel is read back by bulk (async-proxy) copies
+            const int g = gtid % C::NG, slot = gtid / C::NG;
+            sh_mu[(slot * C::NG + g) * 2 + 0] = mu0;
+            sh_mu[(slot * C::NG + g) * 2 + 1] = mu1;
+            named_barrier(2, C::GT);
+            if (gtid == 0) mbar_arrive(panel_full + b);
+            if (gtid < NC) {
+                const int pj = gtid >> 1, cc = gtid & 1;
+                const int j = gp0 + pj;
+                if (j < p.M) {
+                    double m = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) m += sh_mu[(s * C::NG + pj) * 2 + cc];
+                    p.mean[(long)cc * p.out_stride + j] = m;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tbase, C::TMEM_COLS);
+}
+
+template <int S, int NC>
+static size_t i8_panel_bytes(int npad) {
+    // + 5 KB: consecutive panels must not sit at the same offset modulo a power of two (see predict.cu)
+    return (size_t)(npad / I8_KSTEP) * (S * I8Cfg<S, NC>::BTILE) + 5120;
+}
+size_t predict_i8_scratch_bytes(int npad) {
+    const size_t a = i8_panel_bytes<6, 80>(npad), b = i8_panel_bytes<7, 64>(npad);
+    return (size_t)predict_max_ctas() * 2 * (a > b ? a : b);
+}
+
+template <int S, int NC>
+static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scratch, size_t scratch_bytes, cudaStream_t st) {
+    using C = I8Cfg<S, NC>;
+    static PerDeviceOnce once;
+    const int slot = once.pending();
+    if (slot >= 0) {
+        cudaError_t e = cudaFuncSetAttribute(predict_i8_kernel<S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        once.done[slot] = true;
+    }
+    // |K*| <= kmax: scale so that |k| kscale <= 2^(8 S - 2) (top digit within [-64, 64])
+    int ex = 0;
+    frexp(kmax, &ex);
+    const int e = ex + 1;
+    a.kscale = scalbn(1.0, (8 * S - 1) - e);
+    a.cscale = scalbn(1.0, e - (8 * S - 1)) * scalbn(1.0, 8 * (S - 1)) * scalbn(1.0, 8 * (I8_SMAX - S));
+    a.ntiles = (a.M + C::NG - 1) / C::NG;
+    a.panel_bytes = i8_panel_bytes<S, NC>(a.npad);
+    a.scratch = scratch;
+    long grid = a.ntiles;
+    if (grid > predict_max_ctas()) grid = predict_max_ctas();
+    const long panels = (long)(scratch_bytes / (2 * a.panel_bytes));
+    if (grid > panels) grid = panels;
+    if (grid <= 0) return cudaErrorInvalidValue;
+    const long per = (a.ntiles + grid - 1) / grid;
+    grid = (a.ntiles + per - 1) / per;
+    predict_i8_kernel<S, NC><<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    return cudaGetLastError();
+}
+
+// Launches both slice-count variants; each returns at once unless *gate names it (the choice was made at fit
+// time, on the device side of the stream, so no host synchronisation is needed here).
+cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* gate, int npad, const double* alpha_int,
+                             const double* X, int N, const HelmParams& hp, const double* Xs, int M, long out_stride,
+                             double var_add, double* mean, double* var, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                             int only_s) {
+    if (M <= 0) return cudaSuccess;
+    PredictI8Args a{};
+    a.Zq = Zq; a.zunit = zunit; a.gate = gate; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
+    a.Xs = Xs; a.M = M; a.out_stride = out_stride;
+    a.kss = a.kss1 = hp.tvar * (hp.w_df + hp.w_cf);
+    a.var_add = var_add; a.mean = mean; a.var = var;
+    // every entry of the 2x2 block is bounded by the prior variance k** (helmholtz.cuh)
+    const double kmax = a.kss;
+    cudaError_t e = cudaSuccess;
+    if (only_s == 0 || only_s == 6) e = predict_i8_launch<6, 80>(a, kmax, (uint8_t*)scratch, scratch_bytes, st);
+    if (e != cudaSuccess) return e;
+    if (only_s == 0 || only_s == 7) e = predict_i8_launch<7, 64>(a, kmax, (uint8_t*)scratch, scratch_bytes, st);
+    return e;
+}
+
+}  // namespace gp2d

@@ -9,11 +9,18 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ._lib import lib, check, Gp2dError
+from ._lib import lib, check, Gp2dError, GP2D_OPT_PREDICT_I8
 
-__all__ = ["LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
+__all__ = ["set_predict_i8", "LinAlgError", "as_dev", "kernel_K", "kernel_Kdiag", "kernel_grad_sums", "potrf",
            "spd_inverse", "matmul", "HelmholtzGP", "HelmholtzBatch", "krig_snapshots", "fit_predict_host", "rbf_K",
            "rbf_grad_sums", "ScalarGP", "st_K", "st_grad_sums", "SpaceTimeGP"]
+
+
+def set_predict_i8(mode=0):
+    """Which kernel the predictive pass of the Helmholtz families uses (GP2D_OPT_PREDICT_I8, include/gp2d.h; per
+    host thread; set it BEFORE the fit): 0 = automatic (int8-sliced tcgen05 kernel with 6 or 7 slices chosen from the
+    conditioning bound, fp64 tensor-pipe kernel beyond it), 1 = fp64 kernel only, 6 / 7 = that slice count."""
+    check(lib.gp2d_set_option(GP2D_OPT_PREDICT_I8, float(mode)), "gp2d_set_option")
 
 
 class LinAlgError(np.linalg.LinAlgError):

@@ -252,6 +252,21 @@ int gp2d_hsum_predict(const void* fit_ws, int N, int ldx, int Q, const int* type
 int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, const int* type, const double* params,
                        double noise, double jitter, void* ws, size_t ws_bytes, double* out, int* info, void* stream);
 
+/* ---- options (per host thread) ----------------------------------------------------------- */
+
+/* gp2d_set_option(key, value): 0, -1 (unknown key) or -2 (bad value).  Options are thread-local: they apply
+ * to the calls the setting thread makes afterwards and never couple two callers.
+ * GP2D_OPT_PREDICT_I8 -- the predictive pass of the Helmholtz families (gp2d_predict, gp2d_st_predict,
+ *   gp2d_fit_predict_host) has two kernels: the fp64 tensor-pipe kernel and an int8-sliced tcgen05 kernel
+ *   (3-4x faster; exact integer products of base-256 digit slices, deterministic; agrees with the fp64 kernel
+ *   to ~2e-10 relative on the variance with 6 slices, ~1e-12 with 7).  0 (default): gp2d_fit picks 6 or 7
+ *   slices from the conditioning bound n k** / (noise + jitter) -- 6 up to 5e4, 7 up to the robust threshold
+ *   1e7, the fp64 kernel beyond, for N > 10880 and for batched fits; 1: fp64 kernel only; 6 / 7: that slice
+ *   count whenever N <= 10880.  The choice is made by gp2d_fit (it prepares the slices) and honoured by the
+ *   predict calls on that workspace; set the option before the fit. */
+#define GP2D_OPT_PREDICT_I8 1
+int gp2d_set_option(int key, double value);
+
 /* ---- host-buffer convenience (allocates, copies, synchronises) -------------------- */
 
 /* Whole fit + predict with HOST pointers (pageable is fine) on the current device, legacy default
