@@ -91,19 +91,20 @@ int refine_steps_for(double kss, long n_scalar, double diag_add) {
 }
 
 // int8-sliced predictive kernel (predict_i8.cu).  Its error is that of dropping the digit products beyond
-// the S-th: relative to the fp64 path ~2e-10 (S = 6) / ~1e-12 (S = 7) on the variance at a conditioning bound
-// of 1e4 and growing in proportion to the bound (tools/ozaki_emulate.py), so the slice count follows the same
-// bound the robust switch uses, and past the robust threshold the fp64 kernel stays the only path.
+// the S-th.  Measured against an extended-precision product (tools/ozaki_emulate.py) the relative error of the
+// variance follows the prior-to-noise ratio r = k** / (noise + jitter), not the matrix size: S = 6 gives
+// 2e-10 at r = 4 (BASELINE configurations), 3e-9 at r = 20-40, 8e-8 at r = 400; S = 7 gives 1e-12, 1.5e-11 and
+// 3e-10; from n = 2000 to n = 8000 both grow by 1.6.  With m = r sqrt(n / 4000): 6 slices up to m = 20, 7 up to
+// m = 2000 (a factor 3 inside the 1e-8 parity bar), the fp64 kernel beyond, and always in the robust mode.
 // Per host thread: 0 = automatic, 1 = off, 6 / 7 = that slice count whenever the layout carries the slices.
 thread_local int g_i8_mode = 0;
-constexpr double I8_BOUND_S6 = 5e4;
+constexpr double I8_M_S6 = 20.0, I8_M_S7 = 2000.0;
 int i8_slices_for(double kss, long n_scalar, double diag_add, const FitLayout& L) {
     if (!L.i8 || g_i8_mode == 1) return 0;
     if (g_i8_mode == 6 || g_i8_mode == 7) return g_i8_mode;
-    if (!(diag_add > 0.0)) return 0;
-    const double bound = kss * (double)n_scalar / diag_add;
-    if (bound <= I8_BOUND_S6) return 6;
-    return bound <= g_robust_cond ? 7 : 0;
+    if (!(diag_add > 0.0) || refine_steps_for(kss, n_scalar, diag_add)) return 0;
+    const double m = kss / diag_add * sqrt((double)n_scalar / 4000.0);
+    return m <= I8_M_S6 ? 6 : m <= I8_M_S7 ? 7 : 0;
 }
 
 // factor + inverse of the padded covariance in ws (A destroyed or replaced by L), robust when asked
@@ -558,9 +559,16 @@ cudaError_t fit_core_batched(const double* X, long x_stride, int N, const double
     if (e != cudaSuccess) return e;
     e = pack_lower_tiles(Z, L.npad, L.npad, at<double>(ws0, L.off_Zt), st, nb, bs);
     if (e != cudaSuccess) return e;
-    for (int b = 0; b < nb && e == cudaSuccess; ++b)      // batched fits keep the fp64 predictive path
-        e = i8_set_gate(at<int>(ws0, L.off_info + GATE_OFF) + 2 * (long)b * bs, 0, st);
-    if (e != cudaSuccess) return e;
+    {   // digit slices for the int8 predictive kernel, exactly as fit_core prepares them
+        bool any = false;
+        for (int b = 0; b < nb; ++b) any = any || i8_slices_for(pr[b].hp.w_df + pr[b].hp.w_cf, 2L * N, pr[b].diag_add, L) != 0;
+        if (any) e = i8_quantize_lower(Z, L.npad, L.npad, at<double>(ws0, L.off_zunit), at<double>(ws0, L.off_r),
+                                       at<int8_t>(ws0, L.off_Zq), st, nb, bs);
+        for (int b = 0; b < nb && e == cudaSuccess; ++b)
+            e = i8_set_gate(at<int>(ws0, L.off_info + GATE_OFF) + 2 * (long)b * bs,
+                            i8_slices_for(pr[b].hp.w_df + pr[b].hp.w_cf, 2L * N, pr[b].diag_add, L), st);
+        if (e != cudaSuccess) return e;
+    }
     return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws0, L.off_yint), at<double>(ws0, L.off_w),
                            at<double>(ws0, L.off_alpha), at<double>(ws0, L.off_partial), at<double>(ws0, L.off_logdiag),
                            at<double>(ws0, L.off_scal), st, nb, y_stride, bs);

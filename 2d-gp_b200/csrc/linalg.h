@@ -109,7 +109,8 @@ void set_predict_split(int s);          // bring-up override: 1, 2, 4, 8 (0 = he
 // zqs is npad doubles of scratch.  *gate holds the slice count chosen for this fit (6, 7, or 0 = fp64 path only).
 size_t i8_zq_bytes(int npad);
 int i8_max_npad();
-cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st);
+cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st,
+                              int batch = 1, long bstride = 0);
 cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st);
 size_t predict_i8_scratch_bytes(int npad);
 // launches the kernel of every slice count (only_s = 0) or of one; a kernel whose count is not *gate returns at once

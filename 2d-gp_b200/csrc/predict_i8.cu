@@ -78,7 +78,10 @@ struct PredictI8Args {
 // one warp per row: power-of-two scale from max |Z[r][0 .. (r / 128 + 1) 128)| (upper part of the diagonal
 // tile is exactly zero).  zunit[r] = 2^(e - 55), zqs[r] = 2^(55 - e) with max / 2^e in [1/4, 1/2).
 __global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restrict__ Z, long ldz, int npad,
-                                                          double* __restrict__ zunit, double* __restrict__ zqs) {
+                                                          double* __restrict__ zunit, double* __restrict__ zqs, long bstride) {
+    Z += (long)blockIdx.y * bstride;
+    zunit += (long)blockIdx.y * bstride;
+    zqs += (long)blockIdx.y * bstride;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= npad) return;
     const int ncol = (row / TILE + 1) * TILE;
@@ -102,7 +105,10 @@ __global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restri
 // one CTA per lower 128 x 128 tile (I, J): 4 k-steps x 7 slices of 4 KB tile images.  Thread (r, h): row r,
 // k-steps 2h, 2h+1.
 __global__ void __launch_bounds__(256) i8_quantize_kernel(const double* __restrict__ Z, long ldz, const double* __restrict__ zqs,
-                                                          int8_t* __restrict__ Zq) {
+                                                          int8_t* __restrict__ Zq, long bstride) {
+    Z += (long)blockIdx.y * bstride;
+    zqs += (long)blockIdx.y * bstride;
+    Zq += (long)blockIdx.y * bstride * (long)sizeof(double);
     const int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
@@ -140,11 +146,13 @@ size_t i8_zq_bytes(int npad) {
 }
 int i8_max_npad() { return I8_MAX_NPAD; }
 
-// zqs: npad doubles of scratch
-cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st) {
+// zqs: npad doubles of scratch; batch > 1: problem b at every pointer + b bstride doubles
+cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit, double* zqs, int8_t* Zq, cudaStream_t st,
+                              int batch, long bstride) {
     const int nb = npad / TILE;
-    i8_rowscale_kernel<<<(npad + 7) / 8, 256, 0, st>>>(Z, ldz, npad, zunit, zqs);
-    i8_quantize_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(Z, ldz, zqs, Zq);
+    const long bs = batch > 1 ? bstride : 0;
+    i8_rowscale_kernel<<<dim3((npad + 7) / 8, batch), 256, 0, st>>>(Z, ldz, npad, zunit, zqs, bs);
+    i8_quantize_kernel<<<dim3(nb * (nb + 1) / 2, batch), 256, 0, st>>>(Z, ldz, zqs, Zq, bs);
     return cudaGetLastError();
 }
 cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st) {
