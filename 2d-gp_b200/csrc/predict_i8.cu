@@ -31,8 +31,12 @@ namespace gp2d {
 
 constexpr int I8_SMAX = 7;                           // digits stored per entry of Zq
 constexpr int I8_OBS_BATCH = 128;                    // observations staged in shared memory at a time
-// worst-case |accumulator| of d = S - 1 over k rows: k (2 64 128 + (S - 2) 128 128) < 2^31
-constexpr int I8_MAX_NPAD = 21760;
+// An int32 accumulator d sums (d + 1) digit products over k: at most k (2 64 128 + (d - 1) 128 128) for d = S - 1
+// (top digits are within [-64, 64]), which passes 2^31 beyond k = 21845 (S = 7).  Row blocks that reach further are
+// accumulated in segments of I8_KSEG k-steps (16384 rows: 1.6e9 at worst); the partial fp64 sums of the earlier
+// segments wait in a small per-CTA global buffer.
+constexpr int I8_KSEG = 512;
+constexpr int I8_MAX_NPAD = 65536;
 
 template <int S, int NC>
 struct I8Cfg {
@@ -66,8 +70,8 @@ struct PredictI8Args {
     double kscale;                // K* entries are quantised as rint(k kscale), |k kscale| <= 2^(8 S - 2)
     double cscale;                // ku 256^(S-1) 256^(I8_SMAX-S): v = Horner zunit[r] cscale
     double* mean; double* var;
-    uint8_t* scratch;             // gridDim.x x 2 panels
-    size_t panel_bytes;
+    uint8_t* scratch;             // per CTA: 2 panels, then [128][NC] doubles (segment partial sums)
+    size_t panel_bytes, cta_bytes;
     int ntiles;
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
 };
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = p.npad / TILE;
-    uint8_t* panels = p.scratch + (size_t)blockIdx.x * 2 * p.panel_bytes;
+    uint8_t* panels = p.scratch + (size_t)blockIdx.x * p.cta_bytes;
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -302,46 +306,65 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             double colsum[NC / 16];
 #pragma unroll
             for (int c = 0; c < NC / 16; ++c) colsum[c] = 0.0;
+            double* vpart = reinterpret_cast<double*>(panels + 2 * p.panel_bytes) + (size_t)tid * NC;
             for (int rb = 0; rb < nb; ++rb) {
                 const double rs = __ldg(p.zunit + rb * TILE + tid) * cs;
-                mbar_wait(acc_full, ph);
-                ph ^= 1u;
-                tc_fence_after();
+                const int nseg = (4 * (rb + 1) + I8_KSEG - 1) / I8_KSEG;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    mbar_wait(acc_full, ph);
+                    ph ^= 1u;
+                    tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < NC / 16; ++c) {
-                    double t[16];
-                    int r[16];
-                    const unsigned ta = tbase + ((unsigned)(warp * 32) << 16) + c * 16;
-                    tmem_ld16(ta, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) t[j] = (double)r[j];
-#pragma unroll
-                    for (int d = 1; d < S; ++d) {
-                        tmem_ld16(ta + d * NC, r);
+                    for (int c = 0; c < NC / 16; ++c) {
+                        double t[16];
+                        int r[16];
+                        const unsigned ta = tbase + ((unsigned)(warp * 32) << 16) + c * 16;
+                        tmem_ld16(ta, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) t[j] = fma(t[j], 256.0, (double)r[j]);
-                    }
-                    if (c == NC / 16 - 1) {       // the accumulators have been read: the next row block may start
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty);
-                    }
+                        for (int j = 0; j < 16; ++j) t[j] = (double)r[j];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { const double v = t[j] * rs; t[j] = v * v; }
-                    // sum over the 32 rows of the warp, 16 columns at once: halve the columns with each exchange
+                        for (int d = 1; d < S; ++d) {
+                            tmem_ld16(ta + d * NC, r);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int w = 8; w >= 1; w >>= 1) {
-                        const bool up = (lane & (2 * w)) != 0;
-#pragma unroll
-                        for (int j = 0; j < w; ++j) {
-                            const double keep = up ? t[j + w] : t[j], send = up ? t[j] : t[j + w];
-                            t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                            for (int j = 0; j < 16; ++j) t[j] = fma(t[j], 256.0, (double)r[j]);
                         }
+                        if (c == NC / 16 - 1) {       // the accumulators have been read: the next segment may start
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty);
+                        }
+                        if (nseg > 1) {               // long rows: Horner sums of the segments are added in fp64
+                            double* vp = vpart + c * 16;
+                            if (seg > 0) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) {
+                                    const double2 v = *reinterpret_cast<const double2*>(vp + j);
+                                    t[j] += v.x; t[j + 1] += v.y;
+                                }
+                            }
+                            if (seg < nseg - 1) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(vp + j) = make_double2(t[j], t[j + 1]);
+                                continue;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { const double v = t[j] * rs; t[j] = v * v; }
+                        // sum over the 32 rows of the warp, 16 columns at once: halve the columns with each exchange
+#pragma unroll
+                        for (int w = 8; w >= 1; w >>= 1) {
+                            const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+                            for (int j = 0; j < w; ++j) {
+                                const double keep = up ? t[j + w] : t[j], send = up ? t[j] : t[j + w];
+                                t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                            }
+                        }
+                        t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+                        colsum[c] += t[0];            // column c 16 + (lane >> 1)
                     }
-                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
-                    colsum[c] += t[0];            // column c 16 + (lane >> 1)
                 }
             }
             // columns of the item: sum of the four warps in fixed order
@@ -397,28 +420,31 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             unsigned rph = 0;
             long blocks = 0;
             for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
-                for (int rb = 0; rb < nb; ++rb, ++blocks) {
-                    if (blocks > 0) {
-                        mbar_wait(acc_empty, (unsigned)(blocks - 1) & 1u);
-                        tc_fence_after();
-                    }
+                for (int rb = 0; rb < nb; ++rb) {
                     const int nks = 4 * (rb + 1);
-                    for (int ks = 0; ks < nks; ++ks) {
-                        mbar_wait(full + rs, rph);
-                        tc_fence_after();
-                        const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
-                        const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
-                        const unsigned acc0 = ks > 0 ? 1u : 0u;
+                    for (int ks0 = 0; ks0 < nks; ks0 += I8_KSEG, ++blocks) {      // one accumulation segment
+                        if (blocks > 0) {
+                            mbar_wait(acc_empty, (unsigned)(blocks - 1) & 1u);
+                            tc_fence_after();
+                        }
+                        const int ks1 = ks0 + I8_KSEG < nks ? ks0 + I8_KSEG : nks;
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            mbar_wait(full + rs, rph);
+                            tc_fence_after();
+                            const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
+                            const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
+                            const unsigned acc0 = ks > ks0 ? 1u : 0u;
 #pragma unroll
-                        for (int d = 0; d < S; ++d)
+                            for (int d = 0; d < S; ++d)
 #pragma unroll
-                            for (int i = 0; i <= d; ++i)
-                                umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
-                                           i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
-                        umma_commit(empty + rs);
-                        if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+                                for (int i = 0; i <= d; ++i)
+                                    umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
+                                               i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
+                            umma_commit(empty + rs);
+                            if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+                        }
+                        umma_commit(acc_full);
                     }
-                    umma_commit(acc_full);
                 }
                 mbar_arrive(panel_empty + (it & 1));      // every copy out of this item's panel has landed
             }
@@ -469,9 +495,11 @@ static size_t i8_panel_bytes(int npad) {
     // + 5 KB: consecutive panels must not sit at the same offset modulo a power of two (see predict.cu)
     return (size_t)(npad / I8_KSTEP) * (S * I8Cfg<S, NC>::BTILE) + 5120;
 }
+template <int S, int NC>
+static size_t i8_cta_bytes(int npad) { return 2 * i8_panel_bytes<S, NC>(npad) + (size_t)TILE * NC * sizeof(double); }
 size_t predict_i8_scratch_bytes(int npad) {
-    const size_t a = i8_panel_bytes<6, 80>(npad), b = i8_panel_bytes<7, 64>(npad);
-    return (size_t)predict_max_ctas() * 2 * (a > b ? a : b);
+    const size_t a = i8_cta_bytes<6, 80>(npad), b = i8_cta_bytes<7, 64>(npad);
+    return (size_t)predict_max_ctas() * (a > b ? a : b);
 }
 
 template <int S, int NC>
@@ -492,10 +520,11 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     a.cscale = scalbn(1.0, e - (8 * S - 1)) * scalbn(1.0, 8 * (S - 1)) * scalbn(1.0, 8 * (I8_SMAX - S));
     a.ntiles = (a.M + C::NG - 1) / C::NG;
     a.panel_bytes = i8_panel_bytes<S, NC>(a.npad);
+    a.cta_bytes = i8_cta_bytes<S, NC>(a.npad);
     a.scratch = scratch;
     long grid = a.ntiles;
     if (grid > predict_max_ctas()) grid = predict_max_ctas();
-    const long panels = (long)(scratch_bytes / (2 * a.panel_bytes));
+    const long panels = (long)(scratch_bytes / a.cta_bytes);
     if (grid > panels) grid = panels;
     if (grid <= 0) return cudaErrorInvalidValue;
     const long per = (a.ntiles + grid - 1) / grid;

@@ -262,7 +262,7 @@ int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, 
  *   to ~2e-10 relative on the variance with 6 slices, ~1e-12 with 7, at the prior-to-noise ratio 4 of the
  *   reference configurations).  0 (default): gp2d_fit picks the slice count from m = k** / (noise + jitter) *
  *   sqrt(n / 4000) -- 6 up to m = 20, 7 up to m = 2000, the fp64 kernel beyond, in the robust (ill-conditioned)
- *   mode, for N > 10880 and for batched fits; 1: fp64 kernel only; 6 / 7: that slice count whenever N <= 10880.
+ *   mode and for N > 32768; 1: fp64 kernel only; 6 / 7: that slice count whenever N <= 32768.
  *   The choice is made by gp2d_fit (it prepares the slices) and honoured by the predict calls on that workspace;
  *   set the option before the fit. */
 #define GP2D_OPT_PREDICT_I8 1
