@@ -1258,6 +1258,7 @@ int gp2d_dbg_set_robust_cond(double c) { g_robust_cond = c; return 0; }
 int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; }
 
 int gp2d_dbg_set_predict_split(int s) { set_predict_split(s); return s; }
+int gp2d_dbg_set_i8(int v) { set_i8_debug(v); return v; }
 
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,

@@ -74,6 +74,7 @@ struct PredictI8Args {
     size_t panel_bytes, cta_bytes;
     int ntiles;
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
+    int dbg;                      // bring-up timing experiments (wrong results): 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -314,21 +315,44 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     mbar_wait(acc_full, ph);
                     ph ^= 1u;
                     tc_fence_after();
+                    if (p.dbg & 2) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty);
+                        continue;
+                    }
 #pragma unroll
                     for (int c = 0; c < NC / 16; ++c) {
+                        // Horner in 256 over the S accumulators, in 64-bit integers: the first NHI digits and the last
+                        // NLO digits each fit 56 bits; two conversions and one fma give the fp64 value (one rounding)
+                        constexpr int NHI = (S + 1) / 2, NLO = S - NHI;
                         double t[16];
-                        int r[16];
                         const unsigned ta = tbase + ((unsigned)(warp * 32) << 16) + c * 16;
-                        tmem_ld16(ta, r);
-                        tmem_ld_wait();
+                        {
+                            int r[NHI][16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) t[j] = (double)r[j];
-#pragma unroll
-                        for (int d = 1; d < S; ++d) {
-                            tmem_ld16(ta + d * NC, r);
+                            for (int d = 0; d < NHI; ++d) tmem_ld16(ta + d * NC, r[d]);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) t[j] = fma(t[j], 256.0, (double)r[j]);
+                            for (int j = 0; j < 16; ++j) {
+                                long long h = r[0][j];
+#pragma unroll
+                                for (int d = 1; d < NHI; ++d) h = h * 256 + r[d][j];
+                                t[j] = (double)h;
+                            }
+                        }
+                        {
+                            int r[NLO][16];
+#pragma unroll
+                            for (int d = 0; d < NLO; ++d) tmem_ld16(ta + (NHI + d) * NC, r[d]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                long long l = r[0][j];
+#pragma unroll
+                                for (int d = 1; d < NLO; ++d) l = l * 256 + r[d][j];
+                                t[j] = fma(t[j], (double)(1ll << (8 * NLO)), (double)l);
+                            }
                         }
                         if (c == NC / 16 - 1) {       // the accumulators have been read: the next segment may start
                             tc_fence_before();
@@ -395,7 +419,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 const int b = it & 1;
                 mbar_wait(panel_full + b, (unsigned)(it >> 1) & 1u);
                 fence_proxy_async();
-                const uint8_t* pb = panels + (size_t)b * p.panel_bytes;
+                const uint8_t* pb = (p.dbg & 1) ? p.scratch : panels + (size_t)b * p.panel_bytes;
                 for (int rb = 0; rb < nb; ++rb) {
                     const int8_t* za = p.Zq + (size_t)2 * rb * (rb + 1) * (size_t)(I8_SMAX * I8_ATILE_BYTES);
                     const int nks = 4 * (rb + 1);
@@ -413,7 +437,9 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
         }
     } else if (warp == 5) {
         // ------------------------------ MMA issuer ------------------------------------------------
-        if (lane == 0) {
+        // The whole warp walks the loops (so every descriptor is warp-uniform and lives in uniform registers);
+        // one elected lane issues the MMAs and the commits.
+        {
             constexpr unsigned IDESC = i8_idesc(128, NC);
             const unsigned ring_lo = i8_desc_lo(smem_u32(ring));
             int rs = 0, it = 0;
@@ -434,19 +460,23 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                             const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
                             const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
                             const unsigned acc0 = ks > ks0 ? 1u : 0u;
+                            if (elect_one_sync()) {
 #pragma unroll
-                            for (int d = 0; d < S; ++d)
+                                for (int d = 0; d < S; ++d)
 #pragma unroll
-                                for (int i = 0; i <= d; ++i)
-                                    umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
-                                               i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
-                            umma_commit(empty + rs);
+                                    for (int i = 0; i <= d; ++i)
+                                        umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
+                                                   i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
+                                umma_commit(empty + rs);
+                            }
+                            __syncwarp();
                             if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
                         }
-                        umma_commit(acc_full);
+                        if (elect_one_sync()) umma_commit(acc_full);
+                        __syncwarp();
                     }
                 }
-                mbar_arrive(panel_empty + (it & 1));      // every copy out of this item's panel has landed
+                if (lane == 0) mbar_arrive(panel_empty + (it & 1));      // every copy out of this item's panel has landed
             }
         }
     } else {
@@ -460,7 +490,9 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             uint8_t* panel = panels + (size_t)b * p.panel_bytes;
             double mu0 = 0.0, mu1 = 0.0;
             const int gp0 = item * C::NG;
-            if (hp.has_t) {
+            if (p.dbg & 4) {
+                named_barrier(2, C::GT);
+            } else if (hp.has_t) {
                 if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
                 else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
             } else {
@@ -533,6 +565,9 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     return cudaGetLastError();
 }
 
+static thread_local int g_i8_dbg = 0;
+void set_i8_debug(int v) { g_i8_dbg = v; }
+
 // Launches both slice-count variants; each returns at once unless *gate names it (the choice was made at fit
 // time, on the device side of the stream, so no host synchronisation is needed here).
 cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* gate, int npad, const double* alpha_int,
@@ -545,6 +580,7 @@ cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* g
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
     a.kss = a.kss1 = hp.tvar * (hp.w_df + hp.w_cf);
     a.var_add = var_add; a.mean = mean; a.var = var;
+    a.dbg = g_i8_dbg;
     // every entry of the 2x2 block is bounded by the prior variance k** (helmholtz.cuh)
     const double kmax = a.kss;
     cudaError_t e = cudaSuccess;

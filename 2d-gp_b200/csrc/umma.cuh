@@ -65,6 +65,13 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one_sync() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
 
 // Balanced base-256 digits.  q is a signed fixed-point integer of at most 8 S - 2 bits; adding 0x80 to each

@@ -13,6 +13,9 @@ mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 side = int(sys.argv[3]) if len(sys.argv) > 3 else 320
 gp.set_predict_i8(mode)
+if len(sys.argv) > 4:
+    from gp2d_b200._lib import lib
+    lib.gp2d_dbg_set_i8(int(sys.argv[4]))
 X, y = syn.drifter_snapshot(N, config_id=2)
 Xs = gp.as_dev(syn.prediction_grid(X, side, side))
 m = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
