@@ -47,9 +47,15 @@ THETA = (1.3, 3.1, 0.2)
 NOISE = 0.05
 CPU_GRID_FRACTION = 0.10          # share of the grid a bounded CPU step predicts (all of it for <= 3 steps)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# ncu capture named in roofline.traffic_source
+# ncu captures named in roofline.traffic_source (int8-sliced kernel) / roofline_fp64_kernel.traffic_source
+NCU_PREDICT_I8_DRAM_BYTES = 76.145773e9 + 5.078459e9
+NCU_PREDICT_I8_SOURCE = "profiles/r02b_predict_i8_kernel.md"
 NCU_PREDICT_DRAM_BYTES = 108.822557e9 + 6.737815e9
 NCU_PREDICT_SOURCE = "profiles/r01h_predict_kernel.md"
+I8_SLICES = 6                     # slice count gp2d_fit picks at the conditioning of configs[1] / configs[2] / configs[4]
+I8_PRODUCTS = I8_SLICES * (I8_SLICES + 1) // 2     # int8 x int8 MACs per fp64 MAC of the predictive product
+# int8 issue rate of tcgen05.mma kind::i8 measured on this pool (tools/umma_probe2.cu, M=128 N=256 SS, all SMs)
+I8_PROBE_TOPS = 4279.4
 METRIC = "fit_predict_seconds_per_snapshot"
 WORKLOAD = ("configs[1]: single LASER-style snapshot, N=2000 obs (4000x4000 fp64 covariance), "
             "320x320=102400-point grid, curl-free+div-free SE kernel theta=(1.3,3.1,0.2), noise 0.05")
@@ -235,6 +241,13 @@ def potri_launches(nb, need_inv=True):
     return potri_launches(n1, True) + 2 + potri_launches(nb - n1, need_inv) + (2 if need_inv else 0)
 
 
+def bf16_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        return 1590.0       # fallback stated in B200_PROFILING.md
+
+
 def hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -318,10 +331,15 @@ def run_configs2(torch, dist, gp, gdist, syn, rank, world, dev, peak_tf):
             "broadcast_GBps": (state_bytes / 1e9) / (t_bc / 1e3) if world > 1 and t_bc > 0 else None,
             "predict_s": t_pred / 1e3, "gather_s": t_g / 1e3, "total_s": total / 1e3,
             "fit_TFLOPps": flops_fit / (t_fit / 1e3) / 1e12, "fit_frac_of_fp64_peak": flops_fit / (t_fit / 1e3) / 1e12 / peak_tf,
+            "predict_kernel": "int8-sliced tcgen05 kernel, %d slices (fp64 DMMA kernel when the fit state says 0): slices=%d"
+                              % (I8_SLICES, int(m.ws[-256:].view(torch.int32)[2].item())),
             "predict_TFLOPps_aggregate": flops_pred / (t_pred / 1e3) / 1e12,
-            "predict_frac_of_fp64_peak": flops_pred / (t_pred / 1e3) / 1e12 / (world * peak_tf),
+            "predict_TFLOPps_note": "fp64-equivalent: the algorithmic flops n^2 m + 2 n m of the fp64 product over the time",
+            "predict_x_fp64_pipe_peak": flops_pred / (t_pred / 1e3) / 1e12 / (world * peak_tf),
+            "predict_int8_TOPps_aggregate": I8_PRODUCTS * flops_pred / (t_pred / 1e3) / 1e12,
+            "predict_frac_of_int8_peak": I8_PRODUCTS * flops_pred / (t_pred / 1e3) / 1e12 / (world * 2.0 * bf16_peak()),
             "total_TFLOPps_aggregate": (flops_pred + flops_fit) / (total / 1e3) / 1e12,
-            "total_frac_of_fp64_peak": (flops_pred + flops_fit) / (total / 1e3) / 1e12 / (world * peak_tf),
+            "total_x_fp64_pipe_peak": (flops_pred + flops_fit) / (total / 1e3) / 1e12 / (world * peak_tf),
             "unsharded_share_of_total": (t_fit + t_bc) / total,
             "parity": {"gp_identity_residual_rel": resid, "var_min": float(allv.min()), "var_max": float(allv.max()),
                        "var_upper_bound_kss": kss, "gathered_points": int(mu[0].numel()), "info": int(m._info.item()),
@@ -403,6 +421,23 @@ def run_ours(args):
     t_max = float(tt.item())
     value = t_max / (K * world)
     pred_ms = float(np.mean([a.elapsed_time(b) for a, b in pred_ev]))
+
+    # ---- the fp64 tensor-pipe kernel on the same snapshot (GP2D_OPT_PREDICT_I8 = 1): the kernel the int8 path
+    # replaces at this conditioning and the only path beyond it; kept in the line so both rooflines are visible ----
+    i8_slices = int(model.ws[-256:].view(torch.int32)[2].item())
+    gp.set_predict_i8(1)
+    model.fit_async()
+    model.predict(dsn[0][2], out_mean=mean, out_var=var)
+    f0, f1 = ev(), ev()
+    f0.record()
+    for _ in range(3):
+        model.predict(dsn[0][2], out_mean=mean, out_var=var)
+    f1.record()
+    torch.cuda.synchronize()
+    pred_ms_fp64 = f0.elapsed_time(f1) / 3
+    gp.set_predict_i8(0)
+    model.fit_async()
+    torch.cuda.synchronize()
 
     # ---- e2e: the call a user of the reference makes.  gp2d_fit_predict_host takes pageable numpy
     # arrays (what GP_laser.simLaser / GPRegression.predict hand over), copies them to the device,
@@ -562,27 +597,56 @@ def run_ours(args):
         ach = flops_pred / (pred_ms * 1e-3) / 1e12
         sm_max_mhz = clocks.get("sm_max_mhz") or 1965.0
         derived = 148 * 64 * 2 * sm_max_mhz * 1e6 / 1e12
+        ach64 = flops_pred / (pred_ms_fp64 * 1e-3) / 1e12
+        peak_src = ("FP64 DMMA.8x8x4 register-resident loop measured live in this run (MEASURED_PEAKS.json has no fp64 figure); "
+                    "derived ceiling 148 SMs x 64 FP64 FMA/clk/SM x 2 flop x %.0f MHz = %.2f TFLOP/s" % (sm_max_mhz, derived))
+        roofline_fp64 = {
+            "kernel": "predict_kernel (fused K* generation + Z K*^T on DMMA + mean/variance), GP2D_OPT_PREDICT_I8 = 1",
+            "bound": "tensor", "achieved": ach64, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach64 / peak_tf,
+            "traffic": NCU_PREDICT_DRAM_BYTES, "traffic_unit": "bytes", "traffic_source": NCU_PREDICT_SOURCE,
+            "peak_source": peak_src, "peak_derived": derived, "algorithmic_flops_per_launch": flops_pred, "ms_per_launch": pred_ms_fp64,
+        }
+        if i8_slices:
+            nprod = i8_slices * (i8_slices + 1) // 2
+            i8_peak = 2.0 * bf16_peak()
+            ach8 = nprod * flops_pred / (pred_ms * 1e-3) / 1e12
+            roofline = {
+                "kernel": "predict_i8_kernel<%d> (fused K* digit-slice generation + %d tcgen05.mma kind::i8 slice products per "
+                          "k-step into TMEM + fp64 recombination, mean/variance)" % (i8_slices, nprod),
+                "bound": "tensor", "achieved": ach8, "peak": i8_peak, "unit": "TOP/s", "frac": ach8 / i8_peak,
+                "traffic": NCU_PREDICT_I8_DRAM_BYTES, "traffic_unit": "bytes", "traffic_source": NCU_PREDICT_I8_SOURCE,
+                "peak_source": "int8 dense tensor rate = 2 x the measured bf16 figure of MEASURED_PEAKS.json (%.1f TFLOP/s; the file has "
+                               "no int8 entry; nominal 4500 TOP/s); this pool's own tcgen05 kind::i8 issue-rate probe "
+                               "(tools/umma_probe2.cu, N = 256) reads %.0f TOP/s" % (bf16_peak(), I8_PROBE_TOPS),
+                "frac_of_probe_peak": ach8 / I8_PROBE_TOPS,
+                "algorithmic_ops_per_launch": nprod * flops_pred,
+                "algorithmic_ops_note": "%d int8 slice products per fp64 multiply-add of the product (n^2 m + 2 n m flops, SURVEY.md 8d): "
+                                        "slice pairs (i, j), i + j < %d" % (nprod, i8_slices),
+                "ms_per_launch": pred_ms,
+                "fp64_equivalent": {"achieved": ach, "unit": "TFLOP/s", "fp64_pipe_peak": peak_tf, "x_fp64_pipe_peak": ach / peak_tf,
+                                    "speedup_over_fp64_kernel": pred_ms_fp64 / pred_ms},
+                "structural_bound": "an SS-mode MMA re-reads both operand tiles from shared memory: 21 x (4096 + 2560) B read + "
+                                    "6 x 6656 B written per k-step at 128 B/clk/SM = 1404 clk against 840 clk of tensor time, "
+                                    "i.e. at most 0.60 of the int8 issue rate with 80-column accumulators (TMEM holds 6 x 80 columns)",
+            }
+        else:
+            roofline = roofline_fp64
         out = {
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_max / K * 1e3, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(),
+            "dtype_note": "fp64 throughout; the predictive product Z K* runs as exact int8 digit-slice products (int32 accumulation in "
+                          "TMEM) recombined in fp64 when the fit's conditioning allows it (slices=%d here), on the FP64 tensor pipe otherwise" % i8_slices,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "gp2d_fit_predict_host (C ABI, pageable numpy arrays in and out, device buffer cached per thread)",
                     "gpregression_construct_plus_predict_s": e2e_gpy,
                     "gpregression_note": "models.GPRegression(X, Y, myKernel).predict(Xnew): the constructor evaluates LML "
                                          "and its gradient like GPy's, then predict refits and predicts"},
-            "gpu_launches": K * (1 + potri_launches(npad // 128) + 1 + 5 + 1),   # build, potri tree, pack, alpha/LML, predict
-            "roofline": {
-                "kernel": "predict_kernel (fused K* generation + Z K*^T DMMA + mean/variance)",
-                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": NCU_PREDICT_DRAM_BYTES, "traffic_unit": "bytes", "traffic_source": NCU_PREDICT_SOURCE,
-                "peak_source": "FP64 DMMA.8x8x4 register-resident loop measured live in this run "
-                               "(MEASURED_PEAKS.json has no fp64 figure); derived ceiling 148 SMs x 64 FP64 FMA/clk/SM x 2 flop x "
-                               "%.0f MHz = %.2f TFLOP/s" % (sm_max_mhz, derived),
-                "peak_derived": derived,
-                "algorithmic_flops_per_launch": flops_pred, "ms_per_launch": pred_ms,
-            },
+            # build, potri tree, pack, digit slices (row scale, quantise, gate), alpha/LML, predict (the int8 kernel of
+            # each slice count + the fp64 kernel: the fit state selects one on the device, the others return at once)
+            "gpu_launches": K * (1 + potri_launches(npad // 128) + 1 + 3 + 5 + 3),
+            "roofline": roofline, "roofline_fp64_kernel": roofline_fp64,
             "stages": stages, "targets_at_N16384": targets, "info": info,
         }
         if cpu is not None:
