@@ -14,6 +14,8 @@ LIB = os.path.join(HERE, "libgp2d.so")
 SOURCES = ["capi.cu", "linalg.cu", "kernel_build.cu", "predict.cu", "predict_i8.cu", "grad.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("GP2D_I8_WATCHDOG"):           # bring-up: bounded waits in the int8 predictive kernel (predict_i8.cu)
+    FLAGS.append("-DGP2D_I8_WATCHDOG")
 
 
 def nvcc() -> str:

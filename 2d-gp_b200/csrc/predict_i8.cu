@@ -12,17 +12,27 @@
 // remains the path beyond it (gate, below).  Same role as predict.cu: replaces GPy model.predict
 // (krig.py:543-544), GP_scripts.getMean + the diagonal of GP_laser.py:129-131.
 //
-// Why it is faster: the FP64 pipe peaks at 37 TFLOP/s; kind::i8 at M = 128, N = 80 issues one
-// 128 x 80 x 32 product per ~55 clocks per SM (bound by the shared-memory read of its operands), i.e.
-// 21 instructions per k-step of the fp64-equivalent product: ~165 TFLOP/s fp64-equivalent at S = 6.
+// Why it is faster: the FP64 pipe peaks at 37 TFLOP/s; kind::i8 at M = 128, N = 80 takes ~55 clocks per
+// 128 x 80 x 32 product per SM (an SS-mode MMA re-reads both operand tiles from shared memory; whatever N, an
+// instruction costs >= 47 clocks: tools/umma_probe4.cu), i.e. 21 instructions per k-step of the fp64-equivalent
+// product at S = 6.  Two further facts shape the kernel (same probe): the tensor pipe takes one MMA at a time from a
+// warp and queues nothing behind it, so every instruction the issuing warp spends on anything else is pipe idle time
+// (hence two issuing warps taking the stages in turn); and a digit slice of a tile that is identically zero --
+// covariances of distant points, entries of L^-1 far from the diagonal: a third of the slice products at
+// configs[1], 60 % at N = 8192 -- need neither be copied nor multiplied, exactly (tools/sparsity_emulate.py).
 //
-// CTA (one per SM, persistent over column tiles of NC / 2 grid points x 2 components):
-//   warps 0-3   epilogue: TMEM -> registers, Horner, (v zu ku)^2, sum over the 128 rows, running column sums
-//   warp  4     producer: one thread, two bulk copies (A slices of Zq, B slices of the panel) per k-step
-//   warp  5     MMA issuer: one thread
-//   warps 6..   generators: build the digit slices of the K* panel of the NEXT column tile into the other
-//               of two global scratch panels while the tensor core works on the current one, and the mean
-//               K*^T alpha in fp64 on the way
+// CTA (one per SM, persistent over column tiles of NC / 2 grid points x 2 components), by warp:
+//   0-7    epilogue: (A) TMEM -> one 64-bit integer per entry (Horner over the digit sums), accumulators handed
+//          back at once; (B) fp64 scale, square, sum over the 128 rows, running column sums, while the tensor core
+//          is on the next row block.  Warp w: TMEM lanes 32 (w % 4).., column half w / 4
+//   8      producer / scheduler: reads one byte per k-step tile of Z (written at fit time) and of the panel (written
+//          by the generators): the leading all-zero slices a, b; drops the k-step when a + b >= S, else copies the
+//          non-zero slices with two bulk copies and writes the stage header (a, b, segment flags) for the issuers
+//   9, 10  MMA issuers: stage n belongs to issuer n % 2; straight-line code per (a, b)
+//   11..   generators: build the digit slices of the K* panel of the NEXT column tile into the other of two global
+//          scratch panels while the tensor core works on the current one, the mean K*^T alpha in fp64 on the way,
+//          and the OR of the digits per k-step tile (-> b)
+// tests/tools/i8_protocol_sim.py is a discrete-event model of the barrier protocol between these roles.
 #include "common.cuh"
 #include "linalg.h"
 #include "umma.cuh"
@@ -30,7 +40,7 @@
 namespace gp2d {
 
 constexpr int I8_SMAX = 7;                           // digits stored per entry of Zq
-constexpr int I8_OBS_BATCH = 128;                    // observations staged in shared memory at a time
+constexpr int I8_GSLOTS = 4;                         // k-steps a CTA generates side by side (x NC / 2 grid points = generator threads)
 // An int32 accumulator d sums (d + 1) digit products over k: at most k (2 64 128 + (d - 1) 128 128) for d = S - 1
 // (top digits are within [-64, 64]), which passes 2^31 beyond k = 21845 (S = 7).  Row blocks that reach further are
 // accumulated in segments of I8_KSEG k-steps (16384 rows: 1.6e9 at worst); the partial fp64 sums of the earlier
@@ -38,27 +48,97 @@ constexpr int I8_OBS_BATCH = 128;                    // observations staged in s
 constexpr int I8_KSEG = 512;
 constexpr int I8_MAX_NPAD = 65536;
 
+
+// Bring-up watchdog (-DGP2D_I8_WATCHDOG): a wait that does not complete within ~2 s records who was waiting on what
+// and releases every later wait of the launch, so a protocol error ends in a report instead of a hung device.
+#ifdef GP2D_I8_WATCHDOG
+__device__ int g_i8_abort;
+__device__ int g_i8_abort_cta = -1;
+__device__ unsigned long long g_i8_wd[4];
+__device__ unsigned long long g_i8_state[32];        // per warp of the CTA that timed out first: what it was waiting for
+__device__ __forceinline__ void i8_wait(unsigned long long* bar, unsigned parity, unsigned tag, unsigned info) {
+    const long long t0 = clock64();
+    for (unsigned n = 0;; ++n) {
+        unsigned ok;
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if ((n & 255u) == 255u) {
+            bool out = *(volatile int*)&g_i8_abort != 0;
+            if (!out && clock64() - t0 > 4000000000ll) {
+                if (atomicCAS(&g_i8_abort_cta, -1, (int)blockIdx.x) == -1) {
+                    g_i8_wd[0] = ((unsigned long long)tag << 32) | info;
+                    g_i8_wd[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+                    g_i8_wd[2] = parity;
+                }
+                __threadfence();
+                atomicExch(&g_i8_abort, 1);
+                out = true;
+            }
+            if (out) {
+                if (*(volatile int*)&g_i8_abort_cta == (int)blockIdx.x)
+                    g_i8_state[threadIdx.x >> 5] = ((unsigned long long)parity << 63) | ((unsigned long long)tag << 32) | info;
+                return;
+            }
+        }
+    }
+}
+#define I8_WAIT(bar, parity, tag, info) i8_wait(bar, parity, tag, (unsigned)(info))
+#else
+#define I8_WAIT(bar, parity, tag, info) mbar_wait(bar, parity)
+#endif
+
+// Stage header, written by the producer for the MMA issuers: bits 0-7 a, 8-15 b (leading all-zero slices of the A and
+// of the B tile), then:
+constexpr unsigned H_FIRST = 1u << 16;        // first stage of an accumulation segment: taken whole, overwrites the accumulators
+constexpr unsigned H_LAST = 1u << 17;         // last stage of the segment
+constexpr unsigned H_ITEM_LAST = 1u << 18;    // ... and of the item (column tile)
+constexpr unsigned H_FINAL = 1u << 19;        // ... and of the CTA: this issuer is done
+constexpr unsigned H_PENULT = 1u << 20;       // the stage before the last of the segment (the other issuer's last one)
+constexpr unsigned H_ITEM_PENULT = 1u << 21;  // ... of the last segment of the item
+constexpr unsigned H_SECOND = 1u << 22;       // the stage after the first: may not overtake it
+constexpr unsigned H_SEGNZ = 1u << 24;        // not the first segment of the CTA: the epilogue has to hand the accumulators back
+constexpr unsigned H_SEGPAR = 1u << 25;       // parity of the segment count
+constexpr unsigned H_ITEMPAR = 1u << 26;      // parity of the item count (which panel)
+constexpr unsigned H_EXIT = 1u << 27;         // no work: the issuer that did not get the final stage leaves
+
 template <int S, int NC>
 struct I8Cfg {
     static constexpr int NG = NC / 2;                 // grid points per column tile
-    static constexpr int GT = NG * 8;                 // generator threads: (grid point, k-step slot)
-    static constexpr int THREADS = 192 + GT;
+    static constexpr int GSLOTS = I8_GSLOTS;          // k-steps generated side by side
+    static constexpr int OBS_BATCH = 16 * GSLOTS;     // observations staged in shared memory at a time
+    static constexpr int GT = NG * GSLOTS;            // generator threads: (grid point, k-step slot)
+    static constexpr int EPI_WARPS = 8;               // two per TMEM lane quarter: column halves
+    static constexpr int MMA_WARPS = 2;               // the tensor pipe idles whenever its issuing warp does anything else: two take turns
+    static constexpr int GEN0 = 32 * (EPI_WARPS + 1 + MMA_WARPS);   // first generator thread
+    static constexpr int THREADS = GEN0 + GT;
+    static constexpr int HC = NC / 2;                 // accumulator columns per epilogue warp
     static constexpr int BTILE = NC * I8_KSTEP;       // bytes of one B slice tile
     static constexpr int STAGE_BYTES = S * (I8_ATILE_BYTES + BTILE);
     static constexpr int STAGES = S == 6 ? 5 : 4;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int NBARS = 2 * STAGES + 2 + 4;  // full, empty, acc_full, acc_empty, panel_full[2], panel_empty[2]
-    // doubles after the barriers: observation stage, mean partials [8][NG][2], column sums [4][NC], parameters
-    static constexpr int TAIL_DOUBLES = 5 * I8_OBS_BATCH + 8 * NG * 2 + 4 * NC + 64;
+    // A stage's "full" barrier is waited on by the issuer n % MMA_WARPS; with an odd ring each issuer would meet a slot at
+    // every other use only, and one parity bit cannot tell "my last use" from "the use in between has not landed yet"
+    // (copies of different stages complete out of order).  So the full barriers are indexed by n % NFULL, NFULL a
+    // multiple of both the ring and the issuer count: every barrier then belongs to one issuer, use after use.
+    static constexpr int NFULL = MMA_WARPS * STAGES;
+    static constexpr int NBARS = NFULL + STAGES + 2 + 4 + 2;   // full, empty, acc_full, acc_empty, panel_full[2], panel_empty[2], first_done, pad
+    // doubles after the barriers: observation stage, mean partials [GSLOTS][NG][2], column sums [4][NC], parameters,
+    // digit ORs of the generators [2][GSLOTS], stage headers [STAGES] (32-bit)
+    static constexpr int TAIL_DOUBLES = 5 * OBS_BATCH + GSLOTS * NG * 2 + 4 * NC + 64 + 16 + 8;
+    static_assert(STAGES <= 16 && GSLOTS <= 8, "stage headers, digit ORs");
     static constexpr int SMEM_BYTES = RING_BYTES + NBARS * 8 + 16 + TAIL_DOUBLES * 8;
     static constexpr int TMEM_COLS = 512;
     static_assert(S * NC <= TMEM_COLS, "S accumulators of NC columns must fit TMEM");
     static_assert(NC % 16 == 0, "tcgen05.mma M = 128 needs N % 16 == 0");
+    static_assert(HC % 8 == 0, "an epilogue warp reads its columns eight at a time");
+    static_assert(THREADS % 32 == 0 && GT % 32 == 0, "whole warps");
     static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
 struct PredictI8Args {
     const int8_t* Zq;             // [k-step of the lower triangle][I8_SMAX][4096]: digit slices of Z, tile images
+    const uint8_t* zlead;         // [k-step of the lower triangle]: leading all-zero slices of that tile
     const double* zunit;          // [npad] value of one unit of digit I8_SMAX - 1 of row r
     int npad;
     const double* alpha;          // pair-interleaved, zero padded
@@ -70,11 +150,12 @@ struct PredictI8Args {
     double kscale;                // K* entries are quantised as rint(k kscale), |k kscale| <= 2^(8 S - 2)
     double cscale;                // ku 256^(S-1) 256^(I8_SMAX-S): v = Horner zunit[r] cscale
     double* mean; double* var;
-    uint8_t* scratch;             // per CTA: 2 panels, then [128][NC] doubles (segment partial sums)
-    size_t panel_bytes, cta_bytes;
+    uint8_t* scratch;             // per CTA: 2 panels
+    size_t panel_bytes, cta_bytes, lead_off;     // a panel: digit slices, then at lead_off one byte per k-step (leading all-zero slices)
     int ntiles;
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
-    int dbg;                      // bring-up timing experiments (wrong results): 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation
+    int dbg;                      // bring-up knobs: 8 = copy and multiply the all-zero slices too (same results bit for bit);
+                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -107,13 +188,26 @@ __global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restri
     }
 }
 
+// Leading all-zero digits of a set of biased values: y = OR over the set of (q + BIAS) ^ BIAS has byte p zero exactly
+// when digit p of every value is zero, so the count of zero top bytes of y (out of ND) is the number of leading
+// (most significant) slices of the set that are identically zero.
+__device__ __forceinline__ int i8_lead_zero_slices(unsigned long long y, int nd) {
+    const int used = y ? (64 - __clzll((long long)y) + 7) / 8 : 0;
+    return nd - used;
+}
+
 // one CTA per lower 128 x 128 tile (I, J): 4 k-steps x 7 slices of 4 KB tile images.  Thread (r, h): row r,
-// k-steps 2h, 2h+1.
+// k-steps 2h, 2h+1.  Also writes, per k-step tile, how many of its leading slices are all zero (entries far from
+// the diagonal are small against the row unit): the predictive kernel neither copies nor multiplies those.
 __global__ void __launch_bounds__(256) i8_quantize_kernel(const double* __restrict__ Z, long ldz, const double* __restrict__ zqs,
-                                                          int8_t* __restrict__ Zq, long bstride) {
+                                                          int8_t* __restrict__ Zq, uint8_t* __restrict__ lead, long bstride) {
+    __shared__ unsigned long long s_or[4];
     Z += (long)blockIdx.y * bstride;
     zqs += (long)blockIdx.y * bstride;
     Zq += (long)blockIdx.y * bstride * (long)sizeof(double);
+    lead += (long)blockIdx.y * bstride * (long)sizeof(double);
+    if (threadIdx.x < 4) s_or[threadIdx.x] = 0ull;
+    __syncthreads();
     const int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
@@ -124,15 +218,19 @@ __global__ void __launch_bounds__(256) i8_quantize_kernel(const double* __restri
     const double qs = zqs[I * TILE + r];
     constexpr long long BIAS = i8_digit_bias(I8_SMAX);
     const size_t ks0 = (size_t)2 * I * (I + 1) + 4 * (size_t)J + 2 * h;
+    unsigned long long yor[2] = {0ull, 0ull};
 #pragma unroll 1
     for (int c16 = 0; c16 < 4; ++c16) {          // 16 consecutive k: one 16-byte row chunk of every slice image
         long long q[16];
+        unsigned long long y = 0ull;
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
             const double2 v = *reinterpret_cast<const double2*>(src + c16 * 16 + j);
             q[j] = __double2ll_rn(v.x * qs) + BIAS;
             q[j + 1] = __double2ll_rn(v.y * qs) + BIAS;
+            y |= (unsigned long long)(q[j] ^ BIAS) | (unsigned long long)(q[j + 1] ^ BIAS);
         }
+        yor[c16 >> 1] |= y;
         int8_t* dst = Zq + (ks0 + (c16 >> 1)) * (size_t)(I8_SMAX * I8_ATILE_BYTES) + i8_tile_off(r, (c16 & 1) * 16);
 #define GP2D_I8_STORE(P)                                                                                          \
         *reinterpret_cast<uint4*>(dst + (I8_SMAX - 1 - P) * I8_ATILE_BYTES) =                                     \
@@ -141,13 +239,28 @@ __global__ void __launch_bounds__(256) i8_quantize_kernel(const double* __restri
         GP2D_I8_STORE(0) GP2D_I8_STORE(1) GP2D_I8_STORE(2) GP2D_I8_STORE(3) GP2D_I8_STORE(4) GP2D_I8_STORE(5) GP2D_I8_STORE(6)
 #undef GP2D_I8_STORE
     }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        unsigned long long y = yor[e];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) y |= __shfl_xor_sync(0xffffffffu, y, o);
+        if ((threadIdx.x & 31) == 0 && y) atomicOr(&s_or[2 * h + e], y);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4)
+        lead[(size_t)2 * I * (I + 1) + 4 * (size_t)J + threadIdx.x] = (uint8_t)i8_lead_zero_slices(s_or[threadIdx.x], I8_SMAX);
 }
 
 __global__ void i8_set_gate_kernel(int* gate, int s) { *gate = s; }
 
-size_t i8_zq_bytes(int npad) {
+// digit slices of the lower triangle, then one byte per k-step tile (leading all-zero slices)
+static size_t i8_zq_slice_bytes(int npad) {
     const size_t nb = (size_t)npad / TILE;
     return 2 * nb * (nb + 1) * (size_t)(I8_SMAX * I8_ATILE_BYTES);
+}
+size_t i8_zq_bytes(int npad) {
+    const size_t nb = (size_t)npad / TILE;
+    return i8_zq_slice_bytes(npad) + ((2 * nb * (nb + 1) + 255) / 256) * 256;
 }
 int i8_max_npad() { return I8_MAX_NPAD; }
 
@@ -157,7 +270,7 @@ cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit
     const int nb = npad / TILE;
     const long bs = batch > 1 ? bstride : 0;
     i8_rowscale_kernel<<<dim3((npad + 7) / 8, batch), 256, 0, st>>>(Z, ldz, npad, zunit, zqs, bs);
-    i8_quantize_kernel<<<dim3(nb * (nb + 1) / 2, batch), 256, 0, st>>>(Z, ldz, zqs, Zq, bs);
+    i8_quantize_kernel<<<dim3(nb * (nb + 1) / 2, batch), 256, 0, st>>>(Z, ldz, zqs, Zq, reinterpret_cast<uint8_t*>(Zq) + i8_zq_slice_bytes(npad), bs);
     return cudaGetLastError();
 }
 cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st) {
@@ -174,7 +287,7 @@ cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st) {
 template <int S, bool SAME_LEN, bool HAS_T>
 __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const HelmPoint& gpt, double wg, int nvalid, int o0,
                                                   const double* __restrict__ stage, double kscale, uint8_t* __restrict__ dst,
-                                                  int btile, double& m0, double& m1) {
+                                                  int btile, double& m0, double& m1, unsigned long long& yor) {
     constexpr long long BIAS = i8_digit_bias(S);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {                 // 8 observations = 16 consecutive k
@@ -206,6 +319,7 @@ __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const He
                 qa[e] = __double2ll_rn(k11 * kscale) + BIAS;
                 qb[e] = __double2ll_rn(k12 * kscale) + BIAS;
                 qc[e] = __double2ll_rn(k22 * kscale) + BIAS;
+                yor |= (unsigned long long)((qa[e] ^ BIAS) | (qb[e] ^ BIAS) | (qc[e] ^ BIAS));
             }
             // rows k = 2o, 2o+1, 2o+2, 2o+3: column 2g holds (k11, k12) per observation, column 2g+1 (k12, k22)
 #define GP2D_I8_WORDS(P)                                                              \
@@ -226,9 +340,20 @@ __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const He
     }
 }
 
+// Leading all-zero slices of the k-step tile generated in batch b by the threads of one slot: the slot's first thread
+// turns the OR of the batch into the panel's byte for that k-step and clears it for batch b + 2.
+template <int S>
+__device__ __forceinline__ void i8_flush_lead(unsigned long long* sh_or, uint8_t* plead, int b, int slot, int nks) {
+    unsigned long long* o = sh_or + (b & 1) * I8_GSLOTS + slot;
+    const int ks = b * I8_GSLOTS + slot;
+    if (ks < nks) plead[ks] = (uint8_t)i8_lead_zero_slices(*o, S);
+    *o = 0ull;
+}
+
 template <int S, int NC, bool SAME_LEN, bool HAS_T>
 __device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const HelmParams& hp, uint8_t* __restrict__ panel,
-                                                 double* __restrict__ stage, int gp0, int gtid, double& mu0, double& mu1) {
+                                                 double* __restrict__ stage, unsigned long long* sh_or, int gp0, int gtid,
+                                                 double& mu0, double& mu1) {
     using C = I8Cfg<S, NC>;
     const int g = gtid % C::NG, slot = gtid / C::NG;
     const int gj = gp0 + g;
@@ -238,9 +363,14 @@ __device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const H
     // the two image rows (columns 2g, 2g+1 of the tile) of this thread inside a slice tile
     const int rowoff = ((2 * g) >> 3) * 256 + ((2 * g) & 7) * 16;
     double m0 = 0.0, m1 = 0.0;
-    for (int ob = 0; ob < nobs_pad; ob += I8_OBS_BATCH) {
-        named_barrier(2, C::GT);                  // the previous batch has been read
-        if (gtid < I8_OBS_BATCH) {
+    uint8_t* plead = panel + p.lead_off;
+    const int nks_all = p.npad / I8_KSTEP;
+    int batch = 0;
+    for (int ob = 0; ob < nobs_pad; ob += C::OBS_BATCH, ++batch) {
+        named_barrier(2, C::GT);                  // the previous batch has been read, its digit ORs are complete
+        if (batch > 0 && g == 0) i8_flush_lead<S>(sh_or, plead, batch - 1, slot, nks_all);
+        __syncwarp();                             // bar.sync below is warp-aligned: reconverge after the divergent flush
+        if (gtid < C::OBS_BATCH) {
             const int o = ob + gtid;
             const bool ov = o < p.N;
             const HelmPoint q = helm_point(hp, p.X, ov ? o : 0);
@@ -254,12 +384,60 @@ __device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const H
         const int o0 = ob + slot * 16;
         if (o0 < nobs_pad) {
             const int ks = o0 >> 4;
+            unsigned long long yor = 0ull;
             i8_generate_kstep<S, SAME_LEN, HAS_T>(hp, gpt, wg, p.N, o0, stage + slot * 16 * 5, p.kscale,
-                                                  panel + (size_t)ks * (S * C::BTILE) + rowoff, C::BTILE, m0, m1);
+                                                  panel + (size_t)ks * (S * C::BTILE) + rowoff, C::BTILE, m0, m1, yor);
+            if (yor) atomicOr(sh_or + (batch & 1) * I8_GSLOTS + slot, yor);
         }
     }
+    named_barrier(2, C::GT);
+    if (g == 0) i8_flush_lead<S>(sh_or, plead, batch - 1, slot, nks_all);
+    __syncwarp();
     mu0 = m0;
     mu1 = m1;
+}
+
+// The MMAs of one k-step whose A tile has A and whose B tile has B leading all-zero slices: the slice pairs (i, j),
+// i >= A, j >= B, i + j < S, accumulator i + j.  A and B are compile-time so that the issuing lane runs straight-line
+// code (descriptor = stage base + constant): a single warp issues every MMA of the SM, and predicates per MMA
+// (~270 instructions per k-step) cost as much time as the products themselves.  FIRST: the k-step that starts an
+// accumulation segment (taken whole), whose first product per accumulator overwrites.
+template <int S, int NC, int A, int B, bool FIRST>
+__device__ __forceinline__ void i8_issue(unsigned tbase, unsigned a_lo, unsigned b_lo) {
+    constexpr unsigned IDESC = i8_idesc(128, NC);
+    constexpr int BT16 = (NC * I8_KSTEP) >> 4, AT16 = I8_ATILE_BYTES >> 4;
+#pragma unroll
+    for (int d = A + B; d < S; ++d)
+#pragma unroll
+        for (int i = A; i <= d - B; ++i)
+            umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)(i * AT16)), i8_desc(b_lo + (unsigned)((d - i) * BT16)), IDESC,
+                       (FIRST && i == A) ? 0u : 1u);
+}
+template <int S, int NC, int A>
+__device__ __forceinline__ void i8_issue_b(int b, unsigned tbase, unsigned a_lo, unsigned b_lo) {
+    switch (b) {
+        case 0: if (A + 0 < S) i8_issue<S, NC, A, (A + 0 < S ? 0 : 0), false>(tbase, a_lo, b_lo); break;
+        case 1: if (A + 1 < S) i8_issue<S, NC, A, (A + 1 < S ? 1 : 0), false>(tbase, a_lo, b_lo); break;
+        case 2: if (A + 2 < S) i8_issue<S, NC, A, (A + 2 < S ? 2 : 0), false>(tbase, a_lo, b_lo); break;
+        case 3: if (A + 3 < S) i8_issue<S, NC, A, (A + 3 < S ? 3 : 0), false>(tbase, a_lo, b_lo); break;
+        case 4: if (A + 4 < S) i8_issue<S, NC, A, (A + 4 < S ? 4 : 0), false>(tbase, a_lo, b_lo); break;
+        case 5: if (A + 5 < S) i8_issue<S, NC, A, (A + 5 < S ? 5 : 0), false>(tbase, a_lo, b_lo); break;
+        case 6: if (A + 6 < S) i8_issue<S, NC, A, (A + 6 < S ? 6 : 0), false>(tbase, a_lo, b_lo); break;
+        default: break;
+    }
+}
+template <int S, int NC>
+__device__ __forceinline__ void i8_issue_ab(int a, int b, unsigned tbase, unsigned a_lo, unsigned b_lo) {
+    switch (a) {
+        case 0: i8_issue_b<S, NC, 0>(b, tbase, a_lo, b_lo); break;
+        case 1: i8_issue_b<S, NC, 1>(b, tbase, a_lo, b_lo); break;
+        case 2: i8_issue_b<S, NC, 2>(b, tbase, a_lo, b_lo); break;
+        case 3: i8_issue_b<S, NC, 3>(b, tbase, a_lo, b_lo); break;
+        case 4: i8_issue_b<S, NC, 4>(b, tbase, a_lo, b_lo); break;
+        case 5: i8_issue_b<S, NC, 5>(b, tbase, a_lo, b_lo); break;
+        case 6: i8_issue_b<S, NC, (S > 6 ? 6 : 0)>(S > 6 ? b : S, tbase, a_lo, b_lo); break;
+        default: break;
+    }
 }
 
 template <int S, int NC>
@@ -270,133 +448,121 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     uint8_t* ring = smem_raw;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + C::RING_BYTES);
     unsigned long long* full = bars;
-    unsigned long long* empty = bars + C::STAGES;
-    unsigned long long* acc_full = bars + 2 * C::STAGES;
+    unsigned long long* empty = bars + C::NFULL;
+    unsigned long long* acc_full = empty + C::STAGES;
     unsigned long long* acc_empty = acc_full + 1;
     unsigned long long* panel_full = acc_full + 2;
     unsigned long long* panel_empty = acc_full + 4;
+    unsigned long long* first_done = acc_full + 6;
     unsigned* tslot = reinterpret_cast<unsigned*>(bars + C::NBARS);
     double* sh_stage = reinterpret_cast<double*>(smem_raw + C::RING_BYTES + C::NBARS * 8 + 16);
-    double* sh_mu = sh_stage + 5 * I8_OBS_BATCH;          // [8][NG][2]
-    double* sh_red = sh_mu + 8 * C::NG * 2;               // [4][NC]
+    double* sh_mu = sh_stage + 5 * C::OBS_BATCH;          // [GSLOTS][NG][2]
+    double* sh_red = sh_mu + C::GSLOTS * C::NG * 2;       // [4][NC]
     double* sh_par = sh_red + 4 * NC;
+    unsigned long long* sh_or = reinterpret_cast<unsigned long long*>(sh_par + 64);      // [2][8]
+    volatile unsigned* sh_hdr = reinterpret_cast<volatile unsigned*>(sh_or + 16);          // [STAGES]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = p.npad / TILE;
     uint8_t* panels = p.scratch + (size_t)blockIdx.x * p.cta_bytes;
 
     if (tid == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
-        for (int b = 0; b < 2; ++b) { mbar_init(panel_full + b, 1); mbar_init(panel_empty + b, 1); }
+        for (int s = 0; s < C::NFULL; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < C::STAGES; ++s) mbar_init(empty + s, 1);
+        mbar_init(acc_full, C::MMA_WARPS);
+        mbar_init(acc_empty, C::EPI_WARPS);
+        mbar_init(first_done, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(panel_full + b, 1); mbar_init(panel_empty + b, C::MMA_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < (int)(sizeof(HelmParams) / sizeof(double))) sh_par[tid] = reinterpret_cast<const double*>(&p.hp)[tid];
-    if (warp == 5) tmem_alloc(tslot, C::TMEM_COLS);
+    if (tid >= 64 && tid < 80) sh_or[tid - 64] = 0ull;
+    if (warp == C::EPI_WARPS + 1) tmem_alloc(tslot, C::TMEM_COLS);     // the first MMA warp
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tbase = *tslot;
 
-    if (warp < 4) {
+    if (warp < C::EPI_WARPS) {
         // ------------------------------ epilogue ------------------------------------------------
+        // Warp w reads TMEM lanes 32 (w % 4) .. (rows of the row block) and the column half w / 4.  Two phases per row
+        // block: (A) drain the accumulators into one 64-bit integer per entry -- Horner in 256 over the S digits' sums,
+        // the NHI leading and NLO trailing ones each within 56 bits, joined with the lowest SH bits dropped (far below
+        // the products i + j >= S that the slicing leaves out) -- and hand the accumulators back to the MMA issuer;
+        // (B) convert, scale by the row unit, square and sum over the rows while the tensor core works on the next row
+        // block.  Segments of a long row block add up exactly in the integers.
+        constexpr int HC = C::HC, NG8 = HC / 8;
+        constexpr int NHI = (S + 1) / 2, NLO = S - NHI;
+        constexpr int SH = S == 6 ? 8 : 14;
+        static_assert(8 * NLO >= SH, "join shift");
+        const int q = warp & 3, half = warp >> 2;
+        const double cs = p.cscale * (double)(1 << SH);
+        const unsigned tcol0 = tbase + ((unsigned)(q * 32) << 16) + (unsigned)(half * HC);
         unsigned ph = 0;
-        const double cs = p.cscale;
         for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x) {
-            double colsum[NC / 16];
+            double colsum[NG8];
 #pragma unroll
-            for (int c = 0; c < NC / 16; ++c) colsum[c] = 0.0;
-            double* vpart = reinterpret_cast<double*>(panels + 2 * p.panel_bytes) + (size_t)tid * NC;
+            for (int g = 0; g < NG8; ++g) colsum[g] = 0.0;
             for (int rb = 0; rb < nb; ++rb) {
-                const double rs = __ldg(p.zunit + rb * TILE + tid) * cs;
+                const double rs = __ldg(p.zunit + rb * TILE + q * 32 + lane) * cs;
                 const int nseg = (4 * (rb + 1) + I8_KSEG - 1) / I8_KSEG;
+                long long t64[HC];
                 for (int seg = 0; seg < nseg; ++seg) {
-                    mbar_wait(acc_full, ph);
+                    I8_WAIT(acc_full, ph, 1, (item << 8) | rb);
                     ph ^= 1u;
                     tc_fence_after();
-                    if (p.dbg & 2) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty);
-                        continue;
-                    }
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int c = 0; c < NC / 16; ++c) {
-                        // Horner in 256 over the S accumulators, in 64-bit integers: the first NHI digits and the last
-                        // NLO digits each fit 56 bits; two conversions and one fma give the fp64 value (one rounding)
-                        constexpr int NHI = (S + 1) / 2, NLO = S - NHI;
-                        double t[16];
-                        const unsigned ta = tbase + ((unsigned)(warp * 32) << 16) + c * 16;
-                        {
-                            int r[NHI][16];
+                        for (int g = 0; g < HC / 4; ++g) {
+                            int r[S][4];
 #pragma unroll
-                            for (int d = 0; d < NHI; ++d) tmem_ld16(ta + d * NC, r[d]);
+                            for (int d = 0; d < S; ++d) tmem_ld4(tcol0 + d * NC + g * 4, r[d]);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                long long h = r[0][j];
+                            for (int j = 0; j < 4; ++j) {
+                                long long h = r[0][j], l = r[NHI][j];
 #pragma unroll
                                 for (int d = 1; d < NHI; ++d) h = h * 256 + r[d][j];
-                                t[j] = (double)h;
+#pragma unroll
+                                for (int d = 1; d < NLO; ++d) l = l * 256 + r[NHI + d][j];
+                                const long long v = h * (1ll << (8 * NLO - SH)) + ((l + (1ll << (SH - 1))) >> SH);
+                                t64[g * 4 + j] = seg ? t64[g * 4 + j] + v : v;
                             }
                         }
-                        {
-                            int r[NLO][16];
-#pragma unroll
-                            for (int d = 0; d < NLO; ++d) tmem_ld16(ta + (NHI + d) * NC, r[d]);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                long long l = r[0][j];
-#pragma unroll
-                                for (int d = 1; d < NLO; ++d) l = l * 256 + r[d][j];
-                                t[j] = fma(t[j], (double)(1ll << (8 * NLO)), (double)l);
-                            }
-                        }
-                        if (c == NC / 16 - 1) {       // the accumulators have been read: the next segment may start
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(acc_empty);
-                        }
-                        if (nseg > 1) {               // long rows: Horner sums of the segments are added in fp64
-                            double* vp = vpart + c * 16;
-                            if (seg > 0) {
-#pragma unroll
-                                for (int j = 0; j < 16; j += 2) {
-                                    const double2 v = *reinterpret_cast<const double2*>(vp + j);
-                                    t[j] += v.x; t[j + 1] += v.y;
-                                }
-                            }
-                            if (seg < nseg - 1) {
-#pragma unroll
-                                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(vp + j) = make_double2(t[j], t[j + 1]);
-                                continue;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) { const double v = t[j] * rs; t[j] = v * v; }
-                        // sum over the 32 rows of the warp, 16 columns at once: halve the columns with each exchange
-#pragma unroll
-                        for (int w = 8; w >= 1; w >>= 1) {
-                            const bool up = (lane & (2 * w)) != 0;
-#pragma unroll
-                            for (int j = 0; j < w; ++j) {
-                                const double keep = up ? t[j + w] : t[j], send = up ? t[j] : t[j + w];
-                                t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
-                            }
-                        }
-                        t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
-                        colsum[c] += t[0];            // column c 16 + (lane >> 1)
                     }
+                    // the accumulators have been read: the next segment may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+                if (p.dbg & 2) continue;
+#pragma unroll
+                for (int g = 0; g < NG8; ++g) {
+                    double t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const double v = (double)t64[g * 8 + j] * rs; t[j] = v * v; }
+                    // sum over the 32 rows of the warp, 8 columns at once: halve the columns with each exchange
+#pragma unroll
+                    for (int w = 4; w >= 1; w >>= 1) {
+                        const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+                        for (int j = 0; j < w; ++j) {
+                            const double keep = up ? t[j + w] : t[j], send = up ? t[j] : t[j + w];
+                            t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                        }
+                    }
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 16);
+                    colsum[g] += t[0];                // column g 8 + ((lane >> 1) & 7)
                 }
             }
-            // columns of the item: sum of the four warps in fixed order
-            if (!(lane & 1)) {
+            // columns of the item: sum of the four lane quarters in fixed order
+            if (!(lane & 17)) {
 #pragma unroll
-                for (int c = 0; c < NC / 16; ++c) sh_red[warp * NC + c * 16 + (lane >> 1)] = colsum[c];
+                for (int g = 0; g < NG8; ++g) sh_red[q * NC + half * HC + g * 8 + (lane >> 1)] = colsum[g];
             }
-            named_barrier(1, 128);
+            __syncwarp();                             // bar.sync is warp-aligned: reconverge after the divergent store
+            named_barrier(1, 32 * C::EPI_WARPS);
             if (tid < NC) {
                 const int pj = tid >> 1, cc = tid & 1;
                 const int j = item * C::NG + pj;
@@ -407,97 +573,170 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     p.var[(long)cc * p.out_stride + j] = v + p.var_add;
                 }
             }
-            named_barrier(1, 128);
+            __syncwarp();
+            named_barrier(1, 32 * C::EPI_WARPS);
         }
-    } else if (warp == 4) {
-        // ------------------------------ producer --------------------------------------------------
-        if (lane == 0) {
+    } else if (warp == C::EPI_WARPS) {
+        // ------------------------------ producer / scheduler ----------------------------------------
+        // The whole warp walks the k-steps: lane l reads the leading-zero-slice bytes of k-step base + l of the Z row
+        // block and of the panel.  A k-step whose non-zero slices cannot meet (a + b >= S) is dropped; of the others
+        // only the non-zero slices are copied.  The first k-step of an accumulation segment is always taken whole (it
+        // initialises the S accumulators).  Each stage carries a header for the MMA issuer: a, b, first / last of the
+        // segment, last of the item.
+        {
             int rs = 0, it = 0;
             unsigned rph = 0;
-            long fills = 0;
+            long fills = 0, segs = 0;
+            const bool noskip = (p.dbg & (8 | 4)) != 0;
+            // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products)
+            auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, int a, int b, unsigned flags) {
+                if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
+#ifdef GP2D_I8_WATCHDOG
+                if (ks >= 0 && (a < 0 || b < 0 || a + b >= S || ks >= p.npad / I8_KSTEP)) {
+                    if (lane == 0) g_i8_wd[3] = 0xbad0000000000000ull | ((unsigned long long)(unsigned)a << 40) | ((unsigned long long)(unsigned)b << 32) | (unsigned)ks;
+                    a = 0; b = 0; ks = 0;
+                }
+#endif
+                if (lane == 0) {
+                    uint8_t* st = ring + rs * C::STAGE_BYTES;
+                    unsigned long long* fb = full + (int)(fills % C::NFULL);
+                    sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
+                    if (ks < 0 || (p.dbg & 32)) {
+                        mbar_arrive(fb);
+                    } else {
+                        const unsigned abytes = (unsigned)(S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(S - b) * C::BTILE;
+                        mbar_arrive_expect_tx(fb, abytes + bbytes);
+                        bulk_g2s(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb);
+                        bulk_g2s(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb);
+                    }
+                }
+                __syncwarp();
+                ++fills;
+                if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+            };
+            bool final_item = false;
             for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
                 const int b = it & 1;
-                mbar_wait(panel_full + b, (unsigned)(it >> 1) & 1u);
+                final_item = item + (int)gridDim.x >= p.ntiles;
+                I8_WAIT(panel_full + b, (unsigned)(it >> 1) & 1u, 2, it);
                 fence_proxy_async();
                 const uint8_t* pb = (p.dbg & 1) ? p.scratch : panels + (size_t)b * p.panel_bytes;
+                const volatile uint8_t* plead = pb + p.lead_off;
+                const unsigned item_flags = b ? H_ITEMPAR : 0u;
                 for (int rb = 0; rb < nb; ++rb) {
-                    const int8_t* za = p.Zq + (size_t)2 * rb * (rb + 1) * (size_t)(I8_SMAX * I8_ATILE_BYTES);
+                    const size_t kbase = (size_t)2 * rb * (rb + 1);
+                    const int8_t* za = p.Zq + kbase * (size_t)(I8_SMAX * I8_ATILE_BYTES);
+                    const uint8_t* zl = p.zlead + kbase;
                     const int nks = 4 * (rb + 1);
-                    for (int ks = 0; ks < nks; ++ks) {
-                        if (fills >= C::STAGES) mbar_wait(empty + rs, rph ^ 1u);
-                        uint8_t* st = ring + rs * C::STAGE_BYTES;
-                        mbar_arrive_expect_tx(full + rs, C::STAGE_BYTES);
-                        bulk_g2s(st, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES), S * I8_ATILE_BYTES, full + rs);
-                        bulk_g2s(st + S * I8_ATILE_BYTES, pb + (size_t)ks * (S * C::BTILE), S * C::BTILE, full + rs);
-                        ++fills;
-                        if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
+                    for (int ks0 = 0; ks0 < nks; ks0 += I8_KSEG, ++segs) {
+                        const int ks1 = ks0 + I8_KSEG < nks ? ks0 + I8_KSEG : nks;
+                        const bool item_last = rb == nb - 1 && ks1 == nks;
+                        // two stages are held back so that the last and the one before it can be told
+                        int pk[2] = {0, 0}, pa[2] = {0, 0}, pbz[2] = {0, 0}, npend = 0, nlive = 0;
+                        unsigned pf[2] = {0u, 0u};
+                        for (int base = ks0; base < ks1; base += 32) {
+                            const int ks = base + lane;
+                            int a = S, bb = S;
+                            if (ks < ks1) {
+                                a = __ldg(zl + ks);
+                                bb = plead[ks];
+                                if (ks == ks0 || noskip) { a = 0; bb = 0; }
+                            }
+                            unsigned mask = __ballot_sync(0xffffffffu, a + bb < S);
+                            while (mask) {
+                                const int l = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const int ca = __shfl_sync(0xffffffffu, a, l), cb = __shfl_sync(0xffffffffu, bb, l);
+                                if (npend == 2) {
+                                    emit(za, pb, pk[0], pa[0], pbz[0], pf[0]);
+                                    pk[0] = pk[1]; pa[0] = pa[1]; pbz[0] = pbz[1]; pf[0] = pf[1];
+                                    npend = 1;
+                                }
+                                unsigned f = item_flags;
+                                if (nlive == 0) f |= H_FIRST | (segs > 0 ? H_SEGNZ : 0u) | (((segs - 1) & 1) ? H_SEGPAR : 0u);
+                                if (nlive == 1) f |= H_SECOND | ((segs & 1) ? H_SEGPAR : 0u);
+                                pk[npend] = base + l; pa[npend] = ca; pbz[npend] = cb; pf[npend] = f;
+                                ++npend; ++nlive;
+                            }
+                        }
+                        const unsigned endf = H_LAST | (item_last ? H_ITEM_LAST | (final_item ? H_FINAL : 0u) : 0u);
+                        emit(za, pb, pk[0], pa[0], pbz[0], pf[0] | H_PENULT | (item_last ? H_ITEM_PENULT : 0u));
+                        if (npend == 2) {
+                            emit(za, pb, pk[1], pa[1], pbz[1], pf[1] | endf);
+                        } else {
+                            // A segment always has two stages, so that both issuers take part in every segment and neither
+                            // can run a whole segment ahead (the barriers carry one parity bit): an empty second stage.
+                            emit(za, pb, -1, S, 0, item_flags | H_SECOND | ((segs & 1) ? H_SEGPAR : 0u) | endf);
+                        }
                     }
                 }
             }
+            emit(nullptr, nullptr, -1, 0, 0, H_EXIT);          // for the issuer that did not get the final stage
         }
-    } else if (warp == 5) {
-        // ------------------------------ MMA issuer ------------------------------------------------
-        // The whole warp walks the loops (so every descriptor is warp-uniform and lives in uniform registers);
-        // one elected lane issues the MMAs and the commits.
+    } else if (warp <= C::EPI_WARPS + C::MMA_WARPS) {
+        // ------------------------------ MMA issuers -----------------------------------------------
+        // The tensor pipe takes one MMA at a time from a warp and queues nothing: every instruction its issuing warp
+        // spends between two MMAs (waiting for the next stage, reading its header, the commit) is time the pipe idles
+        // (tools/umma_probe4.cu: 1:1).  So two warps take the stages in turn, w issues stage n = w, w + 2, ..: while
+        // one does its bookkeeping the other's MMAs fill the pipe.  The products of two stages may then interleave,
+        // which integer accumulation does not notice; what has to be ordered is the start and the end of an
+        // accumulation segment: the stage after the first waits until the first one (which overwrites) has been
+        // issued (first_done), and both warps commit to acc_full / arrive on panel_empty when their part is done.
+        // Each warp walks the loop whole (descriptors are warp-uniform); one elected lane issues.
         {
-            constexpr unsigned IDESC = i8_idesc(128, NC);
+            const int w = warp - (C::EPI_WARPS + 1);
             const unsigned ring_lo = i8_desc_lo(smem_u32(ring));
-            int rs = 0, it = 0;
-            unsigned rph = 0;
-            long blocks = 0;
-            for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
-                for (int rb = 0; rb < nb; ++rb) {
-                    const int nks = 4 * (rb + 1);
-                    for (int ks0 = 0; ks0 < nks; ks0 += I8_KSEG, ++blocks) {      // one accumulation segment
-                        if (blocks > 0) {
-                            mbar_wait(acc_empty, (unsigned)(blocks - 1) & 1u);
-                            tc_fence_after();
-                        }
-                        const int ks1 = ks0 + I8_KSEG < nks ? ks0 + I8_KSEG : nks;
-                        for (int ks = ks0; ks < ks1; ++ks) {
-                            mbar_wait(full + rs, rph);
-                            tc_fence_after();
-                            const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
-                            const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
-                            const unsigned acc0 = ks > ks0 ? 1u : 0u;
-                            if (elect_one_sync()) {
-#pragma unroll
-                                for (int d = 0; d < S; ++d)
-#pragma unroll
-                                    for (int i = 0; i <= d; ++i)
-                                        umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)((i * I8_ATILE_BYTES) >> 4)),
-                                                   i8_desc(b_lo + (unsigned)(((d - i) * C::BTILE) >> 4)), IDESC, i > 0 ? 1u : acc0);
-                                umma_commit(empty + rs);
-                            }
-                            __syncwarp();
-                            if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
-                        }
-                        if (elect_one_sync()) umma_commit(acc_full);
-                        __syncwarp();
+            const bool nomma = (p.dbg & 16) != 0;
+            for (long n = w;; n += C::MMA_WARPS) {
+                const int rs = (int)(n % C::STAGES);
+                I8_WAIT(full + (int)(n % C::NFULL), (unsigned)(n / C::NFULL) & 1u, 4, (unsigned)n);
+                const unsigned h = sh_hdr[rs];
+                if (h & H_EXIT) break;
+                const int a = (int)(h & 0xffu), b = (int)((h >> 8) & 0xffu);
+                const unsigned segpar = (h & H_SEGPAR) ? 1u : 0u;
+                if ((h & H_FIRST) && (h & H_SEGNZ)) I8_WAIT(acc_empty, segpar, 5, (unsigned)n);    // the epilogue has drained the accumulators
+                if (h & H_SECOND) I8_WAIT(first_done, segpar, 7, (unsigned)n);
+                tc_fence_after();
+                const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
+                const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
+                if (elect_one_sync()) {
+                    if (nomma) {
+                    } else if (h & H_FIRST) {
+                        i8_issue<S, NC, 0, 0, true>(tbase, a_lo, b_lo);
+                    } else {
+                        i8_issue_ab<S, NC>(a, b, tbase, a_lo, b_lo);
+                    }
+                    umma_commit(empty + rs);
+                    if (h & H_FIRST) mbar_arrive(first_done);
+                    if (h & (H_LAST | H_PENULT)) umma_commit(acc_full);
+                    if (h & (H_ITEM_LAST | H_ITEM_PENULT)) {      // every copy this warp waited for out of the item's panel has landed
+                        mbar_arrive(panel_empty + ((h & H_ITEMPAR) ? 1 : 0));
                     }
                 }
-                if (lane == 0) mbar_arrive(panel_empty + (it & 1));      // every copy out of this item's panel has landed
+                __syncwarp();
+                if (h & H_FINAL) break;
             }
         }
     } else {
         // ------------------------------ generators ------------------------------------------------
-        const int gtid = tid - 192;
+        const int gtid = tid - C::GEN0;
         const HelmParams& hp = *reinterpret_cast<const HelmParams*>(sh_par);
         int it = 0;
         for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
             const int b = it & 1;
-            if (it >= 2 && gtid == 0) mbar_wait(panel_empty + b, (unsigned)((it >> 1) - 1) & 1u);
+            // the whole first warp waits (the others wait for it at the named barrier): no divergence ahead of bar.sync
+            if (it >= 2 && gtid < 32) I8_WAIT(panel_empty + b, (unsigned)((it >> 1) - 1) & 1u, 6, it);
             uint8_t* panel = panels + (size_t)b * p.panel_bytes;
             double mu0 = 0.0, mu1 = 0.0;
             const int gp0 = item * C::NG;
             if (p.dbg & 4) {
                 named_barrier(2, C::GT);
             } else if (hp.has_t) {
-                if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
-                else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+                if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
             } else {
-                if (hp.same_len) i8_generate_item<S, NC, true, false>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
-                else i8_generate_item<S, NC, false, false>(p, hp, panel, sh_stage, gp0, gtid, mu0, mu1);
+                if (hp.same_len) i8_generate_item<S, NC, true, false>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, false>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
             }
             fence_proxy_async();                  // the panel is read back by bulk (async-proxy) copies
             const int g = gtid % C::NG, slot = gtid / C::NG;
@@ -511,24 +750,28 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 if (j < p.M) {
                     double m = 0.0;
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) m += sh_mu[(s * C::NG + pj) * 2 + cc];
+                    for (int s = 0; s < C::GSLOTS; ++s) m += sh_mu[(s * C::NG + pj) * 2 + cc];
                     p.mean[(long)cc * p.out_stride + j] = m;
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tbase, C::TMEM_COLS);
+    if (warp == C::EPI_WARPS + 1) tmem_dealloc(tbase, C::TMEM_COLS);
 }
 
 template <int S, int NC>
+static size_t i8_panel_lead_off(int npad) { return (size_t)(npad / I8_KSTEP) * (S * I8Cfg<S, NC>::BTILE); }
+template <int S, int NC>
 static size_t i8_panel_bytes(int npad) {
-    // + 5 KB: consecutive panels must not sit at the same offset modulo a power of two (see predict.cu)
-    return (size_t)(npad / I8_KSTEP) * (S * I8Cfg<S, NC>::BTILE) + 5120;
+    // digit slices, one byte per k-step; + 5 KB: consecutive panels must not sit at the same offset modulo a power
+    // of two (see predict.cu)
+    return i8_panel_lead_off<S, NC>(npad) + (size_t)round_up(npad / I8_KSTEP, 128) + 5120;
 }
 template <int S, int NC>
-static size_t i8_cta_bytes(int npad) { return 2 * i8_panel_bytes<S, NC>(npad) + (size_t)TILE * NC * sizeof(double); }
+static size_t i8_cta_bytes(int npad) { return 2 * i8_panel_bytes<S, NC>(npad); }
 size_t predict_i8_scratch_bytes(int npad) {
     const size_t a = i8_cta_bytes<6, 80>(npad), b = i8_cta_bytes<7, 64>(npad);
     return (size_t)predict_max_ctas() * (a > b ? a : b);
@@ -552,6 +795,7 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     a.cscale = scalbn(1.0, e - (8 * S - 1)) * scalbn(1.0, 8 * (S - 1)) * scalbn(1.0, 8 * (I8_SMAX - S));
     a.ntiles = (a.M + C::NG - 1) / C::NG;
     a.panel_bytes = i8_panel_bytes<S, NC>(a.npad);
+    a.lead_off = i8_panel_lead_off<S, NC>(a.npad);
     a.cta_bytes = i8_cta_bytes<S, NC>(a.npad);
     a.scratch = scratch;
     long grid = a.ntiles;
@@ -565,6 +809,22 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     return cudaGetLastError();
 }
 
+#ifdef GP2D_I8_WATCHDOG
+extern "C" int gp2d_dbg_i8_watchdog(unsigned long long* out36) {      // [4] first time-out, [32] warp states of its CTA
+    int ab = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&ab, g_i8_abort, sizeof(int));
+    cudaMemcpyFromSymbol(out36, g_i8_wd, 4 * sizeof(unsigned long long));
+    cudaMemcpyFromSymbol(out36 + 4, g_i8_state, 32 * sizeof(unsigned long long));
+    const int zero = 0, minus = -1;
+    unsigned long long z[32] = {};
+    cudaMemcpyToSymbol(g_i8_abort, &zero, sizeof(int));
+    cudaMemcpyToSymbol(g_i8_abort_cta, &minus, sizeof(int));
+    cudaMemcpyToSymbol(g_i8_state, z, sizeof(z));
+    return ab;
+}
+#endif
+
 static thread_local int g_i8_dbg = 0;
 void set_i8_debug(int v) { g_i8_dbg = v; }
 
@@ -576,7 +836,7 @@ cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* g
                              int only_s) {
     if (M <= 0) return cudaSuccess;
     PredictI8Args a{};
-    a.Zq = Zq; a.zunit = zunit; a.gate = gate; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
+    a.Zq = Zq; a.zlead = reinterpret_cast<const uint8_t*>(Zq) + i8_zq_slice_bytes(npad); a.zunit = zunit; a.gate = gate; a.npad = npad; a.alpha = alpha_int; a.X = X; a.N = N; a.hp = hp;
     a.Xs = Xs; a.M = M; a.out_stride = out_stride;
     a.kss = a.kss1 = hp.tvar * (hp.w_df + hp.w_cf);
     a.var_add = var_add; a.mean = mean; a.var = var;

@@ -320,3 +320,23 @@ def test_param_fix_and_unfix_restore_the_constraint():
     assert p.constraint == ("bounded", 0.0, 1.0)
     q = Param("l", 2.0).constrain_positive().constrain_fixed()
     assert q.unconstrain_fixed().constraint == "positive"
+
+
+def test_i8_issuer_protocol_model():
+    """The barrier protocol of predict_i8_kernel (one producer, two MMA issuers in turn, epilogue; csrc/predict_i8.cu)
+    in a discrete-event model with one-bit mbarrier parities, out-of-order copy completion and random scheduling:
+    no deadlock, no stale stage header, no product outside its accumulation segment, for both ring sizes; and the
+    model does show the aliasing that indexing the full barriers by slot alone would have on the odd ring."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("i8_protocol_sim", os.path.join(os.path.dirname(__file__), "tools", "i8_protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for seed in range(120):
+        r = random.Random(seed)
+        segs = [r.choice([1, 1, 2, 2, 3, 4, 7, 12]) for _ in range(r.randint(1, 8))]
+        w = {k: r.choice([0.05, 0.3, 1, 4]) for k in ("producer", "copies", "issuer0", "issuer1", "epilogue", "tensor")}
+        for stages in (5, 4):
+            assert sim.run(seed, segs, stages=stages, weights=w) == "ok", (seed, segs, stages)
+    broken = sum(sim.run(seed, [1, 2, 3, 7, 2, 3], stages=5, nfull=5) != "ok" for seed in range(150))
+    assert broken > 0

@@ -138,6 +138,33 @@ def test_i8_long_rows_accumulate_in_segments():
         np.testing.assert_allclose(vv, v1, rtol=2e-9, atol=1e-13)
 
 
+@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("N,side,theta", [(900, 120, (0.5, 0.8, 0.4)), (2500, 90, THETA), (130, 13, (0.45, 2.2, 0.35))])
+def test_i8_zero_slice_skipping_is_bitwise_the_dense_schedule(mode, N, side, theta):
+    """Digit slices that are identically zero (covariances of distant points, entries of L^-1 far from the diagonal)
+    are neither copied nor multiplied; integer accumulation makes that exact.  Short length scales and grids with
+    several column tiles per CTA exercise the sparse schedules: single-stage segments (padded with an empty stage),
+    dropped k-steps, both MMA issuers, both panels."""
+    import ctypes as C
+    from gp2d_b200._lib import lib
+    lib.gp2d_dbg_set_i8.restype = C.c_int
+    lib.gp2d_dbg_set_i8.argtypes = [C.c_int]
+    X, y = synthetic.drifter_snapshot(N, config_id=6, seed_offset=N)
+    Xs = gp.as_dev(synthetic.prediction_grid(X, side, side))
+    gp.set_predict_i8(mode)
+    m = gp.HelmholtzGP(X, y, *theta, NOISE)
+    m.fit()
+    try:
+        lib.gp2d_dbg_set_i8(8)                     # dense schedule: every slice of every k-step
+        md, vd = m.predict(Xs)
+        lib.gp2d_dbg_set_i8(0)
+        for _ in range(3):                         # the sparse schedule is timing dependent in its interleaving only
+            ms, vs = m.predict(Xs)
+            assert torch.equal(ms, md) and torch.equal(vs, vd)
+    finally:
+        lib.gp2d_dbg_set_i8(0)
+
+
 def test_i8_host_entry_point_matches_device_path():
     """gp2d_fit_predict_host (numpy in / out) runs the same kernels as fit + predict on device tensors."""
     X, y = synthetic.drifter_snapshot(500, config_id=2, seed_offset=5)

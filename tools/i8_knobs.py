@@ -1,0 +1,37 @@
+"""Timing of the int8 predictive kernel under its bring-up knobs (wrong results by design for 1, 2, 4).
+    python tools/i8_knobs.py [N] [grid side] [slices]"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gp2d_b200 as gp                                   # noqa: E402
+from gp2d_b200 import synthetic as syn                   # noqa: E402
+from gp2d_b200._lib import lib                           # noqa: E402
+
+lib.gp2d_dbg_set_i8.restype = C.c_int
+lib.gp2d_dbg_set_i8.argtypes = [C.c_int]
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+side = int(sys.argv[2]) if len(sys.argv) > 2 else 320
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+X, y = syn.drifter_snapshot(N, config_id=2)
+Xsd = gp.as_dev(syn.prediction_grid(X, side, side))
+gp.set_predict_i8(S)
+m = gp.HelmholtzGP(X, y, 1.3, 3.1, 0.2, 0.05)
+m.fit()
+names = {1: "B from one shared panel (L2)", 2: "no epilogue math", 4: "no generation", 8: "dense schedule", 16: "no MMAs", 32: "no copies"}
+for dbg in [int(a) for a in (sys.argv[4].split(",") if len(sys.argv) > 4 else "0,8,1,2,4,3,7,9,10,12,15".split(","))]:
+    lib.gp2d_dbg_set_i8(dbg)
+    m.predict(Xsd)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); m.predict(Xsd); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print("dbg %2d: %7.2f ms   %s" % (dbg, min(ts), " + ".join(v for k, v in names.items() if dbg & k) or "production"), flush=True)
+lib.gp2d_dbg_set_i8(0)
+gp.set_predict_i8(0)
