@@ -102,6 +102,10 @@ constexpr unsigned H_SEGPAR = 1u << 25;       // parity of the segment count
 constexpr unsigned H_ITEMPAR = 1u << 26;      // parity of the item count (which panel)
 constexpr unsigned H_EXIT = 1u << 27;         // no work: the issuer that did not get the final stage leaves
 
+// Work counters of the launches so far (statistics for bench.py, read and cleared by gp2d_dbg_i8_counters; one atomic
+// per CTA and launch): slice products issued (MMAs), stages issued, k-steps visited (= stages of the dense schedule).
+__device__ unsigned long long g_i8_count[4];
+
 template <int S, int NC>
 struct I8Cfg {
     static constexpr int NG = NC / 2;                 // grid points per column tile
@@ -587,10 +591,12 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             int rs = 0, it = 0;
             unsigned rph = 0;
             long fills = 0, segs = 0;
+            unsigned long long n_mma = 0, n_stage = 0, n_kstep = 0;
             const bool noskip = (p.dbg & (8 | 4)) != 0;
             // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products)
             auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, int a, int b, unsigned flags) {
                 if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
+                if (ks >= 0) { const int mm = S - a - b; n_mma += (unsigned)(mm * (mm + 1) / 2); ++n_stage; }
 #ifdef GP2D_I8_WATCHDOG
                 if (ks >= 0 && (a < 0 || b < 0 || a + b >= S || ks >= p.npad / I8_KSTEP)) {
                     if (lane == 0) g_i8_wd[3] = 0xbad0000000000000ull | ((unsigned long long)(unsigned)a << 40) | ((unsigned long long)(unsigned)b << 32) | (unsigned)ks;
@@ -631,6 +637,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     for (int ks0 = 0; ks0 < nks; ks0 += I8_KSEG, ++segs) {
                         const int ks1 = ks0 + I8_KSEG < nks ? ks0 + I8_KSEG : nks;
                         const bool item_last = rb == nb - 1 && ks1 == nks;
+                        n_kstep += (unsigned)(ks1 - ks0);
                         // two stages are held back so that the last and the one before it can be told
                         int pk[2] = {0, 0}, pa[2] = {0, 0}, pbz[2] = {0, 0}, npend = 0, nlive = 0;
                         unsigned pf[2] = {0u, 0u};
@@ -672,6 +679,12 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 }
             }
             emit(nullptr, nullptr, -1, 0, 0, H_EXIT);          // for the issuer that did not get the final stage
+            if (lane == 0) {
+                atomicAdd(&g_i8_count[0], n_mma);
+                atomicAdd(&g_i8_count[1], n_stage);
+                atomicAdd(&g_i8_count[2], n_kstep);
+                if (blockIdx.x == 0) atomicAdd(&g_i8_count[3], 1ull);
+            }
         }
     } else if (warp <= C::EPI_WARPS + C::MMA_WARPS) {
         // ------------------------------ MMA issuers -----------------------------------------------
@@ -824,6 +837,15 @@ extern "C" int gp2d_dbg_i8_watchdog(unsigned long long* out36) {      // [4] fir
     return ab;
 }
 #endif
+
+// out4: slice products (tcgen05.mma instructions of 128 x NC x 32) issued, stages issued, k-steps of the dense schedule,
+// launches -- since the last call; clears them
+extern "C" int gp2d_dbg_i8_counters(unsigned long long* out4) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out4, g_i8_count, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    return cudaMemcpyToSymbol(g_i8_count, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
 
 static thread_local int g_i8_dbg = 0;
 void set_i8_debug(int v) { g_i8_dbg = v; }

@@ -48,8 +48,8 @@ NOISE = 0.05
 CPU_GRID_FRACTION = 0.10          # share of the grid a bounded CPU step predicts (all of it for <= 3 steps)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
 # ncu captures named in roofline.traffic_source (int8-sliced kernel) / roofline_fp64_kernel.traffic_source
-NCU_PREDICT_I8_DRAM_BYTES = 76.145773e9 + 5.078459e9
-NCU_PREDICT_I8_SOURCE = "profiles/r02b_predict_i8_kernel.md"
+NCU_PREDICT_I8_DRAM_BYTES = 67.632966e9 + 5.423938e9
+NCU_PREDICT_I8_SOURCE = "profiles/r02d_predict_i8_kernel.md"
 NCU_PREDICT_DRAM_BYTES = 108.822557e9 + 6.737815e9
 NCU_PREDICT_SOURCE = "profiles/r01h_predict_kernel.md"
 I8_SLICES = 6                     # slice count gp2d_fit picks at the conditioning of configs[1] / configs[2] / configs[4]
@@ -241,6 +241,18 @@ def potri_launches(nb, need_inv=True):
     return potri_launches(n1, True) + 2 + potri_launches(nb - n1, need_inv) + (2 if need_inv else 0)
 
 
+def i8_counters():
+    """Slice products / stages / dense k-steps / launches of the int8 predictive kernel since the last call (device counters)."""
+    import ctypes as C
+    from gp2d_b200._lib import lib
+    buf = (C.c_ulonglong * 4)()
+    lib.gp2d_dbg_i8_counters.restype = C.c_int
+    lib.gp2d_dbg_i8_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+    if lib.gp2d_dbg_i8_counters(buf) != 0:
+        raise RuntimeError("gp2d_dbg_i8_counters failed")
+    return [int(v) for v in buf]
+
+
 def bf16_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
@@ -297,6 +309,7 @@ def run_configs2(torch, dist, gp, gdist, syn, rank, world, dev, peak_tf):
         m.fit_async(alpha_out=alpha)
     e1 = ev()
     gdist.broadcast_fit(m, src=0)
+    i8_counters()                 # clear (synchronises: the broadcast has landed on this rank)
     e2 = ev()
     mean, var = m.predict(Xsd)
     e3 = ev()
@@ -306,6 +319,10 @@ def run_configs2(torch, dist, gp, gdist, syn, rank, world, dev, peak_tf):
     torch.cuda.synchronize()
     # the receiving ranks sit in the broadcast while rank 0 is still factorising: the transfer itself is
     # rank 0's own broadcast time
+    cnt = i8_counters()            # this rank's grid slice: slice products issued, stages, dense k-steps
+    csum = torch.tensor([float(cnt[0]), float(cnt[2])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(csum)
     t_fit, t_pred, t_g = tmax(e0.elapsed_time(e1)), tmax(e2.elapsed_time(e3)), tmax(e3.elapsed_time(e4))
     t_bc = tmax(e1.elapsed_time(e2) if rank == 0 else 0.0)
     total = tmax(e0.elapsed_time(e4))
@@ -336,8 +353,11 @@ def run_configs2(torch, dist, gp, gdist, syn, rank, world, dev, peak_tf):
             "predict_TFLOPps_aggregate": flops_pred / (t_pred / 1e3) / 1e12,
             "predict_TFLOPps_note": "fp64-equivalent: the algorithmic flops n^2 m + 2 n m of the fp64 product over the time",
             "predict_x_fp64_pipe_peak": flops_pred / (t_pred / 1e3) / 1e12 / (world * peak_tf),
-            "predict_int8_TOPps_aggregate": I8_PRODUCTS * flops_pred / (t_pred / 1e3) / 1e12,
-            "predict_frac_of_int8_peak": I8_PRODUCTS * flops_pred / (t_pred / 1e3) / 1e12 / (world * 2.0 * bf16_peak()),
+            "predict_int8_TOPps_aggregate": 2.0 * 128 * 80 * 32 * float(csum[0].item()) / (t_pred / 1e3) / 1e12,
+            "predict_frac_of_int8_peak": 2.0 * 128 * 80 * 32 * float(csum[0].item()) / (t_pred / 1e3) / 1e12 / (world * 2.0 * bf16_peak()),
+            "predict_int8_note": "int8 ops of the slice products the kernel issued (device counters); identically zero digit slices "
+                                 "are skipped: %.3f of the dense schedule's %d products per k-step were issued"
+                                 % (float(csum[0].item()) / max(1.0, I8_PRODUCTS * float(csum[1].item())), I8_PRODUCTS),
             "total_TFLOPps_aggregate": (flops_pred + flops_fit) / (total / 1e3) / 1e12,
             "total_x_fp64_pipe_peak": (flops_pred + flops_fit) / (total / 1e3) / 1e12 / (world * peak_tf),
             "unsharded_share_of_total": (t_fit + t_bc) / total,
@@ -403,6 +423,7 @@ def run_ours(args):
 
     for i in range(W):
         step(i)
+    i8_counters()                             # clear: count the slice products of the K timed launches only
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -421,6 +442,7 @@ def run_ours(args):
     t_max = float(tt.item())
     value = t_max / (K * world)
     pred_ms = float(np.mean([a.elapsed_time(b) for a, b in pred_ev]))
+    i8_cnt = i8_counters()                    # slice products, stages, k-steps of the dense schedule, launches
 
     # ---- the fp64 tensor-pipe kernel on the same snapshot (GP2D_OPT_PREDICT_I8 = 1): the kernel the int8 path
     # replaces at this conditioning and the only path beyond it; kept in the line so both rooflines are visible ----
@@ -609,7 +631,11 @@ def run_ours(args):
         if i8_slices:
             nprod = i8_slices * (i8_slices + 1) // 2
             i8_peak = 2.0 * bf16_peak()
-            ach8 = nprod * flops_pred / (pred_ms * 1e-3) / 1e12
+            nc = 80 if i8_slices == 6 else 64                     # accumulator columns of the slice-count variant
+            launches = max(1, int(i8_cnt[3]))
+            ops_exec = 2.0 * 128 * nc * 32 * float(i8_cnt[0]) / launches     # int8 ops of the MMAs actually issued, per launch
+            ops_dense = 2.0 * 128 * nc * 32 * nprod * float(i8_cnt[2]) / launches
+            ach8 = ops_exec / (pred_ms * 1e-3) / 1e12
             roofline = {
                 "kernel": "predict_i8_kernel<%d> (fused K* digit-slice generation + %d tcgen05.mma kind::i8 slice products per "
                           "k-step into TMEM + fp64 recombination, mean/variance)" % (i8_slices, nprod),
@@ -619,15 +645,27 @@ def run_ours(args):
                                "no int8 entry; nominal 4500 TOP/s); this pool's own tcgen05 kind::i8 issue-rate probe "
                                "(tools/umma_probe2.cu, N = 256) reads %.0f TOP/s" % (bf16_peak(), I8_PROBE_TOPS),
                 "frac_of_probe_peak": ach8 / I8_PROBE_TOPS,
-                "algorithmic_ops_per_launch": nprod * flops_pred,
-                "algorithmic_ops_note": "%d int8 slice products per fp64 multiply-add of the product (n^2 m + 2 n m flops, SURVEY.md 8d): "
-                                        "slice pairs (i, j), i + j < %d" % (nprod, i8_slices),
+                "algorithmic_ops_per_launch": ops_exec,
+                "algorithmic_ops_note": "int8 ops of the tcgen05.mma instructions the kernel issued (counted on the device, "
+                                        "gp2d_dbg_i8_counters): of the %d slice pairs (i, j), i + j < %d, per k-step of the padded "
+                                        "lower-triangular product, those whose digit slices are not identically zero -- %.3f of the "
+                                        "dense schedule here (%.4g ops; the unpadded n^2 m + 2 n m fp64 flops of SURVEY.md 8d x %d "
+                                        "x 1 int8 op per flop would be %.4g)" % (nprod, i8_slices, ops_exec / max(ops_dense, 1.0),
+                                                                                 ops_dense, nprod, nprod * flops_pred),
+                "slice_products_issued_per_launch": float(i8_cnt[0]) / launches,
+                "stages_issued_per_launch": float(i8_cnt[1]) / launches,
+                "ksteps_dense_per_launch": float(i8_cnt[2]) / launches,
+                "dense_schedule_equivalent": {"achieved": ops_dense / (pred_ms * 1e-3) / 1e12, "unit": "TOP/s",
+                                              "note": "the same time against every slice product of the dense schedule (zero "
+                                                      "slices included): what a kernel without the skip would have to sustain"},
                 "ms_per_launch": pred_ms,
                 "fp64_equivalent": {"achieved": ach, "unit": "TFLOP/s", "fp64_pipe_peak": peak_tf, "x_fp64_pipe_peak": ach / peak_tf,
                                     "speedup_over_fp64_kernel": pred_ms_fp64 / pred_ms},
-                "structural_bound": "an SS-mode MMA re-reads both operand tiles from shared memory: 21 x (4096 + 2560) B read + "
-                                    "6 x 6656 B written per k-step at 128 B/clk/SM = 1404 clk against 840 clk of tensor time, "
-                                    "i.e. at most 0.60 of the int8 issue rate with 80-column accumulators (TMEM holds 6 x 80 columns)",
+                "structural_bound": "measured with tools/umma_probe4.cu on this pool: a kind::i8 MMA at M = 128 costs at least 47 clocks "
+                                    "whatever N (and whether A comes from shared memory or TMEM), 54-55 at N = 80 in SS mode against "
+                                    "40 clocks of tensor time (TMEM holds 6 accumulators x 80 columns, so N cannot grow), and the pipe "
+                                    "queues nothing behind the instruction it executes: 0.73 of the int8 peak is the ceiling of this "
+                                    "tile shape; copies into shared memory, the K* generators and the epilogue share the SM with it",
             }
         else:
             roofline = roofline_fp64
