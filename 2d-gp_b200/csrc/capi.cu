@@ -228,7 +228,7 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
 cudaError_t predict_helm(const void* fit_ws, const FitLayout& L, int N, const HelmParams& hp, const double* Xs, int M,
                          long out_stride, double var_add, double* mean, double* var, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int* gate = nullptr;
-    if (L.i8 && g_i8_mode != 1 && ws_bytes >= predict_i8_scratch_bytes(L.npad) / predict_max_ctas()) {
+    if (L.i8 && g_i8_mode != 1 && ws_bytes >= predict_i8_min_scratch_bytes(L.npad)) {
         gate = at<int>(fit_ws, L.off_info + GATE_OFF);
         cudaError_t e = predict_fused_i8(at<int8_t>(fit_ws, L.off_Zq), at<double>(fit_ws, L.off_zunit), gate, L.npad,
                                          at<double>(fit_ws, L.off_alpha), at<double>(fit_ws, L.off_X), N, hp, Xs, M, out_stride,

@@ -113,6 +113,7 @@ cudaError_t i8_quantize_lower(const double* Z, long ldz, int npad, double* zunit
                               int batch = 1, long bstride = 0);
 cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st);
 size_t predict_i8_scratch_bytes(int npad);
+size_t predict_i8_min_scratch_bytes(int npad);      // below this the fp64 kernel takes the call
 void set_i8_debug(int v);                // bring-up timing experiments, per host thread
 // launches the kernel of every slice count (only_s = 0) or of one; a kernel whose count is not *gate returns at once
 cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* gate, int npad, const double* alpha_int,

@@ -47,6 +47,9 @@ constexpr int I8_GSLOTS = 4;                         // k-steps a CTA generates 
 // segments wait in a small per-CTA global buffer.
 constexpr int I8_KSEG = 512;
 constexpr int I8_MAX_NPAD = 65536;
+constexpr size_t I8_PACE_BYTES = 4096;               // head of the scratch: one arrival counter per row block (<= 512)
+constexpr int I8_PACE_WINDOW = 2;                    // row blocks a CTA may be ahead of the slowest one
+constexpr long long I8_PACE_LIMIT = 400000;          // clocks a CTA waits for the others at most (pacing is best effort)
 
 
 // Bring-up watchdog (-DGP2D_I8_WATCHDOG): a wait that does not complete within ~2 s records who was waiting on what
@@ -106,6 +109,23 @@ constexpr unsigned H_EXIT = 1u << 27;         // no work: the issuer that did no
 // per CTA and launch): slice products issued (MMAs), stages issued, k-steps visited (= stages of the dense schedule).
 __device__ unsigned long long g_i8_count[4];
 
+// bulk copy with an L2 eviction priority: Zq tiles are re-read by every CTA (keep), panel tiles are read once (stream)
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                     smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+
 template <int S, int NC>
 struct I8Cfg {
     static constexpr int NG = NC / 2;                 // grid points per column tile
@@ -157,9 +177,10 @@ struct PredictI8Args {
     uint8_t* scratch;             // per CTA: 2 panels
     size_t panel_bytes, cta_bytes, lead_off;     // a panel: digit slices, then at lead_off one byte per k-step (leading all-zero slices)
     int ntiles;
+    int* pace;                    // [npad / 128] row-block arrival counters of this launch (zeroed), or null: see the producer
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
     int dbg;                      // bring-up knobs: 8 = copy and multiply the all-zero slices too (same results bit for bit);
-                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies
+                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies; 64 no pacing, 128 pacing whatever the size
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -338,8 +359,8 @@ __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const He
         for (int p = 0; p < S; ++p) {
             // slice index S - 1 - p (most significant first); columns 2g, 2g+1 are adjacent 16-byte rows of the image
             uint4* d = reinterpret_cast<uint4*>(dst + (S - 1 - p) * btile + h * 128);
-            d[0] = make_uint4(wa[p][0], wa[p][1], wa[p][2], wa[p][3]);
-            d[1] = make_uint4(wb[p][0], wb[p][1], wb[p][2], wb[p][3]);
+            __stcs(d, make_uint4(wa[p][0], wa[p][1], wa[p][2], wa[p][3]));        // read once, by a bulk copy: do not keep in L2
+            __stcs(d + 1, make_uint4(wb[p][0], wb[p][1], wb[p][2], wb[p][3]));
         }
     }
 }
@@ -593,6 +614,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             long fills = 0, segs = 0;
             unsigned long long n_mma = 0, n_stage = 0, n_kstep = 0;
             const bool noskip = (p.dbg & (8 | 4)) != 0;
+            const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
             // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products)
             auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, int a, int b, unsigned flags) {
                 if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
@@ -612,8 +634,8 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     } else {
                         const unsigned abytes = (unsigned)(S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(S - b) * C::BTILE;
                         mbar_arrive_expect_tx(fb, abytes + bbytes);
-                        bulk_g2s(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb);
-                        bulk_g2s(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb);
+                        bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
+                        bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb, pol_stream);
                     }
                 }
                 __syncwarp();
@@ -630,6 +652,27 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 const volatile uint8_t* plead = pb + p.lead_off;
                 const unsigned item_flags = b ? H_ITEMPAR : 0u;
                 for (int rb = 0; rb < nb; ++rb) {
+                    // Pacing.  Every CTA walks the same row blocks of Zq, once per column tile.  When Zq is larger than
+                    // the L2 and the CTAs drift apart, each of them streams it from HBM by itself (N = 8192: 0.8 GB per
+                    // column tile, the kernel is HBM bound); kept within a window of row blocks of each other they share
+                    // one pass through the L2.  A CTA counts itself in at row block rb and waits, for a bounded time,
+                    // until every CTA has reached row block rb - window of this round of column tiles.
+                    if (p.pace) {
+                        if (lane == 0) atomicAdd(p.pace + rb, 1);
+                        if (rb >= I8_PACE_WINDOW) {
+                            const long need_l = (long)(it + 1) * (long)gridDim.x;
+                            const int need = need_l < (long)p.ntiles ? (int)need_l : p.ntiles;
+                            const volatile int* pc = p.pace + (rb - I8_PACE_WINDOW);
+                            const long long t0 = clock64();
+                            for (;;) {
+                                int seen = 0;
+                                if (lane == 0) seen = *pc;
+                                seen = __shfl_sync(0xffffffffu, seen, 0);
+                                if (seen >= need || clock64() - t0 > I8_PACE_LIMIT) break;
+                                __nanosleep(256);
+                            }
+                        }
+                    }
                     const size_t kbase = (size_t)2 * rb * (rb + 1);
                     const int8_t* za = p.Zq + kbase * (size_t)(I8_SMAX * I8_ATILE_BYTES);
                     const uint8_t* zl = p.zlead + kbase;
@@ -785,9 +828,13 @@ static size_t i8_panel_bytes(int npad) {
 }
 template <int S, int NC>
 static size_t i8_cta_bytes(int npad) { return 2 * i8_panel_bytes<S, NC>(npad); }
+size_t predict_i8_min_scratch_bytes(int npad) {          // one CTA
+    const size_t a = i8_cta_bytes<6, 80>(npad), b = i8_cta_bytes<7, 64>(npad);
+    return I8_PACE_BYTES + (a > b ? a : b);
+}
 size_t predict_i8_scratch_bytes(int npad) {
     const size_t a = i8_cta_bytes<6, 80>(npad), b = i8_cta_bytes<7, 64>(npad);
-    return (size_t)predict_max_ctas() * (a > b ? a : b);
+    return I8_PACE_BYTES + (size_t)predict_max_ctas() * (a > b ? a : b);
 }
 
 template <int S, int NC>
@@ -810,14 +857,18 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     a.panel_bytes = i8_panel_bytes<S, NC>(a.npad);
     a.lead_off = i8_panel_lead_off<S, NC>(a.npad);
     a.cta_bytes = i8_cta_bytes<S, NC>(a.npad);
-    a.scratch = scratch;
+    if (scratch_bytes < I8_PACE_BYTES) return cudaErrorInvalidValue;
+    a.scratch = scratch + I8_PACE_BYTES;
     long grid = a.ntiles;
     if (grid > predict_max_ctas()) grid = predict_max_ctas();
-    const long panels = (long)(scratch_bytes / a.cta_bytes);
+    const long panels = (long)((scratch_bytes - I8_PACE_BYTES) / a.cta_bytes);
     if (grid > panels) grid = panels;
     if (grid <= 0) return cudaErrorInvalidValue;
     const long per = (a.ntiles + grid - 1) / grid;
     grid = (a.ntiles + per - 1) / per;
+    // pacing pays when the S slices of Z do not fit the L2 beside the panel stream and there are CTAs to keep together
+    const bool big = (size_t)S * a.npad * (size_t)a.npad / 2 > ((size_t)64 << 20);
+    a.pace = (((big && !(a.dbg & 64)) || (a.dbg & 128)) && grid > 1) ? reinterpret_cast<int*>(scratch) : nullptr;
     predict_i8_kernel<S, NC><<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
@@ -865,7 +916,9 @@ cudaError_t predict_fused_i8(const int8_t* Zq, const double* zunit, const int* g
     a.dbg = g_i8_dbg;
     // every entry of the 2x2 block is bounded by the prior variance k** (helmholtz.cuh)
     const double kmax = a.kss;
-    cudaError_t e = cudaSuccess;
+    // row-block arrival counters of the pacing (head of the scratch)
+    cudaError_t e = scratch_bytes >= I8_PACE_BYTES ? cudaMemsetAsync(scratch, 0, I8_PACE_BYTES, st) : cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
     if (only_s == 0 || only_s == 6) e = predict_i8_launch<6, 80>(a, kmax, (uint8_t*)scratch, scratch_bytes, st);
     if (e != cudaSuccess) return e;
     if (only_s == 0 || only_s == 7) e = predict_i8_launch<7, 64>(a, kmax, (uint8_t*)scratch, scratch_bytes, st);

@@ -13,6 +13,9 @@ from gp2d_b200._lib import lib                           # noqa: E402
 
 lib.gp2d_dbg_set_i8.restype = C.c_int
 lib.gp2d_dbg_set_i8.argtypes = [C.c_int]
+lib.gp2d_dbg_i8_counters.restype = C.c_int
+lib.gp2d_dbg_i8_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+cnt = (C.c_ulonglong * 4)()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 side = int(sys.argv[2]) if len(sys.argv) > 2 else 320
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 6
@@ -32,6 +35,10 @@ for dbg in [int(a) for a in (sys.argv[4].split(",") if len(sys.argv) > 4 else "0
         a.record(); m.predict(Xsd); b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    print("dbg %2d: %7.2f ms   %s" % (dbg, min(ts), " + ".join(v for k, v in names.items() if dbg & k) or "production"), flush=True)
+    lib.gp2d_dbg_i8_counters(cnt)
+    L = max(1, cnt[3])
+    print("dbg %2d: %8.2f ms   %-40s per launch: %.4g slice products, %.4g stages, %.4g k-steps (%.1f products / stage, %.3f of the k-steps live)" %
+          (dbg, min(ts), " + ".join(v for k, v in names.items() if dbg & k) or "production", cnt[0] / L, cnt[1] / L, cnt[2] / L,
+           cnt[0] / max(1, cnt[1]), cnt[1] / max(1, cnt[2])), flush=True)
 lib.gp2d_dbg_set_i8(0)
 gp.set_predict_i8(0)
