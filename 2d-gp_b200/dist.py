@@ -28,6 +28,17 @@ def shard_range(n, rank, world_size, align=64):
     return min(lo_u * align, n), min(hi_u * align, n)
 
 
+def shard_cyclic(n, rank, world_size, block=320):
+    """Block-cyclic share of n grid points for ``rank``: blocks of ``block`` points (whole column tiles of both
+    predictive kernels: 40 and 64 points) dealt round robin.  The cost of a column tile is far from uniform -- the
+    product Z K* is lower triangular, so a tile whose covariances concentrate on early observations meets a non-zero
+    K* slice in every row block below them, one at the far end in the last few only (with the zero-slice skip of
+    predict_i8.cu contiguous halves of the configs[2] grid split the work 2 : 1) -- and interleaving evens it out."""
+    blocks = np.arange(rank, -(-n // block), world_size, dtype=np.int64)
+    idx = (blocks[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < n]
+
+
 def round_robin(n, rank, world_size):
     """Indices rank, rank+world, ... : restarts and snapshots."""
     return list(range(rank, n, world_size))
@@ -64,25 +75,33 @@ def broadcast_fit(gp, src=0, chunk_bytes=1 << 30):
 
 
 def predict_sharded(gp, Xs, include_noise=False, refined=None):
-    """Grid-sharded prediction: rank r predicts its contiguous tile-aligned slice with the
+    """Grid-sharded prediction: rank r predicts its block-cyclic share of the grid (shard_cyclic) with the
     fit state it holds (every rank fits the same snapshot, or receives it by broadcast), then
-    mean/var shards are all-gathered.  Returns (mean[2M], var[2M]) on every rank.  ``refined``:
+    mean/var shards are all-gathered and put back in grid order.  Returns (mean[2M], var[2M]) on every rank
+    (the same bits as one rank predicting the whole grid: the kernels are partition invariant).  ``refined``:
     None takes the iterated solve for ill-conditioned covariances (engine.refined_predict), like
     GPRegression.predict; True / False force it."""
     rank, ws = world()
     Xs = np.asarray(Xs, dtype=np.float64) if not isinstance(Xs, torch.Tensor) else Xs
     M = Xs.shape[0]
-    lo, hi = shard_range(M, rank, ws)
     if refined is None:
         refined = hasattr(gp, "cond_bound") and gp.cond_bound() > ROBUST_COND
     fn = gp.predict_refined if refined else gp.predict
-    mean, var = fn(Xs[lo:hi], include_noise=include_noise)
-    m = hi - lo
     if ws == 1:
-        return mean, var
-    mu0, mu1 = gather_concat(mean[:m].contiguous()), gather_concat(mean[m:].contiguous())
-    v0, v1 = gather_concat(var[:m].contiguous()), gather_concat(var[m:].contiguous())
-    return torch.cat([mu0, mu1]), torch.cat([v0, v1])
+        return fn(Xs, include_noise=include_noise)
+    idx = shard_cyclic(M, rank, ws)
+    sel = torch.as_tensor(idx, device=Xs.device) if isinstance(Xs, torch.Tensor) else idx
+    mean, var = fn(Xs[sel], include_noise=include_noise)
+    m = idx.shape[0]
+    # shards arrive concatenated in rank order: scatter them back to grid order
+    order = torch.as_tensor(np.concatenate([shard_cyclic(M, r, ws) for r in range(ws)]), device=mean.device)
+    out = []
+    for t in (mean, var):
+        full = torch.empty(2 * M, dtype=t.dtype, device=t.device)
+        full[order] = gather_concat(t[:m].contiguous())
+        full[M + order] = gather_concat(t[m:].contiguous())
+        out.append(full)
+    return out[0], out[1]
 
 
 def gather_best(model):

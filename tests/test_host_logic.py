@@ -179,6 +179,19 @@ def test_synthetic_snapshot_is_seeded_and_shaped():
 # ---- sharding arithmetic --------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 1000, 102400, 1000000])
 @pytest.mark.parametrize("ws", [1, 2, 3, 8])
+def test_shard_cyclic_is_a_partition_in_whole_blocks(n, ws):
+    parts = [gdist.shard_cyclic(n, r, ws) for r in range(ws)]
+    allidx = np.sort(np.concatenate(parts))
+    np.testing.assert_array_equal(allidx, np.arange(n))               # every point exactly once
+    for r, p in enumerate(parts):
+        assert np.all(np.diff(p) > 0)
+        assert np.all((p // 320) % ws == r)                            # whole 320-point blocks, dealt round robin
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= 320
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 1000, 102400, 1000000])
+@pytest.mark.parametrize("ws", [1, 2, 3, 8])
 def test_shard_range_partitions_whole_tiles(n, ws):
     parts = [gdist.shard_range(n, r, ws) for r in range(ws)]
     assert parts[0][0] == 0 and parts[-1][1] == n
@@ -253,8 +266,8 @@ def _worker(rank, world, port, out_dir):
         # variable-length gather
         loc = torch.arange(3 + 2 * rank, dtype=torch.float64) + 100 * rank
         got = gdist.gather_concat(loc)
-        # grid-sharded prediction: 200 points -> rank 0 gets [0,128), rank 1 [128,200)
-        Xs = np.stack([np.linspace(0, 1, 200), np.linspace(2, 3, 200)], axis=1)
+        # grid-sharded prediction: 900 points in 320-point blocks -> rank 0 gets blocks 0 and 2, rank 1 block 1
+        Xs = np.stack([np.linspace(0, 1, 900), np.linspace(2, 3, 900)], axis=1)
         mean, var = gdist.predict_sharded(_FakeGP(), Xs, include_noise=True)
         # restart sharding: each rank holds its own runs, the best one wins everywhere
         runs = [_Run(5.0 - rank * 3.0 + i, [rank, i, 7.0]) for i in range(2)]
@@ -291,7 +304,7 @@ def test_gloo_world2_gathers(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r = [np.load(str(tmp_path / ("r%d.npz" % k))) for k in range(2)]
-    Xs = np.stack([np.linspace(0, 1, 200), np.linspace(2, 3, 200)], axis=1)
+    Xs = np.stack([np.linspace(0, 1, 900), np.linspace(2, 3, 900)], axis=1)
     m_ref, v_ref = _FakeGP().predict(Xs, include_noise=True)
     for k in range(2):
         np.testing.assert_array_equal(r[k]["got"], np.concatenate([np.arange(3.0), np.arange(5.0) + 100]))
