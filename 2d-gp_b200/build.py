@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgp2d.so")
-SOURCES = ["capi.cu", "linalg.cu", "kernel_build.cu", "predict.cu", "predict_i8.cu", "grad.cu"]
+SOURCES = ["capi.cu", "linalg.cu", "kernel_build.cu", "predict.cu", "predict_i8.cu", "grad.cu", "order.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 if os.environ.get("GP2D_I8_WATCHDOG"):           # bring-up: bounded waits in the int8 predictive kernel (predict_i8.cu)

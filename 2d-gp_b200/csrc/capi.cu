@@ -19,6 +19,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct FitLayout {
     int npad;
     size_t off_A, off_Z, off_Zt, off_logdiag, off_yint, off_w, off_r, off_alpha, off_partial, off_X, off_scal, off_info, total;
+    size_t off_perm;              // spatial order of the observations inside the fit (order.cu), order_n ints
+    int order_n;                  // number of points when the fit sorts them, else 0
     size_t off_Zq, off_zunit;     // int8 digit slices of Z and their row units (Helmholtz layouts; 0 bytes otherwise)
     int i8;                       // the layout carries them
 };
@@ -26,7 +28,7 @@ constexpr size_t GATE_OFF = 2 * sizeof(int);     // int after info in the off_in
 
 // n: scalar observations; x_doubles: size of the copy of the observation points;
 // grad_doubles: partial-sum doubles the likelihood-gradient reduction needs
-FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doubles, bool i8 = false) {
+FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doubles, bool i8 = false, int order_pts = 0) {
     FitLayout L;
     L.npad = round_up((int)n_scalar, TILE);
     const size_t n = (size_t)L.npad, d = sizeof(double);
@@ -42,11 +44,16 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
     size_t part = nchunks * n;
     if (grad_doubles > part) part = grad_doubles;
     L.off_partial = o; o = align256(o + part * d);
+    L.order_n = 0;
+    L.off_perm = 0;
     // what gp2d_predict reads, contiguous so that it can be shipped to another GPU in one piece
     L.off_Zt = o; o = align256(o + packed_tiles_doubles(L.npad) * d);
     L.i8 = i8 && L.npad <= i8_max_npad();
+    // the sort serves the zero-slice skip of the int8 predictive kernel; below a few row blocks there is nothing to skip
+    if (L.i8 && order_pts >= 256 && order_pts <= spatial_order_max_points()) L.order_n = order_pts;
     L.off_Zq = o; o = align256(o + (L.i8 ? i8_zq_bytes(L.npad) : 0));
     L.off_zunit = o; o = align256(o + (L.i8 ? n * d : 0));
+    L.off_perm = o; o = align256(o + (size_t)L.order_n * sizeof(int));
     L.off_alpha = o; o = align256(o + n * d);
     L.off_X = o; o = align256(o + x_doubles * d);
     L.off_scal = o; o = align256(o + 32 * d);
@@ -58,7 +65,7 @@ FitLayout fit_layout_general(size_t n_scalar, size_t x_doubles, size_t grad_doub
 // ldx = 2: points (a, b); ldx = 3: space-time points (t, a, b)
 FitLayout fit_layout(int N, int ldx = 2) {
     return fit_layout_general(2 * (size_t)N, (size_t)ldx * N,
-                              (HELM_NP + 1) * (size_t)lml_grad_partials(round_up(2 * N, TILE)), /*i8=*/true);
+                              (HELM_NP + 1) * (size_t)lml_grad_partials(round_up(2 * N, TILE)), /*i8=*/true, /*order_pts=*/N);
 }
 
 FitLayout rbf_layout(int N, int D) {
@@ -192,14 +199,26 @@ __global__ void unpad_symmetric_kernel(const double* __restrict__ P, int npad, d
     }
 }
 
+// the fit's permutation of the observations (null: caller's order)
+inline const int* perm_of(const void* ws, const FitLayout& L) { return L.order_n ? at<int>(ws, L.off_perm) : nullptr; }
+
+// observations into the fit state: in Z-order when the layout says so (order.cu), as given otherwise
+cudaError_t stage_points(const double* X, int ldx, int xo, int N, void* ws, const FitLayout& L, cudaStream_t st) {
+    if (!L.order_n) return cudaMemcpyAsync(at<double>(ws, L.off_X), X, (size_t)ldx * N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = spatial_order(X, ldx, xo, N, at<int>(ws, L.off_perm), st);
+    if (e != cudaSuccess) return e;
+    return gather_points(X, ldx, N, at<int>(ws, L.off_perm), at<double>(ws, L.off_X), st);
+}
+
 // fit core shared by gp2d_fit and gp2d_lml_grad
 cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& hp, double diag_add,
                      void* ws, const FitLayout& L, cudaStream_t st) {
     double* A = at<double>(ws, L.off_A);
     double* Z = at<double>(ws, L.off_Z);
     cudaError_t e;
-    e = cudaMemcpyAsync(at<double>(ws, L.off_X), X, (size_t)hp.ldx * N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    e = stage_points(X, hp.ldx, hp.xo, N, ws, L, st);
     if (e != cudaSuccess) return e;
+    X = at<double>(ws, L.off_X);                  // from here on the observations in the fit's own order
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);
     if (e != cudaSuccess) return e;
     const int refine = refine_steps_for(hp.tvar * (hp.w_df + hp.w_cf), 2L * N, diag_add);
@@ -216,7 +235,7 @@ cudaError_t fit_core(const double* X, int N, const double* y, const HelmParams& 
     }
     e = solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws, L.off_yint), at<double>(ws, L.off_w),
                         at<double>(ws, L.off_alpha), at<double>(ws, L.off_partial),
-                        at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st);
+                        at<double>(ws, L.off_logdiag), at<double>(ws, L.off_scal), st, 1, 0, 0, perm_of(ws, L), 0);
     if (e != cudaSuccess || !refine) return e;
     e = build_interleaved_lower(X, N, hp, diag_add, A, L.npad, L.npad, st);      // A held the factor: the matrix again
     if (e != cudaSuccess) return e;
@@ -405,7 +424,7 @@ int gp2d_fit(const double* X, int N, const double* y, double l_df, double l_cf, 
     cudaError_t e = fit_core(X, N, y, make_helm(l_df, l_cf, ratio), noise + jitter, ws, L, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (alpha_out) {
-        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st);
+        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st, 1, 0, perm_of(ws, L), 0);
         if (e != cudaSuccess) return cuda_rc(e);
     }
     if (lml_out) {
@@ -550,9 +569,15 @@ cudaError_t fit_core_batched(const double* X, long x_stride, int N, const double
                                  X + (long)c0 * x_stride, x_stride, 2 * N, at<double>(ws0, L.off_X) + (long)c0 * bs, st);
     }
     if (e != cudaSuccess) return e;
+    if (L.order_n) {      // every problem sorts its own observations (the same order for shared data), as fit_core does
+        e = spatial_order(X, 2, 0, N, at<int>(ws0, L.off_perm), st, nb, x_stride, 2 * bs);
+        if (e != cudaSuccess) return e;
+        e = gather_points(X, 2, N, at<int>(ws0, L.off_perm), at<double>(ws0, L.off_X), st, nb, x_stride, 2 * bs, bs);
+        if (e != cudaSuccess) return e;
+    }
     double* A = at<double>(ws0, L.off_A);
     double* Z = at<double>(ws0, L.off_Z);
-    e = build_interleaved_lower_batched(X, x_stride, N, par, A, L.npad, L.npad, nb, bs, st);
+    e = build_interleaved_lower_batched(at<double>(ws0, L.off_X), bs, N, par, A, L.npad, L.npad, nb, bs, st);
     if (e != cudaSuccess) return e;
     e = potri_lower(A, L.npad, Z, L.npad, L.npad, at<double>(ws0, L.off_logdiag), at<int>(ws0, L.off_info),
                     /*need_inv=*/true, /*keep_L=*/false, nullptr, st, 0, nb, bs);
@@ -571,7 +596,7 @@ cudaError_t fit_core_batched(const double* X, long x_stride, int N, const double
     }
     return solve_alpha_lml(Z, L.npad, L.npad, N, 2, y, at<double>(ws0, L.off_yint), at<double>(ws0, L.off_w),
                            at<double>(ws0, L.off_alpha), at<double>(ws0, L.off_partial), at<double>(ws0, L.off_logdiag),
-                           at<double>(ws0, L.off_scal), st, nb, y_stride, bs);
+                           at<double>(ws0, L.off_scal), st, nb, y_stride, bs, perm_of(ws0, L), 2 * bs);
 }
 
 // shared driver of gp2d_fit_batched / gp2d_lml_grad_batched: runs of consecutive plain-mode problems go
@@ -614,7 +639,7 @@ int run_batch(bool grad, const double* X, int64_t x_stride, int N, const double*
                                         at<double>(ws0, L.off_scal) + 1, nb, bs, st);
             if (e != cudaSuccess) break;
         } else if (alpha_out) {
-            e = deinterleave(at<double>(ws0, L.off_alpha), N, alpha_out + (size_t)2 * N * b0, st, nb, bs);
+            e = deinterleave(at<double>(ws0, L.off_alpha), N, alpha_out + (size_t)2 * N * b0, st, nb, bs, perm_of(ws0, L), 2 * bs);
             if (e != cudaSuccess) break;
         }
         gather_batch_out_kernel<<<(nb + 127) / 128, 128, 0, st>>>(at<double>(ws0, L.off_scal), at<int>(ws0, L.off_info), bs,
@@ -737,7 +762,7 @@ int gp2d_st_fit(const double* X3, int N, const double* y, double l_df, double l_
     cudaError_t e = fit_core(X3, N, y, make_helm_st(l_df, l_cf, ratio, tvar, lt), noise + jitter, ws, L, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (alpha_out) {
-        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st);
+        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st, 1, 0, perm_of(ws, L), 0);
         if (e != cudaSuccess) return cuda_rc(e);
     }
     if (lml_out) {
@@ -1081,7 +1106,7 @@ int gp2d_hsum_fit(const double* X, int N, int ldx, const double* y, int Q, const
     cudaError_t e = hsum_fit_core(X, N, y, sp, noise + jitter, ws, L, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (alpha_out) {
-        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st);
+        e = deinterleave(at<double>(ws, L.off_alpha), N, alpha_out, st, 1, 0, perm_of(ws, L), 0);
         if (e != cudaSuccess) return cuda_rc(e);
     }
     if (lml_out) {

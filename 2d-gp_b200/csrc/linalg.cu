@@ -444,27 +444,31 @@ cudaError_t pack_lower_tiles(const double* Z, long ldz, int npad, double* Zt, cu
 // vectors: y -> interleaved, w = Z y, alpha = Z^T w, LML
 // ------------------------------------------------------------------------------------
 // ncomp = 2: stacked [u; v] -> pair-interleaved; ncomp = 1: scalar observations, zero padded
+// perm (optional): internal observation i is the caller's observation perm[i] (order.cu)
 __global__ void interleave_kernel(const double* __restrict__ y, int N, int ncomp, double* __restrict__ yi, int npad,
-                                  long y_bstride, long bstride) {
+                                  long y_bstride, long bstride, const int* __restrict__ perm, long p_bstride) {
     y += (long)blockIdx.y * y_bstride;
     yi += (long)blockIdx.y * bstride;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npad) return;
     if (ncomp == 2) {
         int i = p >> 1, c = p & 1;
-        yi[p] = (i < N) ? y[(long)c * N + i] : 0.0;
+        if (i < N && perm) i = perm[(long)blockIdx.y * p_bstride + i];
+        yi[p] = ((p >> 1) < N) ? y[(long)c * N + i] : 0.0;
     } else {
         yi[p] = (p < N) ? y[p] : 0.0;
     }
 }
 
-__global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double* __restrict__ x, long bstride) {
+__global__ void deinterleave_kernel(const double* __restrict__ xi, int N, double* __restrict__ x, long bstride,
+                                    const int* __restrict__ perm, long p_bstride) {
     xi += (long)blockIdx.y * bstride;
     x += (long)blockIdx.y * 2 * N;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 2 * N) return;
     int c = p / N, i = p - c * N;
-    x[p] = xi[2 * i + c];
+    const int dst = perm ? perm[(long)blockIdx.y * p_bstride + i] : i;
+    x[(long)c * N + dst] = xi[2 * i + c];
 }
 
 // w[i] = sum_{k<=i} Z[i][k] y[k]; one warp per row
@@ -580,9 +584,9 @@ cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, i
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st, int batch, long y_bstride,
-                            long bstride) {
-    if (batch == 1) bstride = y_bstride = 0;
-    interleave_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, st>>>(y_block, N, ncomp, y_int, npad, y_bstride, bstride);
+                            long bstride, const int* perm, long p_bstride) {
+    if (batch == 1) bstride = y_bstride = p_bstride = 0;
+    interleave_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, st>>>(y_block, N, ncomp, y_int, npad, y_bstride, bstride, perm, p_bstride);
     trmv_lower_kernel<<<dim3((npad + 7) / 8, batch), 256, 0, st>>>(Z, ldz, y_int, w, npad, bstride);
     int nchunks = (npad + TRMVT_ROWS - 1) / TRMVT_ROWS;
     trmvT_partial_kernel<<<dim3(npad / 128, nchunks, batch), 128, 0, st>>>(Z, ldz, w, partial, npad, bstride);
@@ -591,8 +595,8 @@ cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncom
     return cudaGetLastError();
 }
 
-cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch, long bstride) {
-    deinterleave_kernel<<<dim3((2 * N + 255) / 256, batch), 256, 0, st>>>(xi, N, x, batch > 1 ? bstride : 0);
+cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch, long bstride, const int* perm, long p_bstride) {
+    deinterleave_kernel<<<dim3((2 * N + 255) / 256, batch), 256, 0, st>>>(xi, N, x, batch > 1 ? bstride : 0, perm, batch > 1 ? p_bstride : 0);
     return cudaGetLastError();
 }
 

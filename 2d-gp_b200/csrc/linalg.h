@@ -29,12 +29,22 @@ void set_potri_overlap(bool on);      // bring-up switch: side-stream overlap of
 cudaError_t solve_alpha_lml(const double* Z, long ldz, int npad, int N, int ncomp, const double* y_block,
                             double* y_int, double* w, double* alpha_int, double* partial,
                             const double* logdiag, double* lml_out, cudaStream_t st, int batch = 1, long y_bstride = 0,
-                            long bstride = 0);
+                            long bstride = 0, const int* perm = nullptr, long p_bstride = 0);
 // robust mode: alpha += Z^T Z (y - K alpha), `steps` times; K = lower tiles of the padded covariance,
 // t1 / t2 scratch vectors of npad doubles (t1 may be the w of solve_alpha_lml: it is not needed afterwards)
 cudaError_t refine_alpha(const double* K, long ldk, const double* Z, long ldz, int npad, const double* y_int,
                          double* t1, double* t2, double* alpha_int, double* partial, int steps, cudaStream_t st);
-cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch = 1, long bstride = 0);
+// perm (optional, order.cu): internal observation i is the caller's observation perm[i]; batch b at perm + b p_bstride
+cudaError_t deinterleave(const double* xi, int N, double* x, cudaStream_t st, int batch = 1, long bstride = 0,
+                         const int* perm = nullptr, long p_bstride = 0);
+// Z-order (Morton) permutation of N <= spatial_order_max_points() points by the coordinates in columns xo, xo + 1 of
+// X[N][ldx]; gather_points writes X in that order.  batch: problem b at X + b x_bstride, perm + b p_bstride (ints),
+// out + b o_bstride.
+int spatial_order_max_points();
+cudaError_t spatial_order(const double* X, int ldx, int xo, int N, int* perm, cudaStream_t st, int batch = 1, long x_bstride = 0,
+                          long p_bstride = 0);
+cudaError_t gather_points(const double* X, int ldx, int N, const int* perm, double* out, cudaStream_t st, int batch = 1,
+                          long x_bstride = 0, long p_bstride = 0, long o_bstride = 0);
 // Tile-major, pre-swizzled copy of the lower triangle of Z (what predict_fused streams with
 // bulk copies): tile (row block li, k-tile kt) is number 8 li (li+1)/2 + kt, 2048 doubles each.
 size_t packed_tiles_doubles(int npad);

@@ -134,8 +134,18 @@ struct I8Cfg {
     static constexpr int GT = NG * GSLOTS;            // generator threads: (grid point, k-step slot)
     static constexpr int EPI_WARPS = 8;               // two per TMEM lane quarter: column halves
     static constexpr int MMA_WARPS = 2;               // the tensor pipe idles whenever its issuing warp does anything else: two take turns
-    static constexpr int GEN0 = 32 * (EPI_WARPS + 1 + MMA_WARPS);   // first generator thread
-    static constexpr int THREADS = GEN0 + GT;
+    static constexpr int THREADS = 32 * (EPI_WARPS + 1 + MMA_WARPS) + GT;
+    // Roles by warp.  A warp's scheduler (and its TMEM lane quarter) is warp % 4.  The issuers are latency critical
+    // (the tensor pipe waits for them), so both sit on scheduler 0, which they share with two epilogue warps only; the
+    // generators, which run long fp64 sequences, and the producer take the warps of the other three schedulers.
+    static constexpr int ISSUER0 = EPI_WARPS, ISSUER1 = EPI_WARPS + 4;
+    static constexpr int GEN_WARPS = GT / 32;
+    static constexpr int PRODUCER = (GEN_WARPS == 5) ? 15 : 14;
+    static_assert(GEN_WARPS == 4 || GEN_WARPS == 5, "role table");
+    // generator warp index of a warp (9, 10, 11, 13, 14 -> 0 .. 4), -1 for the others
+    __host__ __device__ static constexpr int gen_index(int w) {
+        return (w == 9) ? 0 : (w == 10) ? 1 : (w == 11) ? 2 : (w == 13) ? 3 : (w == 14 && GEN_WARPS == 5) ? 4 : -1;
+    }
     static constexpr int HC = NC / 2;                 // accumulator columns per epilogue warp
     static constexpr int BTILE = NC * I8_KSTEP;       // bytes of one B slice tile
     static constexpr int STAGE_BYTES = S * (I8_ATILE_BYTES + BTILE);
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     }
     if (tid < (int)(sizeof(HelmParams) / sizeof(double))) sh_par[tid] = reinterpret_cast<const double*>(&p.hp)[tid];
     if (tid >= 64 && tid < 80) sh_or[tid - 64] = 0ull;
-    if (warp == C::EPI_WARPS + 1) tmem_alloc(tslot, C::TMEM_COLS);     // the first MMA warp
+    if (warp == C::ISSUER0) tmem_alloc(tslot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -601,7 +611,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             __syncwarp();
             named_barrier(1, 32 * C::EPI_WARPS);
         }
-    } else if (warp == C::EPI_WARPS) {
+    } else if (warp == C::PRODUCER) {
         // ------------------------------ producer / scheduler ----------------------------------------
         // The whole warp walks the k-steps: lane l reads the leading-zero-slice bytes of k-step base + l of the Z row
         // block and of the panel.  A k-step whose non-zero slices cannot meet (a + b >= S) is dropped; of the others
@@ -729,7 +739,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 if (blockIdx.x == 0) atomicAdd(&g_i8_count[3], 1ull);
             }
         }
-    } else if (warp <= C::EPI_WARPS + C::MMA_WARPS) {
+    } else if (warp == C::ISSUER0 || warp == C::ISSUER1) {
         // ------------------------------ MMA issuers -----------------------------------------------
         // The tensor pipe takes one MMA at a time from a warp and queues nothing: every instruction its issuing warp
         // spends between two MMAs (waiting for the next stage, reading its header, the commit) is time the pipe idles
@@ -740,7 +750,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
         // issued (first_done), and both warps commit to acc_full / arrive on panel_empty when their part is done.
         // Each warp walks the loop whole (descriptors are warp-uniform); one elected lane issues.
         {
-            const int w = warp - (C::EPI_WARPS + 1);
+            const int w = warp == C::ISSUER0 ? 0 : 1;
             const unsigned ring_lo = i8_desc_lo(smem_u32(ring));
             const bool nomma = (p.dbg & 16) != 0;
             for (long n = w;; n += C::MMA_WARPS) {
@@ -775,7 +785,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
         }
     } else {
         // ------------------------------ generators ------------------------------------------------
-        const int gtid = tid - C::GEN0;
+        const int gtid = C::gen_index(warp) * 32 + lane;
         const HelmParams& hp = *reinterpret_cast<const HelmParams*>(sh_par);
         int it = 0;
         for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
@@ -815,7 +825,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == C::EPI_WARPS + 1) tmem_dealloc(tbase, C::TMEM_COLS);
+    if (warp == C::ISSUER0) tmem_dealloc(tbase, C::TMEM_COLS);
 }
 
 template <int S, int NC>

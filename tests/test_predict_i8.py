@@ -165,6 +165,41 @@ def test_i8_zero_slice_skipping_is_bitwise_the_dense_schedule(mode, N, side, the
         lib.gp2d_dbg_set_i8(0)
 
 
+def test_fit_orders_the_observations_in_space():
+    """The fit sorts the observations along a Z-order curve (csrc/order.cu): shuffled drifters give the shuffled
+    weights and the same prediction as the ordered ones (to rounding: the elimination order is the same), and the
+    zero-slice skip finds the same work -- without the sort a shuffled snapshot has no zero slice at all."""
+    import ctypes as C
+    from gp2d_b200._lib import lib
+    lib.gp2d_dbg_i8_counters.restype = C.c_int
+    lib.gp2d_dbg_i8_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+    cnt = (C.c_ulonglong * 4)()
+    N = 1500
+    X, y = synthetic.drifter_snapshot(N, config_id=7)
+    Xs = gp.as_dev(synthetic.prediction_grid(X, 64, 50))
+    p = np.random.default_rng(3).permutation(N)
+    Xp, yp = X[p], np.concatenate([y[:N][p], y[N:][p]])
+    gp.set_predict_i8(6)
+    res = []
+    for (Xa, ya) in ((X, y), (Xp, yp)):
+        m = gp.HelmholtzGP(Xa, ya, *THETA, NOISE)
+        a = m.alpha().cpu().numpy()
+        lib.gp2d_dbg_i8_counters(cnt)
+        mean, var = m.predict(Xs)
+        assert lib.gp2d_dbg_i8_counters(cnt) == 0
+        res.append((a, mean.cpu().numpy(), var.cpu().numpy(), int(cnt[0]), int(cnt[2]), m.fit()))
+    a0, m0, v0, prod0, dense0, l0 = res[0]
+    a1, m1, v1, prod1, dense1, l1 = res[1]
+    np.testing.assert_allclose(np.concatenate([a0[:N][p], a0[N:][p]]), a1, rtol=1e-9, atol=1e-11 * np.abs(a0).max())
+    np.testing.assert_allclose(m1, m0, rtol=1e-9, atol=1e-11 * np.abs(m0).max())
+    np.testing.assert_allclose(v1, v0, rtol=1e-9, atol=1e-13)
+    assert abs(l1 - l0) <= 1e-10 * abs(l0)
+    assert dense0 == dense1 and abs(prod1 - prod0) <= 0.02 * prod0       # ties of the raster may fall the other way
+    assert prod0 < 0.9 * 21 * dense0                                     # and there IS something to skip
+    f = orc.fit(Xp, yp, *THETA, NOISE)
+    np.testing.assert_allclose(a1, f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
+
+
 def test_i8_host_entry_point_matches_device_path():
     """gp2d_fit_predict_host (numpy in / out) runs the same kernels as fit + predict on device tensors."""
     X, y = synthetic.drifter_snapshot(500, config_id=2, seed_offset=5)

@@ -4,7 +4,7 @@ A balanced base-256 digit slice of a tile is all zero when every entry of the ti
 its row (Z) or of the panel (K*): entries far from the diagonal of Z = L^-1 and covariances between distant points.
 Counts, for a configuration, the MMAs the int8 predictive kernel would issue if it skipped all-zero slices, for the
 observation order as given and for spatially blocked orders.
-    python tools/sparsity_emulate.py [N] [grid side] [order: none|morton|block4]"""
+    python tools/sparsity_emulate.py [N] [grid side] [order: none|morton|block2|random]"""
 import os
 import sys
 
@@ -42,6 +42,8 @@ elif order.startswith("block"):
     # groups of 16 observations that form compact patches: sort by (patch row, patch column, inside)
     w = float(order[5:] or 2.0)           # patch edge in km
     perm = np.lexsort((X[:, 0], X[:, 1], np.floor(X[:, 0] / w), np.floor(X[:, 1] / w)))
+elif order == "random":
+    perm = np.random.default_rng(1).permutation(N)
 else:
     perm = np.arange(N)
 X = X[perm]; y = np.concatenate([y[:N][perm], y[N:][perm]])
