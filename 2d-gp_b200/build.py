@@ -16,6 +16,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 if os.environ.get("GP2D_I8_WATCHDOG"):           # bring-up: bounded waits in the int8 predictive kernel (predict_i8.cu)
     FLAGS.append("-DGP2D_I8_WATCHDOG")
+if os.environ.get("GP2D_I8_WAITPROF"):           # bring-up: clocks spent per kind of wait in the int8 predictive kernel
+    FLAGS.append("-DGP2D_I8_WAITPROF")
 
 
 def nvcc() -> str:

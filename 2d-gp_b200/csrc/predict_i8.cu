@@ -87,6 +87,22 @@ __device__ __forceinline__ void i8_wait(unsigned long long* bar, unsigned parity
     }
 }
 #define I8_WAIT(bar, parity, tag, info) i8_wait(bar, parity, tag, (unsigned)(info))
+#elif defined(GP2D_I8_WAITPROF)
+// Bring-up profile (-DGP2D_I8_WAITPROF): SM clocks spent in each kind of wait (tag), summed over the warps' first lanes
+__device__ unsigned long long g_i8_waitclk[16];
+__device__ __forceinline__ void i8_wait_prof(unsigned long long* bar, unsigned parity, unsigned tag) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_i8_waitclk[tag & 15], (unsigned long long)(clock64() - t0));
+}
+extern "C" int gp2d_dbg_i8_waitprof(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_i8_waitclk, 16 * sizeof(unsigned long long));
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_i8_waitclk, z, sizeof(z));
+    return 0;
+}
+#define I8_WAIT(bar, parity, tag, info) i8_wait_prof(bar, parity, tag)
 #else
 #define I8_WAIT(bar, parity, tag, info) mbar_wait(bar, parity)
 #endif
@@ -107,7 +123,7 @@ constexpr unsigned H_EXIT = 1u << 27;         // no work: the issuer that did no
 
 // Work counters of the launches so far (statistics for bench.py, read and cleared by gp2d_dbg_i8_counters; one atomic
 // per CTA and launch): slice products issued (MMAs), stages issued, k-steps visited (= stages of the dense schedule).
-__device__ unsigned long long g_i8_count[4];
+__device__ unsigned long long g_i8_count[6];         // + SM clocks from the first to the last stage, summed over the CTAs; CTAs
 
 // bulk copy with an L2 eviction priority: Zq tiles are re-read by every CTA (keep), panel tiles are read once (stream)
 __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
@@ -623,21 +639,19 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             unsigned rph = 0;
             long fills = 0, segs = 0;
             unsigned long long n_mma = 0, n_stage = 0, n_kstep = 0;
+            const long long clk0 = clock64();
             const bool noskip = (p.dbg & (8 | 4)) != 0;
             const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
-            // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products)
-            auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, int a, int b, unsigned flags) {
+            // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products).
+            // w packs the leading-zero counts: a | b << 4.  This warp feeds two issuers that need a stage every ~500
+            // clocks each: the loop is kept lean (scalar state, one shuffle per k-step, no 64-bit modulo).
+            int fi = 0;                                   // fills % NFULL
+            auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, unsigned w, unsigned flags) {
                 if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
-                if (ks >= 0) { const int mm = S - a - b; n_mma += (unsigned)(mm * (mm + 1) / 2); ++n_stage; }
-#ifdef GP2D_I8_WATCHDOG
-                if (ks >= 0 && (a < 0 || b < 0 || a + b >= S || ks >= p.npad / I8_KSTEP)) {
-                    if (lane == 0) g_i8_wd[3] = 0xbad0000000000000ull | ((unsigned long long)(unsigned)a << 40) | ((unsigned long long)(unsigned)b << 32) | (unsigned)ks;
-                    a = 0; b = 0; ks = 0;
-                }
-#endif
+                const int a = (int)(w & 15u), b = (int)(w >> 4);
                 if (lane == 0) {
                     uint8_t* st = ring + rs * C::STAGE_BYTES;
-                    unsigned long long* fb = full + (int)(fills % C::NFULL);
+                    unsigned long long* fb = full + fi;
                     sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
                     if (ks < 0 || (p.dbg & 32)) {
                         mbar_arrive(fb);
@@ -646,10 +660,14 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                         mbar_arrive_expect_tx(fb, abytes + bbytes);
                         bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
                         bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb, pol_stream);
+                        const int mm = S - a - b;
+                        n_mma += (unsigned)(mm * (mm + 1) / 2);
+                        ++n_stage;
                     }
                 }
                 __syncwarp();
                 ++fills;
+                if (++fi == C::NFULL) fi = 0;
                 if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
             };
             bool final_item = false;
@@ -692,51 +710,57 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                         const bool item_last = rb == nb - 1 && ks1 == nks;
                         n_kstep += (unsigned)(ks1 - ks0);
                         // two stages are held back so that the last and the one before it can be told
-                        int pk[2] = {0, 0}, pa[2] = {0, 0}, pbz[2] = {0, 0}, npend = 0, nlive = 0;
-                        unsigned pf[2] = {0u, 0u};
+                        int k0 = 0, k1 = 0, npend = 0;
+                        unsigned w0 = 0, w1 = 0, f0 = 0, f1 = 0;
+                        const unsigned first_flags = item_flags | H_FIRST | (segs > 0 ? H_SEGNZ : 0u) | (((segs - 1) & 1) ? H_SEGPAR : 0u);
+                        const unsigned second_flags = item_flags | H_SECOND | ((segs & 1) ? H_SEGPAR : 0u);
+                        unsigned next_flags = first_flags;
                         for (int base = ks0; base < ks1; base += 32) {
                             const int ks = base + lane;
-                            int a = S, bb = S;
+                            unsigned w = 0xffu;                          // dead
                             if (ks < ks1) {
-                                a = __ldg(zl + ks);
-                                bb = plead[ks];
-                                if (ks == ks0 || noskip) { a = 0; bb = 0; }
+                                const unsigned a = __ldg(zl + ks), bb = plead[ks];
+                                w = (ks == ks0 || noskip) ? 0u : (a + bb < (unsigned)S ? (a | (bb << 4)) : 0xffu);
                             }
-                            unsigned mask = __ballot_sync(0xffffffffu, a + bb < S);
+                            unsigned mask = __ballot_sync(0xffffffffu, w != 0xffu);
                             while (mask) {
                                 const int l = __ffs(mask) - 1;
                                 mask &= mask - 1;
-                                const int ca = __shfl_sync(0xffffffffu, a, l), cb = __shfl_sync(0xffffffffu, bb, l);
+                                const unsigned cw = __shfl_sync(0xffffffffu, w, l);
                                 if (npend == 2) {
-                                    emit(za, pb, pk[0], pa[0], pbz[0], pf[0]);
-                                    pk[0] = pk[1]; pa[0] = pa[1]; pbz[0] = pbz[1]; pf[0] = pf[1];
+                                    emit(za, pb, k0, w0, f0);
+                                    k0 = k1; w0 = w1; f0 = f1;
+                                    k1 = base + l; w1 = cw; f1 = item_flags;
+                                } else if (npend == 1) {
+                                    k1 = base + l; w1 = cw; f1 = next_flags;
+                                    npend = 2;
+                                } else {
+                                    k0 = base + l; w0 = cw; f0 = next_flags;
+                                    next_flags = second_flags;
                                     npend = 1;
                                 }
-                                unsigned f = item_flags;
-                                if (nlive == 0) f |= H_FIRST | (segs > 0 ? H_SEGNZ : 0u) | (((segs - 1) & 1) ? H_SEGPAR : 0u);
-                                if (nlive == 1) f |= H_SECOND | ((segs & 1) ? H_SEGPAR : 0u);
-                                pk[npend] = base + l; pa[npend] = ca; pbz[npend] = cb; pf[npend] = f;
-                                ++npend; ++nlive;
                             }
                         }
                         const unsigned endf = H_LAST | (item_last ? H_ITEM_LAST | (final_item ? H_FINAL : 0u) : 0u);
-                        emit(za, pb, pk[0], pa[0], pbz[0], pf[0] | H_PENULT | (item_last ? H_ITEM_PENULT : 0u));
+                        emit(za, pb, k0, w0, f0 | H_PENULT | (item_last ? H_ITEM_PENULT : 0u));
                         if (npend == 2) {
-                            emit(za, pb, pk[1], pa[1], pbz[1], pf[1] | endf);
+                            emit(za, pb, k1, w1, f1 | endf);
                         } else {
                             // A segment always has two stages, so that both issuers take part in every segment and neither
                             // can run a whole segment ahead (the barriers carry one parity bit): an empty second stage.
-                            emit(za, pb, -1, S, 0, item_flags | H_SECOND | ((segs & 1) ? H_SEGPAR : 0u) | endf);
+                            emit(za, pb, -1, (unsigned)S, second_flags | endf);
                         }
                     }
                 }
             }
-            emit(nullptr, nullptr, -1, 0, 0, H_EXIT);          // for the issuer that did not get the final stage
+            emit(nullptr, nullptr, -1, 0u, H_EXIT);          // for the issuer that did not get the final stage
             if (lane == 0) {
                 atomicAdd(&g_i8_count[0], n_mma);
                 atomicAdd(&g_i8_count[1], n_stage);
                 atomicAdd(&g_i8_count[2], n_kstep);
                 if (blockIdx.x == 0) atomicAdd(&g_i8_count[3], 1ull);
+                atomicAdd(&g_i8_count[4], (unsigned long long)(clock64() - clk0));
+                atomicAdd(&g_i8_count[5], 1ull);
             }
         }
     } else if (warp == C::ISSUER0 || warp == C::ISSUER1) {
@@ -904,7 +928,15 @@ extern "C" int gp2d_dbg_i8_watchdog(unsigned long long* out36) {      // [4] fir
 extern "C" int gp2d_dbg_i8_counters(unsigned long long* out4) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(out4, g_i8_count, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
-    const unsigned long long z[4] = {0, 0, 0, 0};
+    const unsigned long long z[6] = {0, 0, 0, 0, 0, 0};
+    return cudaMemcpyToSymbol(g_i8_count, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+// the same and, in out6[4], out6[5]: SM clocks the producers spent (summed over the CTAs of all launches), CTAs -- times
+// in clocks do not move with the power cap the way milliseconds do
+extern "C" int gp2d_dbg_i8_counters6(unsigned long long* out6) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out6, g_i8_count, 6 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    const unsigned long long z[6] = {0, 0, 0, 0, 0, 0};
     return cudaMemcpyToSymbol(g_i8_count, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 
