@@ -172,7 +172,7 @@ struct I8Cfg {
     // (copies of different stages complete out of order).  So the full barriers are indexed by n % NFULL, NFULL a
     // multiple of both the ring and the issuer count: every barrier then belongs to one issuer, use after use.
     static constexpr int NFULL = MMA_WARPS * STAGES;
-    static constexpr int NBARS = NFULL + STAGES + 2 + 4 + 2;   // full, empty, acc_full, acc_empty, panel_full[2], panel_empty[2], first_done, pad
+    static constexpr int NBARS = NFULL + STAGES + 2 + 4 + 2 + 8;   // full, empty, acc_full, (unused), panel_full[2], panel_empty[2], first_done, pad, acc_empty[8]
     // doubles after the barriers: observation stage, mean partials [GSLOTS][NG][2], column sums [4][NC], parameters,
     // digit ORs of the generators [2][GSLOTS], stage headers [STAGES] (32-bit)
     static constexpr int TAIL_DOUBLES = 5 * OBS_BATCH + GSLOTS * NG * 2 + 4 * NC + 64 + 16 + 8;
@@ -203,6 +203,7 @@ struct PredictI8Args {
     uint8_t* scratch;             // per CTA: 2 panels
     size_t panel_bytes, cta_bytes, lead_off;     // a panel: digit slices, then at lead_off one byte per k-step (leading all-zero slices)
     int ntiles;
+    int keep_ks;                  // panel k-steps below this are copied with L2 evict-last priority (see the producer)
     int* pace;                    // [npad / 128] row-block arrival counters of this launch (zeroed), or null: see the producer
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
     int dbg;                      // bring-up knobs: 8 = copy and multiply the all-zero slices too (same results bit for bit);
@@ -464,6 +465,17 @@ __device__ __forceinline__ void i8_issue(unsigned tbase, unsigned a_lo, unsigned
             umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)(i * AT16)), i8_desc(b_lo + (unsigned)((d - i) * BT16)), IDESC,
                        (FIRST && i == A) ? 0u : 1u);
 }
+// the products of accumulator d of a first (whole) k-step: slice pairs (i, d - i), the first one overwrites
+template <int S, int NC>
+__device__ __forceinline__ void i8_issue_first(int d, unsigned tbase, unsigned a_lo, unsigned b_lo) {
+    constexpr unsigned IDESC = i8_idesc(128, NC);
+    constexpr int BT16 = (NC * I8_KSTEP) >> 4, AT16 = I8_ATILE_BYTES >> 4;
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+        if (i <= d)
+            umma_i8_ss(tbase + d * NC, i8_desc(a_lo + (unsigned)(i * AT16)), i8_desc(b_lo + (unsigned)((d - i) * BT16)), IDESC, i == 0 ? 0u : 1u);
+}
+
 template <int S, int NC, int A>
 __device__ __forceinline__ void i8_issue_b(int b, unsigned tbase, unsigned a_lo, unsigned b_lo) {
     switch (b) {
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     unsigned long long* full = bars;
     unsigned long long* empty = bars + C::NFULL;
     unsigned long long* acc_full = empty + C::STAGES;
-    unsigned long long* acc_empty = acc_full + 1;
+    unsigned long long* acc_empty = acc_full + 8;          // [S]: one per accumulator, handed back as soon as it is drained
     unsigned long long* panel_full = acc_full + 2;
     unsigned long long* panel_empty = acc_full + 4;
     unsigned long long* first_done = acc_full + 6;
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
         for (int s = 0; s < C::NFULL; ++s) mbar_init(full + s, 1);
         for (int s = 0; s < C::STAGES; ++s) mbar_init(empty + s, 1);
         mbar_init(acc_full, C::MMA_WARPS);
-        mbar_init(acc_empty, C::EPI_WARPS);
+        for (int d = 0; d < S; ++d) mbar_init(acc_empty + d, C::EPI_WARPS);
         mbar_init(first_done, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(panel_full + b, 1); mbar_init(panel_empty + b, C::MMA_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -562,29 +574,35 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     I8_WAIT(acc_full, ph, 1, (item << 8) | rb);
                     ph ^= 1u;
                     tc_fence_after();
-                    if (!(p.dbg & 2)) {
+                    // accumulator by accumulator (digit sum d has weight 256^(S-1-d); the total keeps bits SH and up, the
+                    // low digits rounded in), each handed back to the issuers as soon as it is in the integers: the first
+                    // stage of the next segment writes them in the same order
 #pragma unroll
-                        for (int g = 0; g < HC / 4; ++g) {
-                            int r[S][4];
+                    for (int d = 0; d < S; ++d) {
+                        constexpr int NQ = HC / 8;        // two batches of loads: half the columns each (registers)
+                        if (!(p.dbg & 2)) {
+                            const int sh = 8 * (S - 1 - d) - SH;      // compile time after unrolling
 #pragma unroll
-                            for (int d = 0; d < S; ++d) tmem_ld4(tcol0 + d * NC + g * 4, r[d]);
-                            tmem_ld_wait();
+                            for (int hb = 0; hb < 2; ++hb) {
+                                int r[NQ][4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                long long h = r[0][j], l = r[NHI][j];
+                                for (int g = 0; g < NQ; ++g) tmem_ld4(tcol0 + d * NC + (hb * NQ + g) * 4, r[g]);
+                                tmem_ld_wait();
 #pragma unroll
-                                for (int d = 1; d < NHI; ++d) h = h * 256 + r[d][j];
+                                for (int g = 0; g < NQ; ++g)
 #pragma unroll
-                                for (int d = 1; d < NLO; ++d) l = l * 256 + r[NHI + d][j];
-                                const long long v = h * (1ll << (8 * NLO - SH)) + ((l + (1ll << (SH - 1))) >> SH);
-                                t64[g * 4 + j] = seg ? t64[g * 4 + j] + v : v;
+                                    for (int j = 0; j < 4; ++j) {
+                                        const long long v = sh >= 0 ? (long long)r[g][j] * (1ll << (sh >= 0 ? sh : 0))
+                                                                    : (((long long)r[g][j] + (1ll << (sh < 0 ? -sh - 1 : 0))) >> (sh < 0 ? -sh : 0));
+                                        const int c = (hb * NQ + g) * 4 + j;
+                                        t64[c] = (d == 0 && seg == 0) ? v : t64[c] + v;
+                                    }
                             }
                         }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + d);
                     }
-                    // the accumulators have been read: the next segment may start
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
                 }
                 if (p.dbg & 2) continue;
 #pragma unroll
@@ -642,6 +660,9 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             const long long clk0 = clock64();
             const bool noskip = (p.dbg & (8 | 4)) != 0;
             const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+            // Panel k-step ks is read once per row block rb >= ks / 4: the first k-steps of the panel are re-read by every
+            // row block, the last ones by a few.  As many of the first as fit the L2 beside Zq are kept there.
+            const int keep_ks = (p.dbg >> 8) & 0xff ? ((p.dbg >> 8) & 0xff) - 1 : p.keep_ks;
             // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products).
             // w packs the leading-zero counts: a | b << 4.  This warp feeds two issuers that need a stage every ~500
             // clocks each: the loop is kept lean (scalar state, one shuffle per k-step, no 64-bit modulo).
@@ -659,7 +680,8 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                         const unsigned abytes = (unsigned)(S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(S - b) * C::BTILE;
                         mbar_arrive_expect_tx(fb, abytes + bbytes);
                         bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
-                        bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb, pol_stream);
+                        bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb,
+                                      ks < keep_ks ? pol_keep : pol_stream);
                         const int mm = S - a - b;
                         n_mma += (unsigned)(mm * (mm + 1) / 2);
                         ++n_stage;
@@ -784,15 +806,24 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 if (h & H_EXIT) break;
                 const int a = (int)(h & 0xffu), b = (int)((h >> 8) & 0xffu);
                 const unsigned segpar = (h & H_SEGPAR) ? 1u : 0u;
-                if ((h & H_FIRST) && (h & H_SEGNZ)) I8_WAIT(acc_empty, segpar, 5, (unsigned)n);    // the epilogue has drained the accumulators
                 if (h & H_SECOND) I8_WAIT(first_done, segpar, 7, (unsigned)n);
                 tc_fence_after();
                 const unsigned a_lo = ring_lo + (unsigned)((rs * C::STAGE_BYTES) >> 4);
                 const unsigned b_lo = a_lo + (unsigned)((S * I8_ATILE_BYTES) >> 4);
+                if (h & H_FIRST) {
+                    // the first stage of a segment overwrites the accumulators: each as soon as the epilogue has drained it
+#pragma unroll
+                    for (int d = 0; d < S; ++d) {
+                        if (h & H_SEGNZ) {
+                            I8_WAIT(acc_empty + d, segpar, 5, (unsigned)n);
+                            tc_fence_after();
+                        }
+                        if (!nomma && elect_one_sync()) i8_issue_first<S, NC>(d, tbase, a_lo, b_lo);
+                        __syncwarp();
+                    }
+                }
                 if (elect_one_sync()) {
-                    if (nomma) {
-                    } else if (h & H_FIRST) {
-                        i8_issue<S, NC, 0, 0, true>(tbase, a_lo, b_lo);
+                    if (nomma || (h & H_FIRST)) {
                     } else {
                         i8_issue_ab<S, NC>(a, b, tbase, a_lo, b_lo);
                     }
@@ -903,6 +934,11 @@ static cudaError_t predict_i8_launch(PredictI8Args a, double kmax, uint8_t* scra
     // pacing pays when the S slices of Z do not fit the L2 beside the panel stream and there are CTAs to keep together
     const bool big = (size_t)S * a.npad * (size_t)a.npad / 2 > ((size_t)64 << 20);
     a.pace = (((big && !(a.dbg & 64)) || (a.dbg & 128)) && grid > 1) ? reinterpret_cast<int*>(scratch) : nullptr;
+    {   // L2 budget for panel tiles: what 96 MB leave beside the S slices of Z, shared by the CTAs' current panels
+        const double zq = (double)S * a.npad * (double)a.npad / 2.0, budget = 96.0 * 1048576.0 - zq;
+        const double per_kstep = (double)grid * S * C::BTILE;
+        a.keep_ks = budget > 0.0 ? (int)(budget / per_kstep) : 0;
+    }
     predict_i8_kernel<S, NC><<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
