@@ -207,7 +207,7 @@ struct PredictI8Args {
     int* pace;                    // [npad / 128] row-block arrival counters of this launch (zeroed), or null: see the producer
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
     int dbg;                      // bring-up knobs: 8 = copy and multiply the all-zero slices too (same results bit for bit);
-                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies; 64 no pacing, 128 pacing whatever the size
+                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies, 2048 copy the slices past S-1-b / S-1-a too; 64 no pacing, 128 pacing whatever the size
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -677,7 +677,9 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     if (ks < 0 || (p.dbg & 32)) {
                         mbar_arrive(fb);
                     } else {
-                        const unsigned abytes = (unsigned)(S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(S - b) * C::BTILE;
+                        // slice pairs (i, j), i >= a, j >= b, i + j < S: A slices a .. S-1-b, B slices b .. S-1-a
+                        const int ns = (p.dbg & 2048) ? 0 : S - a - b;
+                        const unsigned abytes = (unsigned)(ns ? ns : S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(ns ? ns : S - b) * C::BTILE;
                         mbar_arrive_expect_tx(fb, abytes + bbytes);
                         bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
                         bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb,
