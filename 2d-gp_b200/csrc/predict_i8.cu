@@ -549,15 +549,13 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     if (warp < C::EPI_WARPS) {
         // ------------------------------ epilogue ------------------------------------------------
         // Warp w reads TMEM lanes 32 (w % 4) .. (rows of the row block) and the column half w / 4.  Two phases per row
-        // block: (A) drain the accumulators into one 64-bit integer per entry -- Horner in 256 over the S digits' sums,
-        // the NHI leading and NLO trailing ones each within 56 bits, joined with the lowest SH bits dropped (far below
-        // the products i + j >= S that the slicing leaves out) -- and hand the accumulators back to the MMA issuer;
-        // (B) convert, scale by the row unit, square and sum over the rows while the tensor core works on the next row
-        // block.  Segments of a long row block add up exactly in the integers.
+        // block: (A) drain the accumulators, one after the other, into one 64-bit integer per entry -- digit sum d has the
+        // weight 256^(S-1-d); the total keeps bits SH and up (the low digit sums are rounded in: far below the products
+        // i + j >= S that the slicing leaves out) -- and hand each accumulator back to the MMA issuers as soon as it is
+        // read; (B) convert, scale by the row unit, square and sum over the rows while the tensor core works on the
+        // next row block.  Segments of a long row block add up exactly in the integers.
         constexpr int HC = C::HC, NG8 = HC / 8;
-        constexpr int NHI = (S + 1) / 2, NLO = S - NHI;
-        constexpr int SH = S == 6 ? 8 : 14;
-        static_assert(8 * NLO >= SH, "join shift");
+        constexpr int SH = S == 6 ? 8 : 14;               // S = 6: |total| < 2^60 over four segments; S = 7: < 2^62
         const int q = warp & 3, half = warp >> 2;
         const double cs = p.cscale * (double)(1 << SH);
         const unsigned tcol0 = tbase + ((unsigned)(q * 32) << 16) + (unsigned)(half * HC);

@@ -682,9 +682,10 @@ def run_ours(args):
                     "gpregression_construct_plus_predict_s": e2e_gpy,
                     "gpregression_note": "models.GPRegression(X, Y, myKernel).predict(Xnew): the constructor evaluates LML "
                                          "and its gradient like GPy's, then predict refits and predicts"},
-            # build, potri tree, pack, digit slices (row scale, quantise, gate), alpha/LML, predict (the int8 kernel of
-            # each slice count + the fp64 kernel: the fit state selects one on the device, the others return at once)
-            "gpu_launches": K * (1 + potri_launches(npad // 128) + 1 + 3 + 5 + 3),
+            # spatial order (sort, gather), build, potri tree, pack, digit slices (row scale, quantise, gate), alpha/LML,
+            # predict (the int8 kernel of each slice count + the fp64 kernel: the fit state selects one on the device,
+            # the others return at once)
+            "gpu_launches": K * (2 + 1 + potri_launches(npad // 128) + 1 + 3 + 5 + 3),
             "roofline": roofline, "roofline_fp64_kernel": roofline_fp64,
             "stages": stages, "targets_at_N16384": targets, "info": info,
         }
