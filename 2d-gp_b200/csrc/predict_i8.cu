@@ -668,23 +668,32 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, unsigned w, unsigned flags) {
                 if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
                 const int a = (int)(w & 15u), b = (int)(w >> 4);
-                if (lane == 0) {
-                    uint8_t* st = ring + rs * C::STAGE_BYTES;
-                    unsigned long long* fb = full + fi;
-                    sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
-                    if (ks < 0 || (p.dbg & 32)) {
+                unsigned long long* fb = full + fi;
+                uint8_t* st = ring + rs * C::STAGE_BYTES;
+                if (ks < 0 || (p.dbg & 32)) {
+                    if (lane == 0) {
+                        sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
                         mbar_arrive(fb);
-                    } else {
-                        // slice pairs (i, j), i >= a, j >= b, i + j < S: A slices a .. S-1-b, B slices b .. S-1-a
-                        const int ns = (p.dbg & 2048) ? 0 : S - a - b;
-                        const unsigned abytes = (unsigned)(ns ? ns : S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(ns ? ns : S - b) * C::BTILE;
+                    }
+                } else {
+                    // slice pairs (i, j), i >= a, j >= b, i + j < S: A slices a .. S-1-b, B slices b .. S-1-a.
+                    // Lane 0 copies the A slices, lane 1 the B slices: one instruction stream for both copies.
+                    const int ns = (p.dbg & 2048) ? 0 : S - a - b;
+                    const unsigned abytes = (unsigned)(ns ? ns : S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(ns ? ns : S - b) * C::BTILE;
+                    if (lane == 0) {
+                        sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
                         mbar_arrive_expect_tx(fb, abytes + bbytes);
-                        bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
-                        bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb,
-                                      ks < keep_ks ? pol_keep : pol_stream);
                         const int mm = S - a - b;
                         n_mma += (unsigned)(mm * (mm + 1) / 2);
                         ++n_stage;
+                    }
+                    __syncwarp();                                   // the barrier is armed before either copy can complete on it
+                    if (lane < 2) {
+                        const bool isb = lane == 1;
+                        uint8_t* dst = isb ? st + S * I8_ATILE_BYTES + b * C::BTILE : st + a * I8_ATILE_BYTES;
+                        const uint8_t* src = isb ? pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE
+                                                 : reinterpret_cast<const uint8_t*>(za) + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES;
+                        bulk_g2s_hint(dst, src, isb ? bbytes : abytes, fb, (isb && ks >= keep_ks) ? pol_stream : pol_keep);
                     }
                 }
                 __syncwarp();
@@ -709,10 +718,11 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     // until every CTA has reached row block rb - window of this round of column tiles.
                     if (p.pace) {
                         if (lane == 0) atomicAdd(p.pace + rb, 1);
-                        if (rb >= I8_PACE_WINDOW) {
+                        const int pace_window = ((p.dbg >> 12) & 15) ? ((p.dbg >> 12) & 15) : I8_PACE_WINDOW;
+                        if (rb >= pace_window) {
                             const long need_l = (long)(it + 1) * (long)gridDim.x;
                             const int need = need_l < (long)p.ntiles ? (int)need_l : p.ntiles;
-                            const volatile int* pc = p.pace + (rb - I8_PACE_WINDOW);
+                            const volatile int* pc = p.pace + (rb - pace_window);
                             const long long t0 = clock64();
                             for (;;) {
                                 int seen = 0;
