@@ -207,7 +207,7 @@ struct PredictI8Args {
     int* pace;                    // [npad / 128] row-block arrival counters of this launch (zeroed), or null: see the producer
     const int* gate;              // slice count chosen at fit time; the kernel runs only when it equals S
     int dbg;                      // bring-up knobs: 8 = copy and multiply the all-zero slices too (same results bit for bit);
-                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies, 2048 copy the slices past S-1-b / S-1-a too; 64 no pacing, 128 pacing whatever the size
+                                  // timing experiments with wrong results: 1 all CTAs stream panel 0, 2 no epilogue math, 4 no generation, 16 no MMAs, 32 no copies; 64 no pacing, 128 pacing whatever the size
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -645,61 +645,50 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
         }
     } else if (warp == C::PRODUCER) {
         // ------------------------------ producer / scheduler ----------------------------------------
-        // The whole warp walks the k-steps: lane l reads the leading-zero-slice bytes of k-step base + l of the Z row
-        // block and of the panel.  A k-step whose non-zero slices cannot meet (a + b >= S) is dropped; of the others
-        // only the non-zero slices are copied.  The first k-step of an accumulation segment is always taken whole (it
-        // initialises the S accumulators).  Each stage carries a header for the MMA issuer: a, b, first / last of the
-        // segment, last of the item.
+        // Per accumulation segment (the k-steps of a row block, at most I8_KSEG): lane l of chunk c reads the
+        // leading-zero-slice bytes of k-step 32 c + l of the Z row block and of the panel (all chunks' loads in flight
+        // together).  A k-step whose non-zero slices cannot meet (a + b >= S) is dropped, the first one of the segment is
+        // always taken whole (it initialises the accumulators).  Every live lane then emits ITS stage by itself, as
+        // soon as the ring slot of that stage is free: header for the issuers (a, b, position in the segment), barrier,
+        // two bulk copies of exactly the slices that take part in a product.  A stage costs this warp one pass of a
+        // short divergent loop, not a round of shuffles and queue bookkeeping through lane 0 -- in the sparse regime
+        // (10 products per stage) the serial version was what the issuers waited for.
         {
-            int rs = 0, it = 0;
-            unsigned rph = 0;
+            int it = 0;
             long fills = 0, segs = 0;
-            unsigned long long n_mma = 0, n_stage = 0, n_kstep = 0;
+            unsigned long long n_mma = 0, n_stage = 0, n_kstep = 0;       // per lane; summed at the end
             const long long clk0 = clock64();
             const bool noskip = (p.dbg & (8 | 4)) != 0;
             const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
             // Panel k-step ks is read once per row block rb >= ks / 4: the first k-steps of the panel are re-read by every
             // row block, the last ones by a few.  As many of the first as fit the L2 beside Zq are kept there.
             const int keep_ks = (p.dbg >> 8) & 0xff ? ((p.dbg >> 8) & 0xff) - 1 : p.keep_ks;
-            // one stage: header, then the copies of the non-zero slices (ks < 0: header only; a = S: no products).
-            // w packs the leading-zero counts: a | b << 4.  This warp feeds two issuers that need a stage every ~500
-            // clocks each: the loop is kept lean (scalar state, one shuffle per k-step, no 64-bit modulo).
-            int fi = 0;                                   // fills % NFULL
-            auto emit = [&](const int8_t* za, const uint8_t* pb, int ks, unsigned w, unsigned flags) {
-                if (fills >= C::STAGES) I8_WAIT(empty + rs, rph ^ 1u, 3, (it << 16) | rs);
+            const unsigned lt_mask = (1u << lane) - 1u;
+            // is the ring slot of stage n free (the products of stage n - STAGES have completed)?
+            auto slot_free = [&](long n) -> bool {
+                return n < C::STAGES || mbar_test(empty + (int)(n % C::STAGES), ((unsigned)(n / C::STAGES) & 1u) ^ 1u);
+            };
+            // stage n (this lane's), its slot being free: header, barrier, copies.  ks < 0: header only (w = S: no
+            // products).  w packs the leading-zero counts a | b << 4.
+            auto emit_lane = [&](long n, const int8_t* za, const uint8_t* pb, int ks, unsigned w, unsigned flags) {
+                const int rs = (int)(n % C::STAGES);
                 const int a = (int)(w & 15u), b = (int)(w >> 4);
-                unsigned long long* fb = full + fi;
+                unsigned long long* fb = full + (int)(n % C::NFULL);
                 uint8_t* st = ring + rs * C::STAGE_BYTES;
+                sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
                 if (ks < 0 || (p.dbg & 32)) {
-                    if (lane == 0) {
-                        sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
-                        mbar_arrive(fb);
-                    }
+                    mbar_arrive(fb);
                 } else {
-                    // slice pairs (i, j), i >= a, j >= b, i + j < S: A slices a .. S-1-b, B slices b .. S-1-a.
-                    // Lane 0 copies the A slices, lane 1 the B slices: one instruction stream for both copies.
-                    const int ns = (p.dbg & 2048) ? 0 : S - a - b;
-                    const unsigned abytes = (unsigned)(ns ? ns : S - a) * I8_ATILE_BYTES, bbytes = (unsigned)(ns ? ns : S - b) * C::BTILE;
-                    if (lane == 0) {
-                        sh_hdr[rs] = (unsigned)a | ((unsigned)b << 8) | flags;
-                        mbar_arrive_expect_tx(fb, abytes + bbytes);
-                        const int mm = S - a - b;
-                        n_mma += (unsigned)(mm * (mm + 1) / 2);
-                        ++n_stage;
-                    }
-                    __syncwarp();                                   // the barrier is armed before either copy can complete on it
-                    if (lane < 2) {
-                        const bool isb = lane == 1;
-                        uint8_t* dst = isb ? st + S * I8_ATILE_BYTES + b * C::BTILE : st + a * I8_ATILE_BYTES;
-                        const uint8_t* src = isb ? pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE
-                                                 : reinterpret_cast<const uint8_t*>(za) + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES;
-                        bulk_g2s_hint(dst, src, isb ? bbytes : abytes, fb, (isb && ks >= keep_ks) ? pol_stream : pol_keep);
-                    }
+                    // slice pairs (i, j), i >= a, j >= b, i + j < S: A slices a .. S-1-b, B slices b .. S-1-a
+                    const int ns = S - a - b;
+                    const unsigned abytes = (unsigned)ns * I8_ATILE_BYTES, bbytes = (unsigned)ns * C::BTILE;
+                    mbar_arrive_expect_tx(fb, abytes + bbytes);
+                    bulk_g2s_hint(st + a * I8_ATILE_BYTES, za + (size_t)ks * (I8_SMAX * I8_ATILE_BYTES) + a * I8_ATILE_BYTES, abytes, fb, pol_keep);
+                    bulk_g2s_hint(st + S * I8_ATILE_BYTES + b * C::BTILE, pb + (size_t)ks * (S * C::BTILE) + b * C::BTILE, bbytes, fb,
+                                  ks < keep_ks ? pol_keep : pol_stream);
+                    n_mma += (unsigned)(ns * (ns + 1) / 2);
+                    ++n_stage;
                 }
-                __syncwarp();
-                ++fills;
-                if (++fi == C::NFULL) fi = 0;
-                if (++rs == C::STAGES) { rs = 0; rph ^= 1u; }
             };
             bool final_item = false;
             for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, ++it) {
@@ -740,52 +729,82 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     for (int ks0 = 0; ks0 < nks; ks0 += I8_KSEG, ++segs) {
                         const int ks1 = ks0 + I8_KSEG < nks ? ks0 + I8_KSEG : nks;
                         const bool item_last = rb == nb - 1 && ks1 == nks;
-                        n_kstep += (unsigned)(ks1 - ks0);
-                        // two stages are held back so that the last and the one before it can be told
-                        int k0 = 0, k1 = 0, npend = 0;
-                        unsigned w0 = 0, w1 = 0, f0 = 0, f1 = 0;
-                        const unsigned first_flags = item_flags | H_FIRST | (segs > 0 ? H_SEGNZ : 0u) | (((segs - 1) & 1) ? H_SEGPAR : 0u);
-                        const unsigned second_flags = item_flags | H_SECOND | ((segs & 1) ? H_SEGPAR : 0u);
-                        unsigned next_flags = first_flags;
-                        for (int base = ks0; base < ks1; base += 32) {
-                            const int ks = base + lane;
-                            unsigned w = 0xffu;                          // dead
+                        if (lane == 0) n_kstep += (unsigned)(ks1 - ks0);
+                        constexpr int NCH = I8_KSEG / 32;
+                        // pass 1: the lead bytes of the whole segment; wv[c]: this lane's k-step of chunk c (0xff: dead)
+                        unsigned wv[NCH], live_mask[NCH];
+                        int L = 0;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            const int ks = ks0 + 32 * c + lane;
+                            unsigned w = 0xffu;
                             if (ks < ks1) {
                                 const unsigned a = __ldg(zl + ks), bb = plead[ks];
                                 w = (ks == ks0 || noskip) ? 0u : (a + bb < (unsigned)S ? (a | (bb << 4)) : 0xffu);
                             }
-                            unsigned mask = __ballot_sync(0xffffffffu, w != 0xffu);
-                            while (mask) {
-                                const int l = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const unsigned cw = __shfl_sync(0xffffffffu, w, l);
-                                if (npend == 2) {
-                                    emit(za, pb, k0, w0, f0);
-                                    k0 = k1; w0 = w1; f0 = f1;
-                                    k1 = base + l; w1 = cw; f1 = item_flags;
-                                } else if (npend == 1) {
-                                    k1 = base + l; w1 = cw; f1 = next_flags;
-                                    npend = 2;
-                                } else {
-                                    k0 = base + l; w0 = cw; f0 = next_flags;
-                                    next_flags = second_flags;
-                                    npend = 1;
+                            wv[c] = w;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            live_mask[c] = (ks0 + 32 * c < ks1) ? __ballot_sync(0xffffffffu, wv[c] != 0xffu) : 0u;
+                            L += __popc(live_mask[c]);
+                        }
+                        // pass 2: every live lane emits its stage; j: its position among the live k-steps of the segment
+                        const unsigned first_flags = item_flags | H_FIRST | (segs > 0 ? H_SEGNZ : 0u) | (((segs - 1) & 1) ? H_SEGPAR : 0u);
+                        const unsigned second_flags = item_flags | H_SECOND | ((segs & 1) ? H_SEGPAR : 0u);
+                        const unsigned endf = H_LAST | (item_last ? H_ITEM_LAST | (final_item ? H_FINAL : 0u) : 0u);
+                        const unsigned penf = H_PENULT | (item_last ? H_ITEM_PENULT : 0u);
+                        int before = 0;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            if (live_mask[c] == 0u) continue;               // uniform
+                            const int j = before + __popc(live_mask[c] & lt_mask);
+                            unsigned f = j == 0 ? first_flags : j == 1 ? second_flags : item_flags;
+                            if (j == L - 1 && L >= 2) f |= endf;
+                            if (j == L - 2 || L == 1) f |= penf;
+                            // rounds: whoever finds its slot free emits; the warp stays converged between the rounds, so a
+                            // lane waiting for a slot never keeps back one whose slot is free (its stage may be what the
+                            // issuers need next to free the other's).  A lane may look at its slot's barrier only once the
+                            // stage STAGES before it has been emitted: one parity bit tells "the previous use is over"
+                            // from "not yet", not from the uses before that -- so the window is the STAGES stages after
+                            // the emitted prefix.
+                            const int rank = __popc(live_mask[c] & lt_mask);
+                            bool done = wv[c] == 0xffu;
+                            for (;;) {
+                                const unsigned rem = live_mask[c] & ~__ballot_sync(0xffffffffu, done);
+                                if (rem == 0u) break;
+                                const int prefix = __popc(live_mask[c] & ((rem & (0u - rem)) - 1u));      // live lanes below the first one not done
+                                if (!done && rank < prefix + C::STAGES && slot_free(fills + j)) {
+                                    emit_lane(fills + j, za, pb, ks0 + 32 * c + lane, wv[c], f);
+                                    done = true;
                                 }
                             }
+                            before += __popc(live_mask[c]);
                         }
-                        const unsigned endf = H_LAST | (item_last ? H_ITEM_LAST | (final_item ? H_FINAL : 0u) : 0u);
-                        emit(za, pb, k0, w0, f0 | H_PENULT | (item_last ? H_ITEM_PENULT : 0u));
-                        if (npend == 2) {
-                            emit(za, pb, k1, w1, f1 | endf);
-                        } else {
+                        fills += L;
+                        if (L == 1) {
                             // A segment always has two stages, so that both issuers take part in every segment and neither
                             // can run a whole segment ahead (the barriers carry one parity bit): an empty second stage.
-                            emit(za, pb, -1, (unsigned)S, second_flags | endf);
+                            bool done = lane != 0;
+                            while (!__all_sync(0xffffffffu, done)) {
+                                if (!done && slot_free(fills)) { emit_lane(fills, za, pb, -1, (unsigned)S, second_flags | endf); done = true; }
+                            }
+                            ++fills;
                         }
                     }
                 }
             }
-            emit(nullptr, nullptr, -1, 0u, H_EXIT);          // for the issuer that did not get the final stage
+            {   // for the issuer that did not get the final stage
+                bool done = lane != 0;
+                while (!__all_sync(0xffffffffu, done)) {
+                    if (!done && slot_free(fills)) { emit_lane(fills, nullptr, nullptr, -1, 0u, H_EXIT); done = true; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                n_mma += __shfl_xor_sync(0xffffffffu, n_mma, o);
+                n_stage += __shfl_xor_sync(0xffffffffu, n_stage, o);
+            }
             if (lane == 0) {
                 atomicAdd(&g_i8_count[0], n_mma);
                 atomicAdd(&g_i8_count[1], n_stage);
