@@ -664,6 +664,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             // row block, the last ones by a few.  As many of the first as fit the L2 beside Zq are kept there.
             const int keep_ks = (p.dbg >> 8) & 0xff ? ((p.dbg >> 8) & 0xff) - 1 : p.keep_ks;
             const unsigned lt_mask = (1u << lane) - 1u;
+            int pace_timeouts = 0;
             // is the ring slot of stage n free (the products of stage n - STAGES have completed)?
             auto slot_free = [&](long n) -> bool {
                 return n < C::STAGES || mbar_test(empty + (int)(n % C::STAGES), ((unsigned)(n / C::STAGES) & 1u) ^ 1u);
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                     if (p.pace) {
                         if (lane == 0) atomicAdd(p.pace + rb, 1);
                         const int pace_window = ((p.dbg >> 12) & 15) ? ((p.dbg >> 12) & 15) : I8_PACE_WINDOW;
-                        if (rb >= pace_window) {
+                        if (rb >= pace_window && pace_timeouts < 4) {
                             const long need_l = (long)(it + 1) * (long)gridDim.x;
                             const int need = need_l < (long)p.ntiles ? (int)need_l : p.ntiles;
                             const volatile int* pc = p.pace + (rb - pace_window);
@@ -717,7 +718,10 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                                 int seen = 0;
                                 if (lane == 0) seen = *pc;
                                 seen = __shfl_sync(0xffffffffu, seen, 0);
-                                if (seen >= need || clock64() - t0 > I8_PACE_LIMIT) break;
+                                if (seen >= need) break;
+                                // best effort: CTAs that are not co-resident (another kernel holds SMs) never arrive; after a
+                                // few time-outs this CTA stops waiting for the rest of the launch
+                                if (clock64() - t0 > I8_PACE_LIMIT) { ++pace_timeouts; break; }
                                 __nanosleep(256);
                             }
                         }

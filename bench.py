@@ -48,8 +48,8 @@ NOISE = 0.05
 CPU_GRID_FRACTION = 0.10          # share of the grid a bounded CPU step predicts (all of it for <= 3 steps)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
 # ncu captures named in roofline.traffic_source (int8-sliced kernel) / roofline_fp64_kernel.traffic_source
-NCU_PREDICT_I8_DRAM_BYTES = 47.051927e9 + 5.163798e9
-NCU_PREDICT_I8_SOURCE = "profiles/r02j_predict_i8_kernel.md"
+NCU_PREDICT_I8_DRAM_BYTES = 47.294351e9 + 5.190785e9
+NCU_PREDICT_I8_SOURCE = "profiles/r02m_predict_i8_kernel.md"
 NCU_PREDICT_DRAM_BYTES = 108.822557e9 + 6.737815e9
 NCU_PREDICT_SOURCE = "profiles/r01h_predict_kernel.md"
 I8_SLICES = 6                     # slice count gp2d_fit picks at the conditioning of configs[1] / configs[2] / configs[4]
