@@ -21,17 +21,22 @@
 // covariances of distant points, entries of L^-1 far from the diagonal: a third of the slice products at
 // configs[1], 60 % at N = 8192 -- need neither be copied nor multiplied, exactly (tools/sparsity_emulate.py).
 //
-// CTA (one per SM, persistent over column tiles of NC / 2 grid points x 2 components), by warp:
-//   0-7    epilogue: (A) TMEM -> one 64-bit integer per entry (Horner over the digit sums), accumulators handed
-//          back at once; (B) fp64 scale, square, sum over the 128 rows, running column sums, while the tensor core
-//          is on the next row block.  Warp w: TMEM lanes 32 (w % 4).., column half w / 4
-//   8      producer / scheduler: reads one byte per k-step tile of Z (written at fit time) and of the panel (written
-//          by the generators): the leading all-zero slices a, b; drops the k-step when a + b >= S, else copies the
-//          non-zero slices with two bulk copies and writes the stage header (a, b, segment flags) for the issuers
-//   9, 10  MMA issuers: stage n belongs to issuer n % 2; straight-line code per (a, b)
-//   11..   generators: build the digit slices of the K* panel of the NEXT column tile into the other of two global
-//          scratch panels while the tensor core works on the current one, the mean K*^T alpha in fp64 on the way,
-//          and the OR of the digits per k-step tile (-> b)
+// CTA (one per SM, persistent over column tiles of NC / 2 grid points x 2 components), by warp (a warp's scheduler
+// and TMEM lane quarter are warp % 4):
+//   0-7         epilogue: (A) TMEM -> one 64-bit integer per entry, accumulator by accumulator, each handed back to
+//               the issuers as soon as it is read; (B) fp64 scale, square, sum over the 128 rows, running column
+//               sums, while the tensor core is on the next row block.  Warp w: TMEM lanes 32 (w % 4).., column half w / 4
+//   8, 12       MMA issuers: stage n belongs to issuer n % 2; straight-line code per (a, b)
+//   15 (14)     producer / scheduler: reads one byte per k-step tile of Z (written at fit time) and of the panel
+//               (written by the generators): the leading all-zero slices a, b; drops the k-step when a + b >= S, else
+//               copies exactly the slices that take part in a product (A: a .. S-1-b, B: b .. S-1-a) with two bulk
+//               copies and writes the stage header (a, b, segment flags) for the issuers; lane-parallel
+//   9-11, 13, 14  generators: build the digit slices of the K* panel of the NEXT column tile into the other of two
+//               global scratch panels while the tensor core works on the current one, the mean K*^T alpha in fp64 on
+//               the way, and the OR of the digits per k-step tile (-> b)
+// The kernel runs against the board's power cap (back to back it settles at ~1600 of 1965 MHz): bytes not moved
+// come back as clock, which is why only the slices that are used are copied and why the first panel k-steps keep L2
+// priority.  Times of bring-up experiments are therefore taken in SM clocks AND in milliseconds (tools/i8_ab.py).
 // tests/tools/i8_protocol_sim.py is a discrete-event model of the barrier protocol between these roles.
 #include "common.cuh"
 #include "linalg.h"
@@ -43,8 +48,8 @@ constexpr int I8_SMAX = 7;                           // digits stored per entry 
 constexpr int I8_GSLOTS = 4;                         // k-steps a CTA generates side by side (x NC / 2 grid points = generator threads)
 // An int32 accumulator d sums (d + 1) digit products over k: at most k (2 64 128 + (d - 1) 128 128) for d = S - 1
 // (top digits are within [-64, 64]), which passes 2^31 beyond k = 21845 (S = 7).  Row blocks that reach further are
-// accumulated in segments of I8_KSEG k-steps (16384 rows: 1.6e9 at worst); the partial fp64 sums of the earlier
-// segments wait in a small per-CTA global buffer.
+// accumulated in segments of I8_KSEG k-steps (16384 rows: 1.6e9 at worst); the segments add up exactly in the
+// 64-bit integers of the epilogue.
 constexpr int I8_KSEG = 512;
 constexpr int I8_MAX_NPAD = 65536;
 constexpr size_t I8_PACE_BYTES = 4096;               // head of the scratch: one arrival counter per row block (<= 512)
