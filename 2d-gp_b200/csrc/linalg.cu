@@ -137,6 +137,18 @@ cudaError_t launch_dgemm(bool a_mn, bool b_mn, const GemmArgs& a, cudaStream_t s
 constexpr int LEAF_LD = TILE + 1;
 constexpr int LEAF_SMEM_BYTES = TILE * LEAF_LD * (int)sizeof(double);
 
+// Reciprocal of a positive pivot: hardware seed (rcp.approx.ftz.f64, ~20 bits) and two Newton steps (error 2^-40, then
+// below double rounding).  The reciprocal heads the dependent chain of every column step of the leaf; the IEEE division
+// the compiler emits for 1.0 / d is twice as long.  NaN stays NaN (a non-positive pivot has been turned into one).
+__device__ __forceinline__ double pivot_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int* info, int row0, int keep_L,
                   long bstride) {
@@ -193,7 +205,7 @@ potri_leaf_kernel(double* A, long lda, double* Z, long ldz, double* logdiag, int
             double d = cb[j];
             if (tid == 0) dsave[j] = d;
             if (!(d > 0.0)) d = nan("");
-            const double rd = 1.0 / d;
+            const double rd = pivot_rcp(d);
             // row multipliers from the lane that owns row j in this half-warp (unscaled Y[j,c])
             const int src = (lane & 16) | jr;
             double m[8], l[8];
