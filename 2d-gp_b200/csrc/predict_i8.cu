@@ -837,9 +837,12 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             const int w = warp == C::ISSUER0 ? 0 : 1;
             const unsigned ring_lo = i8_desc_lo(smem_u32(ring));
             const bool nomma = (p.dbg & 16) != 0;
-            for (long n = w;; n += C::MMA_WARPS) {
-                const int rs = (int)(n % C::STAGES);
-                I8_WAIT(full + (int)(n % C::NFULL), (unsigned)(n / C::NFULL) & 1u, 4, (unsigned)n);
+            // stage n = w, w + MMA_WARPS, ..: ring slot n % STAGES, full barrier n % NFULL in its phase n / NFULL, kept as
+            // small counters (64-bit divisions by constants in this loop are time the tensor pipe waits)
+            int rs = w % C::STAGES, fi = w % C::NFULL;
+            unsigned fph = 0;
+            for (unsigned n = (unsigned)w;; n += C::MMA_WARPS) {
+                I8_WAIT(full + fi, fph, 4, n);
                 const unsigned h = sh_hdr[rs];
                 if (h & H_EXIT) break;
                 const int a = (int)(h & 0xffu), b = (int)((h >> 8) & 0xffu);
@@ -874,6 +877,10 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
                 }
                 __syncwarp();
                 if (h & H_FINAL) break;
+                rs += C::MMA_WARPS;
+                if (rs >= C::STAGES) rs -= C::STAGES;
+                fi += C::MMA_WARPS;
+                if (fi >= C::NFULL) { fi -= C::NFULL; fph ^= 1u; }
             }
         }
     } else {
