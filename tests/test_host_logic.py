@@ -338,8 +338,9 @@ def test_param_fix_and_unfix_restore_the_constraint():
 def test_i8_issuer_protocol_model():
     """The barrier protocol of predict_i8_kernel (one producer, two MMA issuers in turn, epilogue; csrc/predict_i8.cu)
     in a discrete-event model with one-bit mbarrier parities, out-of-order copy completion and random scheduling:
-    no deadlock, no stale stage header, no product outside its accumulation segment, for both ring sizes; and the
-    model does show the aliasing that indexing the full barriers by slot alone would have on the odd ring."""
+    no deadlock, no stale stage header, no ring slot written over before its products have completed, no product
+    outside its accumulation segment, for both ring sizes; and the model does show the aliasing that indexing the full
+    barriers by slot alone would have on the odd ring."""
     import importlib.util
     import random
     spec = importlib.util.spec_from_file_location("i8_protocol_sim", os.path.join(os.path.dirname(__file__), "tools", "i8_protocol_sim.py"))
@@ -353,3 +354,7 @@ def test_i8_issuer_protocol_model():
             assert sim.run(seed, segs, stages=stages, weights=w) == "ok", (seed, segs, stages)
     broken = sum(sim.run(seed, [1, 2, 3, 7, 2, 3], stages=5, nfull=5) != "ok" for seed in range(150))
     assert broken > 0
+    # ... and the one a lane-parallel producer has without its emission window (a lane several ring turns ahead reads
+    # "free" off a barrier whose parity it cannot interpret)
+    assert all(sim.run(seed, [2, 3, 7, 12, 3, 2], stages=5, chunk=16, window=None) != "ok" for seed in range(20))
+    assert all(sim.run(seed, [2, 3, 7, 12, 3, 2], stages=5, chunk=16) == "ok" for seed in range(20))

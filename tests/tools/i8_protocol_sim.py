@@ -7,7 +7,11 @@ bring-up were found (or explained) with it and not on the device:
     wait can no longer tell the phases apart  ->  every segment has two stages (an empty second one if need be);
   * copies of different stages complete out of order; with an odd ring an issuer meets a slot at every other use
     only, and the parity test for "my use" also passes when the use in between has not landed yet  ->  the full
-    barriers are indexed n % (issuers x stages) so that each belongs to one issuer (nfull argument).
+    barriers are indexed n % (issuers x stages) so that each belongs to one issuer (nfull argument);
+  * the producer emits the stages of a chunk lane-parallel, each lane as soon as the ring slot of its stage is free; a
+    lane many stages ahead would read "free" off the slot's barrier for the same reason (one parity bit)  ->  a lane may
+    look at its barrier only when the stage one ring earlier has been emitted: a window of `stages` stages past the
+    emitted prefix (window argument; None = any lane may look, which the model shows to be wrong).
 run(seed, segments, stages, nfull) returns "ok" or a description of the violation / deadlock."""
 import random
 
@@ -48,7 +52,7 @@ def stage_list(segments):
     return out
 
 
-def run(seed, segments, stages=5, nfull=None, weights=None, min_two=True):
+def run(seed, segments, stages=5, nfull=None, weights=None, min_two=True, chunk=8, window="stages"):
     rnd = random.Random(seed)
     nfull = nfull or 2 * stages
     full = [MBar(1, "full%d" % i) for i in range(nfull)]
@@ -59,15 +63,27 @@ def run(seed, segments, stages=5, nfull=None, weights=None, min_two=True):
     pipe, landing = [], []                      # tensor pipe (in order); copies in flight (any order)
     acc = {"seg": -1, "drained": True}
 
+    in_ring = {}                                 # slot -> stage whose data the slot holds, until its products have completed
+
     def producer():
-        for n, (c, f) in enumerate(sl):
-            rs, rph = n % stages, (n // stages) & 1
-            if n >= stages:
-                while not empty[rs].test(rph ^ 1):
-                    yield "producer: empty of stage %d" % n
-            hdr[rs] = (c, f, n)
-            landing.append(n % nfull)            # the copy lands (completes the full barrier) some time later
-            yield None
+        # chunks of `chunk` stages are emitted lane-parallel: in every round each lane that is inside the window and
+        # finds its slot's barrier in the "previous use is over" state emits its stage
+        win = stages if window == "stages" else (10 ** 9 if window is None else window)
+        for base in range(0, len(sl), chunk):
+            todo = list(range(base, min(base + chunk, len(sl))))
+            while todo:
+                prefix = todo[0]                 # every stage below has been emitted
+                for n in list(todo):
+                    if n >= prefix + win or rnd.random() < 0.3:
+                        continue
+                    rs = n % stages
+                    if n < stages or empty[rs].test(((n // stages) & 1) ^ 1):
+                        assert rs not in in_ring, ("stage %d written over stage %d, which is still in the ring" % (n, in_ring[rs]))
+                        in_ring[rs] = n
+                        hdr[rs] = sl[n] + (n,)
+                        landing.append(n % nfull)    # the copy lands (completes the full barrier) some time later
+                        todo.remove(n)
+                yield "producer: ring slots of stages %d.." % todo[0] if todo else None
 
     def copies():
         while True:
@@ -114,6 +130,8 @@ def run(seed, segments, stages=5, nfull=None, weights=None, min_two=True):
                         seen.add(it[1])
                     elif it[1] not in seen:
                         pipe.pop(i)
+                        if it[2][0] == "empty":
+                            in_ring.pop(it[2][1], None)
                         (empty[it[2][1]] if it[2][0] == "empty" else acc_full).arrive()
                         fired = True
                         break
