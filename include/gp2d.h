@@ -258,9 +258,11 @@ int gp2d_hsum_lml_grad(const double* X, int N, int ldx, const double* y, int Q, 
  * to the calls the setting thread makes afterwards and never couple two callers.
  * GP2D_OPT_PREDICT_I8 -- the predictive pass of the Helmholtz families (gp2d_predict, gp2d_st_predict,
  *   gp2d_fit_predict_host) has two kernels: the fp64 tensor-pipe kernel and an int8-sliced tcgen05 kernel
- *   (3-4x faster; exact integer products of base-256 digit slices, deterministic; agrees with the fp64 kernel
- *   to ~2e-10 relative on the variance with 6 slices, ~1e-12 with 7, at the prior-to-noise ratio 4 of the
- *   reference configurations).  0 (default): gp2d_fit picks the slice count from m = k** / (noise + jitter) *
+ *   (5x faster at the reference configurations; exact integer products of base-256 digit slices, deterministic;
+ *   digit slices that are identically zero -- distant points -- are skipped, which is why the fits keep the
+ *   observations in a spatial order internally (invisible at this boundary: alpha_out is in the caller's order);
+ *   agrees with the fp64 kernel to ~2e-10 relative on the variance with 6 slices, ~1e-12 with 7, at the
+ *   prior-to-noise ratio 4 of the reference configurations).  0 (default): gp2d_fit picks the slice count from m = k** / (noise + jitter) *
  *   sqrt(n / 4000) -- 6 up to m = 20, 7 up to m = 2000, the fp64 kernel beyond, in the robust (ill-conditioned)
  *   mode and for N > 32768; 1: fp64 kernel only; 6 / 7: that slice count whenever N <= 32768.
  *   The choice is made by gp2d_fit (it prepares the slices) and honoured by the predict calls on that workspace;
