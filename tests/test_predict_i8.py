@@ -200,6 +200,41 @@ def test_fit_orders_the_observations_in_space():
     np.testing.assert_allclose(a1, f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
 
 
+def test_i8_concurrent_streams_and_pacing():
+    """Three host threads, each fitting and predicting on its own stream at a size where the row-block pacing is on
+    (the six slices of Z exceed 64 MB): the kernels queue for the SMs (one CTA takes a whole SM and all of its TMEM),
+    CTAs of a launch are not co-resident from the start -- the pacing must give up, not hang -- and every thread gets
+    the bits of the sequential run."""
+    import threading
+    N = 2600
+    X, y = synthetic.drifter_snapshot(N, config_id=3)
+    Xs = synthetic.prediction_grid(X, 110, 100)
+    gp.set_predict_i8(0)
+    m0 = gp.HelmholtzGP(X, y, *THETA, NOISE)
+    m0.fit()
+    assert _gate(m0) == 6
+    r0 = m0.predict(Xs)
+    torch.cuda.synchronize()
+    out = {}
+
+    def work(k):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            m = gp.HelmholtzGP(X, y, *THETA, NOISE)
+            m.fit()
+            for _ in range(2):
+                mean, var = m.predict(Xs)
+            s.synchronize()
+            out[k] = (mean.clone(), var.clone())
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    [t.start() for t in ths]
+    [t.join(timeout=100) for t in ths]
+    assert len(out) == 3
+    for k in out:
+        assert torch.equal(out[k][0], r0[0]) and torch.equal(out[k][1], r0[1])
+
+
 def test_i8_host_entry_point_matches_device_path():
     """gp2d_fit_predict_host (numpy in / out) runs the same kernels as fit + predict on device tensors."""
     X, y = synthetic.drifter_snapshot(500, config_id=2, seed_offset=5)
