@@ -128,7 +128,7 @@ constexpr unsigned H_EXIT = 1u << 27;         // no work: the issuer that did no
 
 // Work counters of the launches so far (statistics for bench.py, read and cleared by gp2d_dbg_i8_counters; one atomic
 // per CTA and launch): slice products issued (MMAs), stages issued, k-steps visited (= stages of the dense schedule).
-__device__ unsigned long long g_i8_count[6];         // + SM clocks from the first to the last stage, summed over the CTAs; CTAs
+__device__ unsigned long long g_i8_count[8];         // [6]: clocks the generators spent building panels (first generator thread), summed over CTAs         // + SM clocks from the first to the last stage, summed over the CTAs; CTAs
 
 // bulk copy with an L2 eviction priority: Zq tiles are re-read by every CTA (keep), panel tiles are read once (stream)
 __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
@@ -180,9 +180,10 @@ struct I8Cfg {
     static constexpr int NBARS = NFULL + STAGES + 2 + 4 + 2 + 8;   // full, empty, acc_full, (unused), panel_full[2], panel_empty[2], first_done, pad, acc_empty[8]
     // doubles after the barriers: observation stage, mean partials [GSLOTS][NG][2], column sums [4][NC], parameters,
     // digit ORs of the generators [2][GSLOTS], stage headers [STAGES] (32-bit)
-    static constexpr int TAIL_DOUBLES = 5 * OBS_BATCH + GSLOTS * NG * 2 + 4 * NC + 64 + 16 + 8;
+    static constexpr int TAIL_DOUBLES = 6 * OBS_BATCH + GSLOTS * NG * 2 + 4 * NC + 64 + 16 + 8 + 64;      // ... and a copy of the exp table
     static_assert(STAGES <= 16 && GSLOTS <= 8, "stage headers, digit ORs");
-    static constexpr int SMEM_BYTES = RING_BYTES + NBARS * 8 + 16 + TAIL_DOUBLES * 8;
+    static constexpr int BARS_BYTES = (NBARS * 8 + 16 + 15) / 16 * 16;     // barriers, TMEM slot; the observation stage behind it is read 16 bytes at a time
+    static constexpr int SMEM_BYTES = RING_BYTES + BARS_BYTES + TAIL_DOUBLES * 8;
     static constexpr int TMEM_COLS = 512;
     static_assert(S * NC <= TMEM_COLS, "S accumulators of NC columns must fit TMEM");
     static_assert(NC % 16 == 0, "tcgen05.mma M = 128 needs N % 16 == 0");
@@ -338,14 +339,39 @@ cudaError_t i8_set_gate(int* gate, int s, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------
 // predict side
 // ---------------------------------------------------------------------------------------------------
+// exp(x), x <= 0, without a table: the generators run beside a tensor core that keeps the shared-memory / L1 data pipe
+// 70 % busy, where every load of theirs queues (they take four times as long as on an idle SM and are then what the
+// column tile waits for: tools/i8_knobs.py, "generators busy"); fp64 arithmetic is what the SM has to spare.
+// n = rint(4 x / ln 2), r = x - n ln2 / 4 in two pieces (|r| <= 0.0867), Taylor to r^9 (6e-18), 2^((n & 3) / 4) from
+// three constants, 2^(n >> 2) into the exponent: 1 ulp, like helmholtz.cuh's table version.
+__device__ __forceinline__ double exp_neg_sel(double x) {
+    x = fmax(x, -708.0);
+    const double nd = rint(x * 0x1.71547652b82fep+2);
+    const int ni = (int)nd;
+    double r = fma(-nd, 0x1.62e42fefa0000p-3, x);
+    r = fma(-nd, 0x1.cf79abc9e3b3ap-42, r);
+    const double r2 = r * r;
+    // Estrin on 1 + r + r^2/2 + ... + r^9/9!
+    const double c01 = 1.0 + r, c23 = fma(r, 1.0 / 6.0, 0.5), c45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double c67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0), c89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double r4 = r2 * r2;
+    const double lo = fma(r2, c23, c01), mid = fma(r2, c67, c45);
+    const double pol = fma(r4, fma(r4, c89, mid), lo);
+    const int j = ni & 3;
+    const double c = j == 0 ? 1.0 : j == 1 ? 0x1.306fe0a31b715p+0 : j == 2 ? 0x1.6a09e667f3bcdp+0 : 0x1.ae89f995ad3adp+0;
+    return pol * __longlong_as_double(__double_as_longlong(c) + ((long long)(ni >> 2) << 52));
+}
+
 // Generator: thread (g, slot) owns grid point gp0 + g and the k-steps slot, slot + 8, ... (16 observations =
 // 32 rows of K* each).  Per k-step it forms 16 2x2 blocks, quantises the 48 distinct values and stores, for
 // each digit and each of its two columns, the two 16-byte row chunks of the slice image.
 template <int S, bool SAME_LEN, bool HAS_T>
 __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const HelmPoint& gpt, double wg, int nvalid, int o0,
                                                   const double* __restrict__ stage, double kscale, uint8_t* __restrict__ dst,
-                                                  int btile, double& m0, double& m1, unsigned long long& yor) {
+                                                  int btile, double& m0, double& m1, unsigned long long& yor,
+                                                  const double* __restrict__ tab) {
     constexpr long long BIAS = i8_digit_bias(S);
+    const double wdk = hp.w_df * wg * kscale, wck = hp.w_cf * wg * kscale;      // wg is 0 or 1, kscale a power of two: exact
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {                 // 8 observations = 16 consecutive k
         unsigned wa[S][4], wb[S][4];               // column 2g / 2g+1, digit p, word w
@@ -355,27 +381,34 @@ __device__ __forceinline__ void i8_generate_kstep(const HelmParams& hp, const He
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int ol = h * 8 + w * 2 + e;
-                const double* sp = stage + ol * 5;
-                const double d1 = sp[0] - gpt.a, d2 = sp[1] - gpt.b;
+                // (a, b), (t, -), (alpha_u, alpha_v): three 16-byte loads per observation
+                const double2 s01 = *reinterpret_cast<const double2*>(stage + ol * 6);
+                const double2 s23 = *reinterpret_cast<const double2*>(stage + ol * 6 + 2);
+                const double2 s45 = *reinterpret_cast<const double2*>(stage + ol * 6 + 4);
+                const double d1 = s01.x - gpt.a, d2 = s01.y - gpt.b;
                 const double a = d1 * d1, b = d2 * d2, c = d1 * d2, r2 = a + b;
-                const double E = exp_neg(-0.5 * hp.s_df * r2);
-                const double F = SAME_LEN ? E : exp_neg(-0.5 * hp.s_cf * r2);
-                double wv = (o0 + ol) < nvalid ? wg : 0.0;
+                const double E = exp_neg(-0.5 * hp.s_df * r2, tab);
+                const double F = SAME_LEN ? E : exp_neg(-0.5 * hp.s_cf * r2, tab);
+                // The quantisation scale (a power of two) and the validity of the pair ride on the two kernel weights:
+                // fp64 instructions are what this kernel cannot afford (they only issue in the gaps the tensor pipe
+                // leaves and push its work back by more than their own time: tools/i8_knobs.py), and the block below
+                // then yields k kscale directly -- the same bits as scaling afterwards, zero for a padded pair.
+                double wd = (o0 + ol) < nvalid ? wdk : 0.0, wc = (o0 + ol) < nvalid ? wck : 0.0;
                 if (HAS_T) {
-                    const double dt = sp[2] - gpt.t;
-                    wv *= hp.tvar * exp_neg(-hp.thalf * dt * dt);
+                    const double dt = s23.x - gpt.t;
+                    const double tf = hp.tvar * exp_neg(-hp.thalf * dt * dt, tab);
+                    wd *= tf; wc *= tf;
                 }
-                const double ee = hp.w_df * E, ff = hp.w_cf * F;
+                const double ee = wd * E, ff = wc * F;
                 const double es = ee * hp.s_df, fs = ff * hp.s_cf;
-                double k11 = fma(-b, es, ee) + fma(-a, fs, ff);
-                double k22 = fma(-a, es, ee) + fma(-b, fs, ff);
-                double k12 = c * (es - fs);
-                k11 *= wv; k12 *= wv; k22 *= wv;
-                m0 = fma(k11, sp[3], fma(k12, sp[4], m0));
-                m1 = fma(k12, sp[3], fma(k22, sp[4], m1));
-                qa[e] = __double2ll_rn(k11 * kscale) + BIAS;
-                qb[e] = __double2ll_rn(k12 * kscale) + BIAS;
-                qc[e] = __double2ll_rn(k22 * kscale) + BIAS;
+                const double k11 = fma(-b, es, ee) + fma(-a, fs, ff);
+                const double k22 = fma(-a, es, ee) + fma(-b, fs, ff);
+                const double k12 = c * (es - fs);
+                m0 = fma(k11, s45.x, fma(k12, s45.y, m0));           // scaled by kscale: undone once per grid point
+                m1 = fma(k12, s45.x, fma(k22, s45.y, m1));
+                qa[e] = __double2ll_rn(k11) + BIAS;
+                qb[e] = __double2ll_rn(k12) + BIAS;
+                qc[e] = __double2ll_rn(k22) + BIAS;
                 yor |= (unsigned long long)((qa[e] ^ BIAS) | (qb[e] ^ BIAS) | (qc[e] ^ BIAS));
             }
             // rows k = 2o, 2o+1, 2o+2, 2o+3: column 2g holds (k11, k12) per observation, column 2g+1 (k12, k22)
@@ -409,8 +442,8 @@ __device__ __forceinline__ void i8_flush_lead(unsigned long long* sh_or, uint8_t
 
 template <int S, int NC, bool SAME_LEN, bool HAS_T>
 __device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const HelmParams& hp, uint8_t* __restrict__ panel,
-                                                 double* __restrict__ stage, unsigned long long* sh_or, int gp0, int gtid,
-                                                 double& mu0, double& mu1) {
+                                                 double* __restrict__ stage, unsigned long long* sh_or, const double* __restrict__ tab,
+                                                 int gp0, int gtid, double& mu0, double& mu1) {
     using C = I8Cfg<S, NC>;
     const int g = gtid % C::NG, slot = gtid / C::NG;
     const int gj = gp0 + g;
@@ -431,27 +464,29 @@ __device__ __forceinline__ void i8_generate_item(const PredictI8Args& p, const H
             const int o = ob + gtid;
             const bool ov = o < p.N;
             const HelmPoint q = helm_point(hp, p.X, ov ? o : 0);
-            stage[gtid * 5 + 0] = q.a;
-            stage[gtid * 5 + 1] = q.b;
-            stage[gtid * 5 + 2] = q.t;
-            stage[gtid * 5 + 3] = ov ? __ldg(p.alpha + 2 * o) : 0.0;
-            stage[gtid * 5 + 4] = ov ? __ldg(p.alpha + 2 * o + 1) : 0.0;
+            stage[gtid * 6 + 0] = q.a;
+            stage[gtid * 6 + 1] = q.b;
+            stage[gtid * 6 + 2] = q.t;
+            stage[gtid * 6 + 3] = 0.0;
+            stage[gtid * 6 + 4] = ov ? __ldg(p.alpha + 2 * o) : 0.0;
+            stage[gtid * 6 + 5] = ov ? __ldg(p.alpha + 2 * o + 1) : 0.0;
         }
         named_barrier(2, C::GT);
         const int o0 = ob + slot * 16;
         if (o0 < nobs_pad) {
             const int ks = o0 >> 4;
             unsigned long long yor = 0ull;
-            i8_generate_kstep<S, SAME_LEN, HAS_T>(hp, gpt, wg, p.N, o0, stage + slot * 16 * 5, p.kscale,
-                                                  panel + (size_t)ks * (S * C::BTILE) + rowoff, C::BTILE, m0, m1, yor);
+            i8_generate_kstep<S, SAME_LEN, HAS_T>(hp, gpt, wg, p.N, o0, stage + slot * 16 * 6, p.kscale,
+                                                  panel + (size_t)ks * (S * C::BTILE) + rowoff, C::BTILE, m0, m1, yor, tab);
             if (yor) atomicOr(sh_or + (batch & 1) * I8_GSLOTS + slot, yor);
         }
     }
     named_barrier(2, C::GT);
     if (g == 0) i8_flush_lead<S>(sh_or, plead, batch - 1, slot, nks_all);
     __syncwarp();
-    mu0 = m0;
-    mu1 = m1;
+    const double unscale = 1.0 / p.kscale;        // a power of two
+    mu0 = m0 * unscale;
+    mu1 = m1 * unscale;
 }
 
 // The MMAs of one k-step whose A tile has A and whose B tile has B leading all-zero slices: the slice pairs (i, j),
@@ -523,12 +558,14 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     unsigned long long* panel_empty = acc_full + 4;
     unsigned long long* first_done = acc_full + 6;
     unsigned* tslot = reinterpret_cast<unsigned*>(bars + C::NBARS);
-    double* sh_stage = reinterpret_cast<double*>(smem_raw + C::RING_BYTES + C::NBARS * 8 + 16);
-    double* sh_mu = sh_stage + 5 * C::OBS_BATCH;          // [GSLOTS][NG][2]
+    double* sh_stage = reinterpret_cast<double*>(smem_raw + C::RING_BYTES + C::BARS_BYTES);
+    double* sh_mu = sh_stage + 6 * C::OBS_BATCH;          // [GSLOTS][NG][2]
     double* sh_red = sh_mu + C::GSLOTS * C::NG * 2;       // [4][NC]
     double* sh_par = sh_red + 4 * NC;
     unsigned long long* sh_or = reinterpret_cast<unsigned long long*>(sh_par + 64);      // [2][8]
     volatile unsigned* sh_hdr = reinterpret_cast<volatile unsigned*>(sh_or + 16);          // [STAGES]
+    double* sh_tab = reinterpret_cast<double*>(sh_or + 16) + 8;                             // exp_neg's table: the L1 left beside
+                                                                                           // 208 KB of shared memory does not keep it
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = p.npad / TILE;
@@ -545,6 +582,7 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
     }
     if (tid < (int)(sizeof(HelmParams) / sizeof(double))) sh_par[tid] = reinterpret_cast<const double*>(&p.hp)[tid];
     if (tid >= 64 && tid < 80) sh_or[tid - 64] = 0ull;
+    if (tid >= 128 && tid < 192) sh_tab[tid - 128] = EXP2_TAB[tid - 128];
     if (warp == C::ISSUER0) tmem_alloc(tslot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -895,15 +933,17 @@ __global__ void __launch_bounds__(I8Cfg<S, NC>::THREADS, 1) predict_i8_kernel(co
             uint8_t* panel = panels + (size_t)b * p.panel_bytes;
             double mu0 = 0.0, mu1 = 0.0;
             const int gp0 = item * C::NG;
+            const long long gclk0 = clock64();
             if (p.dbg & 4) {
                 named_barrier(2, C::GT);
             } else if (hp.has_t) {
-                if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
-                else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
+                if (hp.same_len) i8_generate_item<S, NC, true, true>(p, hp, panel, sh_stage, sh_or, sh_tab, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, true>(p, hp, panel, sh_stage, sh_or, sh_tab, gp0, gtid, mu0, mu1);
             } else {
-                if (hp.same_len) i8_generate_item<S, NC, true, false>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
-                else i8_generate_item<S, NC, false, false>(p, hp, panel, sh_stage, sh_or, gp0, gtid, mu0, mu1);
+                if (hp.same_len) i8_generate_item<S, NC, true, false>(p, hp, panel, sh_stage, sh_or, sh_tab, gp0, gtid, mu0, mu1);
+                else i8_generate_item<S, NC, false, false>(p, hp, panel, sh_stage, sh_or, sh_tab, gp0, gtid, mu0, mu1);
             }
+            if (gtid == 0) atomicAdd(&g_i8_count[6], (unsigned long long)(clock64() - gclk0));
             fence_proxy_async();                  // the panel is read back by bulk (async-proxy) copies
             const int g = gtid % C::NG, slot = gtid / C::NG;
             sh_mu[(slot * C::NG + g) * 2 + 0] = mu0;
@@ -1009,15 +1049,15 @@ extern "C" int gp2d_dbg_i8_watchdog(unsigned long long* out36) {      // [4] fir
 extern "C" int gp2d_dbg_i8_counters(unsigned long long* out4) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(out4, g_i8_count, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
-    const unsigned long long z[6] = {0, 0, 0, 0, 0, 0};
+    const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     return cudaMemcpyToSymbol(g_i8_count, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 // the same and, in out6[4], out6[5]: SM clocks the producers spent (summed over the CTAs of all launches), CTAs -- times
 // in clocks do not move with the power cap the way milliseconds do
-extern "C" int gp2d_dbg_i8_counters6(unsigned long long* out6) {
+extern "C" int gp2d_dbg_i8_counters6(unsigned long long* out6) {      // out6[6]: clocks the generators were busy (one thread per CTA)
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(out6, g_i8_count, 6 * sizeof(unsigned long long)) != cudaSuccess) return -1;
-    const unsigned long long z[6] = {0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out6, g_i8_count, 7 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     return cudaMemcpyToSymbol(g_i8_count, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 

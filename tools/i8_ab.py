@@ -16,7 +16,7 @@ lib.gp2d_dbg_set_i8.restype = C.c_int
 lib.gp2d_dbg_set_i8.argtypes = [C.c_int]
 lib.gp2d_dbg_i8_counters6.restype = C.c_int
 lib.gp2d_dbg_i8_counters6.argtypes = [C.POINTER(C.c_ulonglong)]
-cnt = (C.c_ulonglong * 6)()
+cnt = (C.c_ulonglong * 8)()
 A, B = int(sys.argv[1]), int(sys.argv[2])
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
 side = int(sys.argv[4]) if len(sys.argv) > 4 else 320
