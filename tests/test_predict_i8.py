@@ -200,6 +200,35 @@ def test_fit_orders_the_observations_in_space():
     np.testing.assert_allclose(a1, f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
 
 
+@pytest.mark.parametrize("case", ["duplicates", "collinear256", "thin257", "tiny"])
+def test_spatial_order_degenerate_inputs(case):
+    """The Z-order sort of the fit (csrc/order.cu) on inputs with no extent in one or both directions, repeated points,
+    and N at the threshold where it switches on: weights in the caller's order, mean and variance against the oracle."""
+    rng = np.random.default_rng(1)
+    if case == "duplicates":
+        X = rng.uniform(0, 5, (300, 2))
+        X[50:120] = X[7]
+    elif case == "collinear256":
+        X = np.stack([np.linspace(0, 9, 256), np.full(256, 3.0)], 1)
+    elif case == "thin257":
+        X = rng.uniform(0, 5, (257, 2))
+        X[:, 1] = X[:, 0] * 1e-12
+    else:
+        X = rng.uniform(0, 1e-9, (400, 2))
+    N = X.shape[0]
+    y = rng.normal(size=2 * N) * 0.3
+    Xs = rng.uniform(-1, 10, (500, 2))
+    theta = (1.3, 2.1, 0.4)
+    m = gp.HelmholtzGP(X, y, *theta, NOISE)
+    a = m.alpha().cpu().numpy()
+    mean, var = m.predict(Xs)
+    f = orc.fit(X, y, *theta, NOISE)
+    mo, vo = orc.predict(X, f, *theta, Xs)
+    np.testing.assert_allclose(a, f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
+    np.testing.assert_allclose(mean.cpu().numpy(), mo, rtol=1e-8, atol=1e-9 * np.abs(mo).max())
+    np.testing.assert_allclose(var.cpu().numpy(), vo, rtol=1e-8, atol=1e-12)
+
+
 def test_i8_concurrent_streams_and_pacing():
     """Three host threads, each fitting and predicting on its own stream at a size where the row-block pacing is on
     (the six slices of Z exceed 64 MB): the kernels queue for the SMs (one CTA takes a whole SM and all of its TMEM),
