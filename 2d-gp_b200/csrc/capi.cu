@@ -1285,6 +1285,18 @@ int gp2d_dbg_set_potri_overlap(int on) { set_potri_overlap(on != 0); return on; 
 int gp2d_dbg_set_predict_split(int s) { set_predict_split(s); return s; }
 int gp2d_dbg_set_i8(int v) { set_i8_debug(v); return v; }
 
+// the permutation the last fit in this workspace (Helmholtz / space-time families) applied to its observations:
+// perm_out[i] = caller's index of internal observation i (device pointer, N ints); returns 0 when the fit keeps the
+// caller's order (perm_out untouched), N otherwise
+int gp2d_dbg_fit_order(const void* fit_ws, int N, int ldx, int* perm_out, void* stream) {
+    if (!fit_ws || !perm_out || N <= 0 || (ldx != 2 && ldx != 3)) return -1;
+    const FitLayout L = fit_layout(N, ldx);
+    if (!L.order_n) return 0;
+    cudaError_t e = cudaMemcpyAsync(perm_out, at<int>(fit_ws, L.off_perm), (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream);
+    return e == cudaSuccess ? N : cuda_rc(e);
+}
+
 int gp2d_dbg_gemm(int a_mn, int b_mn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, double alpha, double beta, int lower_out, int krule,
                   void* stream) {

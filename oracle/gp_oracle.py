@@ -527,3 +527,27 @@ def simlaser_inputs(tr, ts=0, lat0=28.69, lon0=-88.28, dx=0.5):
     Xg, Yg = np.meshgrid(x, yv)
     Xs = np.stack([Xg.reshape(-1), Yg.reshape(-1)], axis=1)
     return np.stack([xo, yo], axis=1), np.concatenate([uo, vo]), Xs
+
+
+# --------------------------------------------------------------------------------------
+# spatial order of the observations inside a fit (no counterpart upstream: the reference takes the
+# drifters in file order, GP_laser.py:62-110; a GP does not depend on the order)
+# --------------------------------------------------------------------------------------
+def morton_order(P):
+    """Permutation along a Z-order curve: 8 bits per axis on a square raster of the bounding box (cell =
+    extent / 255.999 of the longer side), x bits even, y bits odd, ties in the given order.  What
+    2d-gp_b200/csrc/order.cu computes on the device; internal observation i is the caller's perm[i]."""
+    P = np.asarray(P, dtype=np.float64)
+    lo = P.min(axis=0)
+    ext = max(P[:, 0].max() - lo[0], P[:, 1].max() - lo[1])
+    s = 255.999 / ext if (ext > 0 and np.isfinite(ext)) else 0.0
+    q = np.minimum(np.maximum((P - lo) * s, 0.0), 255.0).astype(np.uint32)
+
+    def spread(v):
+        v = (v | (v << 4)) & 0x0F0F
+        v = (v | (v << 2)) & 0x3333
+        v = (v | (v << 1)) & 0x5555
+        return v
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << 1)
+    return np.argsort(key, kind="stable")
+

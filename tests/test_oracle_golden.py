@@ -281,3 +281,22 @@ def test_hsum_oracle_gradient_and_validity():
         assert abs(fd - g0[4 * q + j]) <= 1e-6 * max(1.0, abs(fd))
     fd = (orc.hsum_fit(X3, y, types, P, 0.1 + 1e-6)["lml"] - orc.hsum_fit(X3, y, types, P, 0.1 - 1e-6)["lml"]) / 2e-6
     assert abs(fd - g0[-1]) <= 1e-6 * max(1.0, abs(fd))
+
+
+def test_morton_order_is_a_locality_preserving_permutation():
+    """oracle.morton_order (the restatement of csrc/order.cu): a permutation, stable on ties, invariant under
+    translation and uniform scaling, and consecutive points are close: groups of 16 consecutive points of a jittered
+    lattice span a few lattice cells, not the domain."""
+    rng = np.random.default_rng(2)
+    gx, gy = np.meshgrid(np.arange(40) * 0.5, np.arange(40) * 0.5)
+    P = np.stack([gx.ravel(), gy.ravel()], 1) + rng.uniform(-0.2, 0.2, (1600, 2))
+    P = P[rng.permutation(1600)]
+    perm = orc.morton_order(P)
+    assert sorted(perm.tolist()) == list(range(1600))
+    np.testing.assert_array_equal(orc.morton_order(3.0 * P + 11.0), perm)
+    Q = P[perm]
+    spans = [np.ptp(Q[i:i + 16], axis=0).max() for i in range(0, 1600, 16)]
+    assert np.median(spans) < 3.0 and np.ptp(P, axis=0).max() > 19.0
+    D = np.array([[0.0, 0.0], [1.0, 1.0], [0.0, 0.0], [1.0, 1.0]])
+    np.testing.assert_array_equal(orc.morton_order(D), [0, 2, 1, 3])
+

@@ -200,6 +200,29 @@ def test_fit_orders_the_observations_in_space():
     np.testing.assert_allclose(a1, f["alpha"], rtol=1e-8, atol=1e-9 * np.abs(f["alpha"]).max())
 
 
+def test_spatial_order_is_the_oracles_z_order():
+    """The permutation the fit applies (read back through a bring-up export) is oracle.morton_order's, ties included."""
+    import ctypes as C
+    from gp2d_b200._lib import lib
+    lib.gp2d_dbg_fit_order.restype = C.c_int
+    lib.gp2d_dbg_fit_order.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4)
+    for N in (255, 256, 1000, 3001):
+        X = rng.uniform(-3, 7, (N, 2))
+        X[N // 3] = X[N // 2]                          # a tie
+        y = rng.normal(size=2 * N)
+        m = gp.HelmholtzGP(X, y, *THETA, NOISE)
+        m.fit()
+        perm = torch.full((N,), -1, dtype=torch.int32, device="cuda")
+        rc = lib.gp2d_dbg_fit_order(m.ws.data_ptr(), N, 2, perm.data_ptr(), None)
+        torch.cuda.synchronize()
+        if N < 256:
+            assert rc == 0                              # below the threshold the caller's order is kept
+            continue
+        assert rc == N
+        np.testing.assert_array_equal(perm.cpu().numpy(), orc.morton_order(X))
+
+
 @pytest.mark.parametrize("case", ["duplicates", "collinear256", "thin257", "tiny"])
 def test_spatial_order_degenerate_inputs(case):
     """The Z-order sort of the fit (csrc/order.cu) on inputs with no extent in one or both directions, repeated points,
